@@ -1,0 +1,137 @@
+/*
+ * shotfpfh_b200 — C ABI of the B200 (sm_100a) hot path of aubin-tchoi/shot-fpfh:
+ * fixed-radius neighbour search -> SHOT / FPFH descriptors -> descriptor nearest-neighbour matching.
+ *
+ * The reference is pure Python and has no FFI of its own; the entry points below are what a
+ * binding for its hot-path functions has to call. Each one names the reference code it replaces (paths relative
+ * to the reference repository). INTEGRATION.md shows the ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, an opaque grid handle; no C++ or torch types, no exceptions across the boundary;
+ *   - every function returns SF_OK (0) or an SF_ERR_* code; sf_last_error() gives the text (thread-local);
+ *   - pointers named *_dev are DEVICE pointers on the current CUDA device, `stream` is a cudaStream_t passed as
+ *     void* (NULL = default stream); work is enqueued on that stream and the call returns without
+ *     synchronising, except where a host result is produced (documented per function);
+ *   - coordinates, normals, radii are float64 exactly as the reference's NumPy arrays (row-major (n,3));
+ *   - neighbour lists are CSR: int64 offsets[q + 1], int32 entries;
+ *   - "cell-sorted position" = index into the grid's internal cell-ordered copy of the cloud (better locality
+ *     for the descriptor kernels); sf_grid_permutation maps it from/to original point indices.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SHOTFPFH_B200_H
+#define SHOTFPFH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SF_ABI_VERSION 1
+
+#define SF_OK 0
+#define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
+#define SF_ERR_ARG 2      /* invalid argument */
+#define SF_ERR_CAPACITY 3 /* a fixed capacity (descriptor length, k, shared memory) was exceeded */
+
+#define SF_SHOT_LEN 352 /* 11 cosine x 8 azimuth x 2 elevation x 2 radial bins (shot.py:197) */
+
+typedef struct sf_grid sf_grid;
+
+const char* sf_last_error(void);
+int sf_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * G — spatial index.  Replaces `KDTree(points)` (sklearn; shot_parallelization.py:167, fpfh.py:26, shot.py:340).
+ * ---------------------------------------------------------------------------------------------------------- */
+int sf_grid_create(sf_grid** out);
+int sf_grid_destroy(sf_grid* grid);
+
+/* Builds (or rebuilds, reusing its buffers) the uniform grid over `n` points for searches of radius <= `radius`.
+ * xyz_dev, normals_dev: float64 (n,3); normals_dev may be NULL when only neighbour search is needed.
+ * Synchronises `stream` once (the bounding box is needed on the host to size the cell table). */
+int sf_grid_build(sf_grid* grid, const double* xyz_dev, const double* normals_dev, int64_t n, double radius,
+                  void* stream);
+int sf_grid_info(const sf_grid* grid, int64_t* n, int64_t* ncells, double* cell_edge, int32_t* dims3);
+/* Copies perm[n] (cell-sorted position -> original index) and/or its inverse into caller buffers (NULL = skip). */
+int sf_grid_permutation(const sf_grid* grid, int32_t* perm_out_dev, int32_t* inv_perm_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * G — fixed-radius search.  Replaces `KDTree.query_radius(X, r[, return_distance=True])`
+ * (shot_parallelization.py:167-169, fpfh.py:28-30). Predicate: ((dx*dx + dy*dy) + dz*dz) <= r*r in float64,
+ * inclusive, the query point itself included when it belongs to the cloud — sklearn's, bit for bit.
+ * queries_dev == NULL means "the cloud's own points in cell-sorted order" (nq is then the cloud size).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Pass 1: offsets_dev[0..nq] (exclusive prefix of the neighbour counts). When total_host != NULL the total is
+ * copied to the host and `stream` is synchronised. */
+int sf_radius_count(sf_grid* grid, const double* queries_dev, int64_t nq, double radius, int64_t* offsets_dev,
+                    int64_t* total_host, void* stream);
+/* Pass 2: any of the three outputs may be NULL. nbr_sorted_dev: cell-sorted positions (what the descriptor
+ * kernels consume); nbr_index_dev: original point indices (what query_radius returns, in grid-walk order);
+ * dist_dev: float64 sqrt of the reduced distance (what return_distance=True returns). */
+int sf_radius_fill(sf_grid* grid, const double* queries_dev, int64_t nq, double radius, const int64_t* offsets_dev,
+                   int32_t* nbr_sorted_dev, int32_t* nbr_index_dev, double* dist_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * S — SHOT.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Local reference frames. Replaces `get_local_rf` (shot.py:16-48) fanned out by
+ * `ShotMultiprocessor.compute_local_rf` (shot_parallelization.py:46-84). lrf_dev: float64 (nq,3,3), columns
+ * [x y z]; identity for an empty neighbourhood. */
+int sf_shot_lrf(sf_grid* grid, const double* queries_dev, int64_t nq, double radius, const int64_t* offsets_dev,
+                const int32_t* nbr_sorted_dev, double* lrf_dev, void* stream);
+/* Descriptors. Replaces `compute_single_shot_descriptor` (shot.py:175-306) fanned out by
+ * `ShotMultiprocessor.compute_descriptor` (shot_parallelization.py:86-133), including the reference's
+ * last-writer-wins binning. out_dev: (nq,352), float64 when out_is_f64 else float32. */
+int sf_shot_descriptor(sf_grid* grid, const double* queries_dev, int64_t nq, double radius,
+                       const int64_t* offsets_dev, const int32_t* nbr_sorted_dev, const double* lrf_dev,
+                       int32_t min_neighborhood_size, int32_t normalize, void* out_dev, int32_t out_is_f64,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * P — FPFH.  Replaces `compute_fpfh_descriptor` (fpfh.py:16-117).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Stage 1 (fpfh.py:38-90): SPFH of every cloud point, rows in CELL-SORTED order. offsets/nbr_sorted: the CSR of
+ * sf_radius_* called with queries_dev == NULL. edges_host: float64 (3, n_bins + 1) histogram edges
+ * (np.linspace(lo, hi, n_bins + 1) for alpha, phi, theta). width = 3*n_bins (decorrelated) or n_bins^3. */
+int sf_spfh(sf_grid* grid, const int64_t* offsets_dev, const int32_t* nbr_sorted_dev, int32_t n_bins,
+            int32_t decorrelated, const double* edges_host, float* spfh_dev, void* stream);
+/* Stage 2 (fpfh.py:97-116) on keypoints given as ORIGINAL point indices. dist_dev: the CSR distances. */
+int sf_fpfh(sf_grid* grid, const int64_t* offsets_dev, const int32_t* nbr_sorted_dev, const double* dist_dev,
+            const float* spfh_dev, int32_t width, const int64_t* keypoint_index_dev, int64_t nq, void* out_dev,
+            int32_t out_is_f64, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * M — descriptor matching.  Replaces `cdist(...).argmin(axis=1)` in `basic_matching` (matching.py:162-169),
+ * `match_descriptors` (matching.py:43-52) and the ratio test `double_matching_with_rejects` (matching.py:172-221).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Rows with at least one non-zero entry (matching.py:43-44): ascending row ids into rows_dev[0..count). */
+int sf_nonempty_rows(const double* desc_dev, int64_t n, int32_t width, int64_t* rows_dev, int64_t* count_host,
+                     void* stream);
+/* Gathers rows `rows_dev` of a float64 matrix into the GEMM operand format: float16 (count, width_padded)
+ * scaled by `scale`, plus the float32 squared norms of the ROUNDED rows. width_padded is a multiple of 64. */
+int sf_match_pack(const double* desc_dev, int32_t width, const int64_t* rows_dev, int64_t count, double scale,
+                  void* packed_dev, int32_t width_padded, float* sqnorm_dev, void* stream);
+/* Shortlist: for each of the qa packed query rows, the k packed target rows with the smallest
+ * |b|^2 - 2 a.b (tensor-core GEMM, float16 operands, float32 accumulation). idx_dev: int32 (qa,k) positions in
+ * the packed target set plus `b_index_offset`; score_dev: float32 (qa,k), ascending. k <= 16.
+ * use_tensor_cores = 0 selects the plain CUDA-core kernel (used to cross-check the tcgen05 kernel). */
+int sf_match_topk(const void* a_packed_dev, int64_t qa, const void* b_packed_dev, const float* b_sqnorm_dev,
+                  int64_t qb, int32_t width_padded, int32_t k, int32_t b_index_offset, float* score_dev,
+                  int32_t* idx_dev, int32_t use_tensor_cores, void* stream);
+/* k-way merge of `parts` shortlists laid out (parts, qa, k) into (qa, k) (the step after the all-gather when the
+ * target set is sharded across GPUs). */
+int sf_topk_merge(const float* score_dev, const int32_t* idx_dev, int32_t parts, int64_t qa, int32_t k,
+                  float* score_out_dev, int32_t* idx_out_dev, void* stream);
+/* Exact re-rank: float64 `sqrt(sum((a-b)^2))` accumulated sequentially (what scipy's cdist computes) between each
+ * query row and its k candidates; nn_dev = candidate with the smallest distance (lowest index on ties),
+ * d1_dev / d2_dev = smallest and second smallest distance (d2 = +inf when k == 1 or a single candidate).
+ * rows_a/rows_b map packed positions to rows of the float64 matrices. nn_dev holds PACKED positions of b. */
+int sf_match_rerank(const double* a_desc_dev, const int64_t* rows_a_dev, int64_t qa, const double* b_desc_dev,
+                    const int64_t* rows_b_dev, int32_t width, const int32_t* cand_idx_dev, int32_t k,
+                    int32_t* nn_dev, double* d1_dev, double* d2_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOTFPFH_B200_H */

@@ -1,0 +1,152 @@
+// Kernel group P: FPFH (compute_fpfh_descriptor, fpfh.py:16-117), one warp per point.
+//   P1 spfh_kernel <- fpfh.py:38-90: Darboux-frame features (alpha, phi, theta) of every neighbour at distance > 0,
+//      binned with NumPy's histogram semantics (float64 edges from np.linspace handed in by the host), integer
+//      counts in shared memory (order-independent, hence exact), divided by the neighbourhood size INCLUDING the
+//      point itself. Rows are written in cell-sorted order so that stage 2 gathers them with good locality.
+//   P2 fpfh_kernel <- fpfh.py:97-116: spfh[i] + (sum_{j, d_j > 0} spfh[j] / d_j) / K_i on the keypoints.
+#include "sf_common.cuh"
+
+namespace sf {
+
+constexpr int kMaxBins = 64;
+__constant__ double c_edges[3][kMaxBins + 1];
+
+__global__ void __launch_bounds__(256)
+    spfh_kernel(GridView g, const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr, int n_bins,
+                int decorrelated, int width, float* __restrict__ spfh) {
+  extern __shared__ int hist_mem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  int* hist = hist_mem + warp * width;
+  const int64_t warps_total = int64_t(gridDim.x) * warps_per_block;
+  for (int64_t s = blockIdx.x * int64_t(warps_per_block) + warp; s < g.n; s += warps_total) {
+    for (int b = lane; b < width; b += 32) hist[b] = 0;
+    __syncwarp();
+    const double4 p = load_pt(g.pts + s);
+    const double4 un = load_pt(g.nrm + s);
+    const double u[3] = {un.x, un.y, un.z};
+    const int64_t begin = offsets[s], end = offsets[s + 1];
+    for (int64_t i = begin + lane; i < end; i += 32) {
+      const int j = __ldg(nbr + i);
+      const double4 pj = load_pt(g.pts + j);
+      const double rel[3] = {pj.x - p.x, pj.y - p.y, pj.z - p.z};
+      const double d2 = rdist3(rel[0], rel[1], rel[2]);
+      if (d2 > 0.0) {
+        const double4 nj4 = load_pt(g.nrm + j);
+        const double nj[3] = {nj4.x, nj4.y, nj4.z};
+        double alpha, phi, theta;
+        fpfh_features(rel, sqrt(d2), u, nj, alpha, phi, theta);
+        const int ia = histogram_bin(alpha, c_edges[0], n_bins);
+        const int ip = histogram_bin(phi, c_edges[1], n_bins);
+        const int it = histogram_bin(theta, c_edges[2], n_bins);
+        if (decorrelated) {  // three independent np.histogram calls: each feature dropped on its own
+          if (ia >= 0) atomicAdd(hist + ia, 1);
+          if (ip >= 0) atomicAdd(hist + n_bins + ip, 1);
+          if (it >= 0) atomicAdd(hist + 2 * n_bins + it, 1);
+        } else if (ia >= 0 && ip >= 0 && it >= 0) {  // np.histogramdd: dropped when any coordinate is outside
+          atomicAdd(hist + (ia * n_bins + ip) * n_bins + it, 1);
+        }
+      }
+    }
+    __syncwarp();
+    const double k_all = double(end - begin);
+    float* row = spfh + s * int64_t(width);
+    for (int b = lane; b < width; b += 32) row[b] = end > begin ? float(double(hist[b]) / k_all) : 0.0f;
+    __syncwarp();
+  }
+}
+
+template <int kRegs, typename OutT>
+__global__ void __launch_bounds__(256)
+    fpfh_kernel(const int32_t* __restrict__ inv_perm, const int64_t* __restrict__ offsets,
+                const int32_t* __restrict__ nbr, const double* __restrict__ dist, const float* __restrict__ spfh,
+                int width, int bin_base, const int64_t* __restrict__ keypoints, int64_t nq, OutT* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const int64_t s = inv_perm[keypoints[q]];
+  const int64_t begin = offsets[s], end = offsets[s + 1];
+  double acc[kRegs];
+#pragma unroll
+  for (int r = 0; r < kRegs; ++r) acc[r] = 0.0;
+  for (int64_t i = begin; i < end; ++i) {
+    const double d = __ldg(dist + i);
+    if (d > 0.0) {  // fpfh.py:112-114: the tree's own distances decide
+      const double w = 1.0 / d;
+      const float* row = spfh + int64_t(__ldg(nbr + i)) * width + bin_base;
+#pragma unroll
+      for (int r = 0; r < kRegs; ++r) {
+        const int b = lane + 32 * r;
+        if (bin_base + b < width) acc[r] += double(__ldg(row + b)) * w;
+      }
+    }
+  }
+  const double k_all = double(end - begin);
+  const float* own = spfh + s * width + bin_base;
+#pragma unroll
+  for (int r = 0; r < kRegs; ++r) {
+    const int b = lane + 32 * r;
+    if (bin_base + b < width)
+      out[q * int64_t(width) + bin_base + b] = OutT(end > begin ? double(own[b]) + acc[r] / k_all : 0.0);
+  }
+}
+
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" int sf_spfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, int32_t n_bins, int32_t decorrelated,
+                       const double* edges_host, float* spfh, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_spfh: grid built without normals");
+  SF_REQUIRE(offsets && nbr && edges_host && spfh, SF_ERR_ARG, "sf_spfh: null argument");
+  SF_REQUIRE(n_bins >= 1 && n_bins <= kMaxBins, SF_ERR_CAPACITY, "sf_spfh: n_bins must be in [1, %d]", kMaxBins);
+  const int64_t width64 = decorrelated ? 3 * int64_t(n_bins) : int64_t(n_bins) * n_bins * n_bins;
+  SF_REQUIRE(width64 <= 8192, SF_ERR_CAPACITY, "sf_spfh: histogram width %lld exceeds 8192", (long long)width64);
+  const int width = int(width64);
+  double edges[3][kMaxBins + 1] = {};
+  for (int f = 0; f < 3; ++f)
+    for (int b = 0; b <= n_bins; ++b) edges[f][b] = edges_host[f * (n_bins + 1) + b];
+  SF_CUDA(cudaMemcpyToSymbolAsync(c_edges, edges, sizeof(edges), 0, cudaMemcpyHostToDevice, stream));
+  SF_CUDA(cudaStreamSynchronize(stream));  // `edges` is a stack buffer
+  int warps = 8;
+  while (warps > 1 && size_t(warps) * width * sizeof(int) > 64 * 1024) warps >>= 1;
+  const size_t smem = size_t(warps) * width * sizeof(int);
+  if (smem > 48 * 1024)
+    SF_CUDA(cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int64_t blocks_needed = (g->n + warps - 1) / warps;
+  const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
+  spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), offsets, nbr, n_bins, decorrelated, width, spfh);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+template <typename OutT>
+static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist, const float* spfh,
+                       int width, const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
+  const int64_t threads = nq * 32;
+  const unsigned blocks = unsigned((threads + 255) / 256);
+  for (int base = 0; base < width; base += 128) {
+    const int left = width - base;
+    if (left <= 32)
+      fpfh_kernel<1, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, keypoints, nq, out);
+    else if (left <= 64)
+      fpfh_kernel<2, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, keypoints, nq, out);
+    else
+      fpfh_kernel<4, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, keypoints, nq, out);
+  }
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist, const float* spfh,
+                       int32_t width, const int64_t* keypoints, int64_t nq, void* out, int32_t out_is_f64,
+                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_fpfh: grid not built");
+  SF_REQUIRE(offsets && nbr && dist && spfh && keypoints && out && width > 0, SF_ERR_ARG, "sf_fpfh: null argument");
+  if (nq == 0) return SF_OK;
+  return out_is_f64 ? launch_fpfh(g, offsets, nbr, dist, spfh, width, keypoints, nq, static_cast<double*>(out), stream)
+                    : launch_fpfh(g, offsets, nbr, dist, spfh, width, keypoints, nq, static_cast<float*>(out), stream);
+}

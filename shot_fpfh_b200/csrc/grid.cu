@@ -1,0 +1,362 @@
+// Kernel group G: uniform-grid spatial hash with sort-by-cell, and fixed-radius search into CSR neighbour lists.
+// Replaces sklearn.neighbors.KDTree(points).query_radius(queries, r) — reference call sites
+// shot_parallelization.py:167-169, :220-222, :229-231, :283-285; fpfh.py:26-30; shot.py:340-341.
+//
+// Layout in HBM after sf_grid_build (n points, cell edge c >= 1.001 * radius):
+//   pts[n]        double4  cell-sorted coordinates, .w = original index (int64 bit pattern)    32 B / point
+//   nrm[n]        double4  cell-sorted normals                                                  32 B / point
+//   perm[n], inv_perm[n]   int32   sorted position <-> original index
+//   cell_start[ncells + 1] int32   exclusive prefix of the per-cell counts, key = (z*ny + y)*nx + x
+// The predicate is sklearn's, bit for bit: ((dx*dx + dy*dy) + dz*dz) <= r*r in float64 without FMA contraction.
+#include <cub/cub.cuh>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "sf_common.cuh"
+
+namespace sf {
+
+static thread_local char g_error[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+// ---- bounding box: per-block reduction + one atomic per block on the ordered-int image of the doubles -----
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double from_ordered_bits(unsigned long long o) {
+  const unsigned long long b = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(static_cast<long long>(b));
+#else
+  double d;
+  memcpy(&d, &b, sizeof(d));
+  return d;
+#endif
+}
+
+__global__ void bbox_init_kernel(unsigned long long* box) {
+  if (threadIdx.x < 3) box[threadIdx.x] = ~0ull;
+  else if (threadIdx.x < 6) box[threadIdx.x] = 0ull;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xyz, int64_t n, unsigned long long* box) {
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = xyz[3 * i + a];
+      lo[a] = fmin(lo[a], v);
+      hi[a] = fmax(hi[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fmin(lo[a], __shfl_xor_sync(kFull, lo[a], o));
+      hi[a] = fmax(hi[a], __shfl_xor_sync(kFull, hi[a], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(box + a, ordered_bits(lo[a]));
+      atomicMax(box + 3 + a, ordered_bits(hi[a]));
+    }
+  }
+}
+
+// ---- cell keys + per-cell histogram ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    key_kernel(const double* __restrict__ xyz, int64_t n, GridView g, uint32_t* __restrict__ keys,
+               int32_t* __restrict__ vals, int32_t* __restrict__ cell_count) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  int c[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    c[a] = cell_coord(xyz[3 * i + a], g.origin[a], g.inv_cell, g.dims[a]);
+    c[a] = min(max(c[a], 0), g.dims[a] - 1);
+  }
+  const uint32_t key = (uint32_t(c[2]) * g.dims[1] + c[1]) * g.dims[0] + c[0];
+  keys[i] = key;
+  vals[i] = int32_t(i);
+  atomicAdd(cell_count + key, 1);
+}
+
+// ---- gather into cell order ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    reorder_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int64_t n,
+                   const int32_t* __restrict__ perm, double4* __restrict__ pts, double4* __restrict__ nrm,
+                   int32_t* __restrict__ inv_perm) {
+  const int64_t s = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (s >= n) return;
+  const int32_t i = perm[s];
+  inv_perm[i] = int32_t(s);
+  pts[s] = make_double4(xyz[3 * int64_t(i)], xyz[3 * int64_t(i) + 1], xyz[3 * int64_t(i) + 2],
+                        __longlong_as_double(static_cast<long long>(i)));
+  if (normals != nullptr)
+    nrm[s] = make_double4(normals[3 * int64_t(i)], normals[3 * int64_t(i) + 1], normals[3 * int64_t(i) + 2], 0.0);
+}
+
+// ---- fixed-radius search: one warp per query ---------------------------------------------------------------
+// queries == nullptr means "the cloud's own points, in cell-sorted order" (the FPFH case, fpfh.py:28-30).
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+    radius_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double r2,
+                  int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                  int32_t* __restrict__ nbr_sorted, int32_t* __restrict__ nbr_index, double* __restrict__ dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  double qx, qy, qz;
+  if (queries != nullptr) {
+    qx = __ldg(queries + 3 * q);
+    qy = __ldg(queries + 3 * q + 1);
+    qz = __ldg(queries + 3 * q + 2);
+  } else {
+    const double4 p = load_pt(g.pts + q);
+    qx = p.x; qy = p.y; qz = p.z;
+  }
+  const Runs runs = build_runs(g, qx, qy, qz, lane);
+  const int total = runs.pref[9];
+  int64_t out = kFill ? offsets[q] : 0;
+  int count = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int v = base + lane;
+    bool hit = false;
+    int pos = 0;
+    double d2 = 0.0;
+    double4 p = make_double4(0, 0, 0, 0);
+    if (v < total) {
+      pos = run_position(runs, v);
+      p = load_pt(g.pts + pos);
+      d2 = rdist3(qx - p.x, qy - p.y, qz - p.z);
+      hit = d2 <= r2;
+    }
+    const unsigned mask = __ballot_sync(kFull, hit);
+    if (kFill) {
+      if (hit) {
+        const int64_t o = out + __popc(mask & lanemask_lt());
+        if (nbr_sorted != nullptr) nbr_sorted[o] = pos;
+        if (nbr_index != nullptr) nbr_index[o] = int32_t(__double_as_longlong(p.w));
+        if (dist != nullptr) dist[o] = sqrt(d2);
+      }
+      out += __popc(mask);
+    } else {
+      count += __popc(mask);
+    }
+  }
+  if (!kFill && lane == 0) counts[q] = count;
+}
+
+__global__ void widen_total_kernel(const int32_t* counts, int64_t* offsets, int64_t nq) {
+  // offsets[0..nq) hold the exclusive scan; close the CSR with offsets[nq] = offsets[nq-1] + counts[nq-1].
+  if (threadIdx.x == 0 && blockIdx.x == 0) offsets[nq] = nq > 0 ? offsets[nq - 1] + counts[nq - 1] : 0;
+}
+
+struct CountToI64 {
+  __host__ __device__ int64_t operator()(int32_t c) const { return int64_t(c); }
+};
+
+static int ensure_temp(sf_grid* g, size_t bytes) {
+  if (bytes <= g->cub_bytes) return SF_OK;
+  if (g->cub_temp) SF_CUDA(cudaFree(g->cub_temp));
+  g->cub_temp = nullptr;
+  g->cub_bytes = 0;
+  SF_CUDA(cudaMalloc(&g->cub_temp, bytes));
+  g->cub_bytes = bytes;
+  return SF_OK;
+}
+
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" const char* sf_last_error(void) { return sf::g_error; }
+extern "C" int sf_abi_version(void) { return SF_ABI_VERSION; }
+
+extern "C" int sf_grid_create(sf_grid** out) {
+  SF_REQUIRE(out != nullptr, SF_ERR_ARG, "sf_grid_create: null output");
+  *out = new sf_grid();
+  SF_CUDA(cudaGetDevice(&(*out)->device));
+  return SF_OK;
+}
+
+static void free_all(sf_grid* g) {
+  cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->perm); cudaFree(g->inv_perm);
+  cudaFree(g->cell_start); cudaFree(g->cell_count); cudaFree(g->keys_in); cudaFree(g->keys_out);
+  cudaFree(g->vals_in); cudaFree(g->bbox); cudaFree(g->cub_temp);
+}
+
+extern "C" int sf_grid_destroy(sf_grid* g) {
+  if (g == nullptr) return SF_OK;
+  free_all(g);
+  delete g;
+  return SF_OK;
+}
+
+extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normals, int64_t n, double radius,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && xyz != nullptr, SF_ERR_ARG, "sf_grid_build: null grid or points");
+  SF_REQUIRE(n > 0 && n < (int64_t(1) << 31), SF_ERR_ARG, "sf_grid_build: n = %lld out of range", (long long)n);
+  SF_REQUIRE(radius > 0.0 && std::isfinite(radius), SF_ERR_ARG, "sf_grid_build: radius must be positive and finite");
+  if (n > g->capacity) {
+    cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->perm); cudaFree(g->inv_perm);
+    cudaFree(g->keys_in); cudaFree(g->keys_out); cudaFree(g->vals_in);
+    g->capacity = 0;
+    SF_CUDA(cudaMalloc(&g->pts, n * sizeof(double4)));
+    SF_CUDA(cudaMalloc(&g->nrm, n * sizeof(double4)));
+    SF_CUDA(cudaMalloc(&g->perm, n * sizeof(int32_t)));
+    SF_CUDA(cudaMalloc(&g->inv_perm, n * sizeof(int32_t)));
+    SF_CUDA(cudaMalloc(&g->keys_in, n * sizeof(uint32_t)));
+    SF_CUDA(cudaMalloc(&g->keys_out, n * sizeof(uint32_t)));
+    SF_CUDA(cudaMalloc(&g->vals_in, n * sizeof(int32_t)));
+    g->capacity = n;
+  }
+  if (g->bbox == nullptr) SF_CUDA(cudaMalloc(&g->bbox, 6 * sizeof(double)));
+  g->n = n;
+  g->has_normals = normals != nullptr;
+
+  // 1. bounding box (device) -> host, the only synchronisation of the build
+  unsigned long long* box = reinterpret_cast<unsigned long long*>(g->bbox);
+  bbox_init_kernel<<<1, 32, 0, stream>>>(box);
+  const int bbox_blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  bbox_kernel<<<bbox_blocks, 256, 0, stream>>>(xyz, n, box);
+  unsigned long long hbox[6];
+  SF_CUDA(cudaMemcpyAsync(hbox, box, sizeof(hbox), cudaMemcpyDeviceToHost, stream));
+  SF_CUDA(cudaStreamSynchronize(stream));
+  double lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = from_ordered_bits(hbox[a]);
+    hi[a] = from_ordered_bits(hbox[3 + a]);
+    SF_REQUIRE(std::isfinite(lo[a]) && std::isfinite(hi[a]), SF_ERR_ARG, "sf_grid_build: non-finite coordinates");
+  }
+  // 2. cell edge: slightly above the radius so that rounding in the cell coordinate can never push a point
+  //    within `radius` of a query two cells away; grown when the dense table would exceed 2^25 cells.
+  double cell = radius * 1.001;
+  const double kMaxCells = double(1 << 25);
+  for (int iter = 0; iter < 64; ++iter) {
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) cells *= std::floor((hi[a] - lo[a]) * (1.0 / cell)) + 1.0;
+    if (cells <= kMaxCells) break;
+    cell *= std::cbrt(cells / kMaxCells) * 1.01;
+  }
+  g->cell = cell;
+  int64_t ncells = 1;
+  for (int a = 0; a < 3; ++a) {
+    g->origin[a] = lo[a];
+    g->dims[a] = int(std::floor((hi[a] - lo[a]) * (1.0 / cell))) + 1;
+    ncells *= g->dims[a];
+  }
+  SF_REQUIRE(ncells <= (int64_t(1) << 26), SF_ERR_ARG, "sf_grid_build: %lld cells", (long long)ncells);
+  g->ncells = ncells;
+  if (ncells + 1 > g->cells_capacity) {
+    cudaFree(g->cell_start); cudaFree(g->cell_count);
+    g->cells_capacity = 0;
+    SF_CUDA(cudaMalloc(&g->cell_start, (ncells + 1) * sizeof(int32_t)));
+    SF_CUDA(cudaMalloc(&g->cell_count, (ncells + 1) * sizeof(int32_t)));
+    g->cells_capacity = ncells + 1;
+  }
+  // 3. keys + histogram, 4. radix sort by cell (stable: ascending original index inside a cell),
+  // 5. prefix over cells, 6. gather into cell order
+  SF_CUDA(cudaMemsetAsync(g->cell_count, 0, (ncells + 1) * sizeof(int32_t), stream));
+  const GridView view = g->view();
+  const int blocks = int((n + 255) / 256);
+  key_kernel<<<blocks, 256, 0, stream>>>(xyz, n, view, g->keys_in, g->vals_in, g->cell_count);
+  int end_bit = 1;
+  while ((int64_t(1) << end_bit) < ncells) ++end_bit;
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, g->keys_in, g->keys_out, g->vals_in, g->perm, int(n), 0,
+                                  end_bit, stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, g->cell_count, g->cell_start, int(ncells + 1), stream);
+  if (int rc = ensure_temp(g, std::max(sort_bytes, scan_bytes) + 256)) return rc;
+  size_t bytes = g->cub_bytes;
+  SF_CUDA(cub::DeviceRadixSort::SortPairs(g->cub_temp, bytes, g->keys_in, g->keys_out, g->vals_in, g->perm, int(n), 0,
+                                          end_bit, stream));
+  bytes = g->cub_bytes;
+  SF_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_temp, bytes, g->cell_count, g->cell_start, int(ncells + 1), stream));
+  reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->perm, g->pts, g->nrm, g->inv_perm);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_grid_info(const sf_grid* g, int64_t* n, int64_t* ncells, double* cell, int32_t* dims3) {
+  SF_REQUIRE(g != nullptr, SF_ERR_ARG, "sf_grid_info: null grid");
+  if (n) *n = g->n;
+  if (ncells) *ncells = g->ncells;
+  if (cell) *cell = g->cell;
+  if (dims3) for (int a = 0; a < 3; ++a) dims3[a] = g->dims[a];
+  return SF_OK;
+}
+
+extern "C" int sf_grid_permutation(const sf_grid* g, int32_t* perm_out, int32_t* inv_perm_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_grid_permutation: grid not built");
+  if (perm_out)
+    SF_CUDA(cudaMemcpyAsync(perm_out, g->perm, g->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  if (inv_perm_out)
+    SF_CUDA(cudaMemcpyAsync(inv_perm_out, g->inv_perm, g->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  return SF_OK;
+}
+
+extern "C" int sf_radius_count(sf_grid* g, const double* queries, int64_t nq, double radius, int64_t* offsets,
+                               int64_t* total_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_radius_count: grid not built");
+  SF_REQUIRE(offsets != nullptr && nq >= 0, SF_ERR_ARG, "sf_radius_count: bad arguments");
+  SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
+             "sf_radius_count: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
+  if (queries == nullptr) nq = g->n;
+  if (nq == 0) {
+    SF_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int64_t), stream));
+    if (total_host) *total_host = 0;
+    return SF_OK;
+  }
+  // counts live in the (now free) sort scratch when it is large enough, else in a fresh temp
+  size_t scan_bytes = 0;
+  cub::TransformInputIterator<int64_t, CountToI64, const int32_t*> dummy(nullptr, CountToI64());
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, dummy, offsets, int(nq), stream);
+  const size_t counts_bytes = ((size_t(nq) * sizeof(int32_t) + 255) / 256) * 256;
+  if (int rc = ensure_temp(g, counts_bytes + scan_bytes + 256)) return rc;
+  int32_t* counts = static_cast<int32_t*>(g->cub_temp);
+  void* scan_temp = static_cast<char*>(g->cub_temp) + counts_bytes;
+  const double r2 = radius * radius;
+  const int64_t threads = nq * 32;
+  radius_kernel<false><<<unsigned((threads + 255) / 256), 256, 0, stream>>>(g->view(), queries, nq, r2, counts,
+                                                                           nullptr, nullptr, nullptr, nullptr);
+  cub::TransformInputIterator<int64_t, CountToI64, const int32_t*> in(counts, CountToI64());
+  size_t bytes = scan_bytes + 256;
+  SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, bytes, in, offsets, int(nq), stream));
+  widen_total_kernel<<<1, 32, 0, stream>>>(counts, offsets, nq);
+  SF_CUDA(cudaGetLastError());
+  if (total_host != nullptr) {
+    SF_CUDA(cudaMemcpyAsync(total_host, offsets + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaStreamSynchronize(stream));
+  }
+  return SF_OK;
+}
+
+extern "C" int sf_radius_fill(sf_grid* g, const double* queries, int64_t nq, double radius, const int64_t* offsets,
+                              int32_t* nbr_sorted, int32_t* nbr_index, double* dist, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_radius_fill: grid not built");
+  SF_REQUIRE(offsets != nullptr && nq >= 0, SF_ERR_ARG, "sf_radius_fill: bad arguments");
+  SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG, "sf_radius_fill: radius exceeds the cell edge");
+  if (queries == nullptr) nq = g->n;
+  if (nq == 0) return SF_OK;
+  const int64_t threads = nq * 32;
+  radius_kernel<true><<<unsigned((threads + 255) / 256), 256, 0, stream>>>(
+      g->view(), queries, nq, radius * radius, nullptr, offsets, nbr_sorted, nbr_index, dist);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}

@@ -1,0 +1,296 @@
+// Kernel group M (everything except the tcgen05 GEMM, which lives in match_tc.cu):
+//   M0 nonempty_kernel / sf_nonempty_rows <- np.any(desc, axis=1).nonzero()[0], matching.py:43-44, :162-163
+//   M0 pack_kernel    : float64 rows -> float16 GEMM operands + float32 squared norms of the rounded rows
+//   M1 topk_simt_kernel: CUDA-core shortlist kernel (cross-check of the tensor-core kernel, small problems)
+//   M2 rerank_kernel  <- cdist(...).argmin(axis=1) and the nearest / second-nearest distances,
+//                        matching.py:47-52, :164-168, :197-211: exact float64, sequential accumulation like SciPy
+//   topk_merge_kernel : k-way merge of per-shard shortlists (after the all-gather when targets are sharded)
+#include <cub/cub.cuh>
+#include <cuda_fp16.h>
+
+#include "sf_common.cuh"
+
+namespace sf {
+
+int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bnorm, int64_t qb, int width_padded,
+                   int k, int index_offset, float* score, int32_t* idx, cudaStream_t stream);  // match_tc.cu
+
+__global__ void __launch_bounds__(256)
+    nonempty_kernel(const double* __restrict__ desc, int64_t n, int width, uint8_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= n) return;
+  bool any = false;
+  for (int c = lane; c < width; c += 32) any |= desc[row * width + c] != 0.0;  // NaN counts as non-zero, like np.any
+  any = __any_sync(kFull, any);
+  if (lane == 0) flags[row] = any;
+}
+
+__global__ void __launch_bounds__(256)
+    pack_kernel(const double* __restrict__ desc, int width, const int64_t* __restrict__ rows, int64_t count,
+                double scale, __half* __restrict__ packed, int width_padded, float* __restrict__ sqnorm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (r >= count) return;
+  const double* src = desc + rows[r] * width;
+  float acc = 0.0f;
+  for (int c = lane; c < width_padded; c += 32) {
+    const __half h = c < width ? __double2half(src[c] * scale) : __float2half(0.0f);
+    packed[r * width_padded + c] = h;
+    const float f = __half2float(h);
+    acc += f * f;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) sqnorm[r] = acc;
+}
+
+// ---- running top-k of (score, index), ascending, ties broken by the lower index ----------------------------
+template <int K>
+struct TopK {
+  float s[K];
+  int i[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { s[k] = INFINITY; i[k] = -1; }
+  }
+  __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) const {
+    return sa < sb || (sa == sb && unsigned(ia) < unsigned(ib));
+  }
+  __device__ __forceinline__ void push(float score, int index) {
+    if (!before(score, index, s[K - 1], i[K - 1])) return;
+    s[K - 1] = score; i[K - 1] = index;
+#pragma unroll
+    for (int k = K - 1; k > 0; --k) {
+      if (before(s[k], i[k], s[k - 1], i[k - 1])) {
+        const float ts = s[k]; s[k] = s[k - 1]; s[k - 1] = ts;
+        const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti;
+      }
+    }
+  }
+};
+
+// ---- M1 (CUDA cores): 64 queries x 64 targets per tile, 4x4 micro-tiles, float32 accumulation ---------------
+template <int K>
+__global__ void __launch_bounds__(256)
+    topk_simt_kernel(const __half* __restrict__ a, int64_t qa, const __half* __restrict__ b,
+                     const float* __restrict__ bnorm, int64_t qb, int wp, int index_offset,
+                     float* __restrict__ score, int32_t* __restrict__ idx) {
+  __shared__ float sa[32][64 + 1];
+  __shared__ float sb[32][64 + 1];
+  __shared__ float sc[64][64 + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // micro-tile: rows ty*4.., cols tx*4..
+  const int64_t row0 = blockIdx.x * int64_t(64);
+  TopK<K> top;
+  top.init();
+  for (int64_t col0 = 0; col0 < qb; col0 += 64) {
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < wp; k0 += 32) {
+      for (int e = tid; e < 64 * 32; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        sa[c][r] = row0 + r < qa ? __half2float(a[(row0 + r) * wp + k0 + c]) : 0.0f;
+        sb[c][r] = col0 + r < qb ? __half2float(b[(col0 + r) * wp + k0 + c]) : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { av[u] = sa[c][ty * 4 + u]; bv[u] = sb[c][tx * 4 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int64_t col = col0 + tx * 4 + v;
+        sc[ty * 4 + u][tx * 4 + v] = col < qb ? fmaf(-2.0f, acc[u][v], bnorm[col]) : INFINITY;
+      }
+    __syncthreads();
+    if (tid < 64) {
+      const int ncols = int(qb - col0 < 64 ? qb - col0 : 64);
+      for (int c = 0; c < ncols; ++c) top.push(sc[tid][c], int(col0 + c) + index_offset);
+    }
+    __syncthreads();
+  }
+  if (tid < 64 && row0 + tid < qa) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      score[(row0 + tid) * K + k] = top.s[k];
+      idx[(row0 + tid) * K + k] = top.i[k];
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+    topk_merge_kernel(const float* __restrict__ score, const int32_t* __restrict__ idx, int parts, int64_t qa,
+                      float* __restrict__ score_out, int32_t* __restrict__ idx_out) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= qa) return;
+  TopK<K> top;
+  top.init();
+  for (int p = 0; p < parts; ++p)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int64_t o = (int64_t(p) * qa + q) * K + k;
+      const int id = idx[o];
+      if (id >= 0) top.push(score[o], id);
+    }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    score_out[q * K + k] = top.s[k];
+    idx_out[q * K + k] = top.i[k];
+  }
+}
+
+// ---- M2: exact float64 re-rank, one thread per query row ---------------------------------------------------
+__global__ void __launch_bounds__(128)
+    rerank_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a, int64_t qa,
+                  const double* __restrict__ b, const int64_t* __restrict__ rows_b, int width,
+                  const int32_t* __restrict__ cand, int k, int32_t* __restrict__ nn, double* __restrict__ d1,
+                  double* __restrict__ d2) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= qa) return;
+  const double* ra = a + (rows_a ? rows_a[q] : q) * width;
+  double best = INFINITY, second = INFINITY;
+  int best_idx = -1;
+  for (int c = 0; c < k; ++c) {
+    const int id = cand[q * k + c];
+    if (id < 0) continue;
+    const double* rb = b + (rows_b ? rows_b[id] : int64_t(id)) * width;
+    double s = 0.0;
+    for (int e = 0; e < width; ++e) {  // SciPy: s += (u[e] - v[e])^2, sequential, no FMA
+      const double d = ra[e] - rb[e];
+      s = add_rn(s, mul_rn(d, d));
+    }
+    const double dist = sqrt(s);
+    if (dist < best || (dist == best && id < best_idx)) {
+      second = best;
+      best = dist;
+      best_idx = id;
+    } else if (dist < second) {
+      second = dist;
+    }
+  }
+  nn[q] = best_idx;
+  if (d1) d1[q] = best;
+  if (d2) d2[q] = second;
+}
+
+struct IsSet {
+  const uint8_t* flags;
+  __host__ __device__ bool operator()(int64_t i) const { return flags[i] != 0; }
+};
+
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" int sf_nonempty_rows(const double* desc, int64_t n, int32_t width, int64_t* rows, int64_t* count_host,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(desc && rows && count_host && n >= 0 && width > 0, SF_ERR_ARG, "sf_nonempty_rows: bad arguments");
+  *count_host = 0;
+  if (n == 0) return SF_OK;
+  SF_REQUIRE(n < (int64_t(1) << 31), SF_ERR_ARG, "sf_nonempty_rows: too many rows");
+  uint8_t* flags = nullptr;
+  int64_t* count_dev = nullptr;
+  void* temp = nullptr;
+  size_t temp_bytes = 0;
+  cub::CountingInputIterator<int64_t> ids(0);
+  cub::DeviceSelect::Flagged(nullptr, temp_bytes, ids, flags, rows, count_dev, int(n), stream);
+  SF_CUDA(cudaMallocAsync(&flags, size_t(n), stream));
+  SF_CUDA(cudaMallocAsync(&count_dev, sizeof(int64_t), stream));
+  SF_CUDA(cudaMallocAsync(&temp, temp_bytes + 16, stream));
+  nonempty_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, stream>>>(desc, n, width, flags);
+  SF_CUDA(cub::DeviceSelect::Flagged(temp, temp_bytes, ids, flags, rows, count_dev, int(n), stream));
+  SF_CUDA(cudaMemcpyAsync(count_host, count_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  SF_CUDA(cudaFreeAsync(flags, stream));
+  SF_CUDA(cudaFreeAsync(count_dev, stream));
+  SF_CUDA(cudaFreeAsync(temp, stream));
+  SF_CUDA(cudaStreamSynchronize(stream));
+  return SF_OK;
+}
+
+extern "C" int sf_match_pack(const double* desc, int32_t width, const int64_t* rows, int64_t count, double scale,
+                             void* packed, int32_t width_padded, float* sqnorm, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(desc && rows && packed && sqnorm, SF_ERR_ARG, "sf_match_pack: null argument");
+  SF_REQUIRE(width > 0 && width_padded >= width && width_padded % 64 == 0, SF_ERR_ARG,
+             "sf_match_pack: width_padded must be a multiple of 64 that is >= width");
+  if (count == 0) return SF_OK;
+  pack_kernel<<<unsigned((count * 32 + 255) / 256), 256, 0, stream>>>(desc, width, rows, count, scale,
+                                                                     static_cast<__half*>(packed), width_padded, sqnorm);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+template <int K>
+static int launch_simt(const __half* a, int64_t qa, const __half* b, const float* bnorm, int64_t qb, int wp, int off,
+                       float* score, int32_t* idx, cudaStream_t stream) {
+  topk_simt_kernel<K><<<unsigned((qa + 63) / 64), 256, 0, stream>>>(a, qa, b, bnorm, qb, wp, off, score, idx);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_match_topk(const void* a, int64_t qa, const void* b, const float* bnorm, int64_t qb,
+                             int32_t width_padded, int32_t k, int32_t index_offset, float* score, int32_t* idx,
+                             int32_t use_tensor_cores, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(a && b && bnorm && score && idx, SF_ERR_ARG, "sf_match_topk: null argument");
+  SF_REQUIRE(width_padded > 0 && width_padded % 64 == 0, SF_ERR_ARG, "sf_match_topk: width_padded %% 64 != 0");
+  SF_REQUIRE(k == 1 || k == 2 || k == 4 || k == 8 || k == 16, SF_ERR_CAPACITY, "sf_match_topk: k must be 1,2,4,8,16");
+  SF_REQUIRE(qb + int64_t(index_offset) < (int64_t(1) << 31), SF_ERR_ARG, "sf_match_topk: target index overflow");
+  if (qa == 0) return SF_OK;
+  const __half* ha = static_cast<const __half*>(a);
+  const __half* hb = static_cast<const __half*>(b);
+  if (use_tensor_cores)
+    return launch_topk_tc(ha, qa, hb, bnorm, qb, width_padded, k, index_offset, score, idx, stream);
+  switch (k) {
+    case 1: return launch_simt<1>(ha, qa, hb, bnorm, qb, width_padded, index_offset, score, idx, stream);
+    case 2: return launch_simt<2>(ha, qa, hb, bnorm, qb, width_padded, index_offset, score, idx, stream);
+    case 4: return launch_simt<4>(ha, qa, hb, bnorm, qb, width_padded, index_offset, score, idx, stream);
+    case 8: return launch_simt<8>(ha, qa, hb, bnorm, qb, width_padded, index_offset, score, idx, stream);
+    default: return launch_simt<16>(ha, qa, hb, bnorm, qb, width_padded, index_offset, score, idx, stream);
+  }
+}
+
+template <int K>
+static int launch_merge(const float* score, const int32_t* idx, int parts, int64_t qa, float* so, int32_t* io,
+                        cudaStream_t stream) {
+  topk_merge_kernel<K><<<unsigned((qa + 127) / 128), 128, 0, stream>>>(score, idx, parts, qa, so, io);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_topk_merge(const float* score, const int32_t* idx, int32_t parts, int64_t qa, int32_t k,
+                             float* score_out, int32_t* idx_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(score && idx && score_out && idx_out && parts >= 1, SF_ERR_ARG, "sf_topk_merge: bad arguments");
+  SF_REQUIRE(k == 1 || k == 2 || k == 4 || k == 8 || k == 16, SF_ERR_CAPACITY, "sf_topk_merge: k must be 1,2,4,8,16");
+  if (qa == 0) return SF_OK;
+  switch (k) {
+    case 1: return launch_merge<1>(score, idx, parts, qa, score_out, idx_out, stream);
+    case 2: return launch_merge<2>(score, idx, parts, qa, score_out, idx_out, stream);
+    case 4: return launch_merge<4>(score, idx, parts, qa, score_out, idx_out, stream);
+    case 8: return launch_merge<8>(score, idx, parts, qa, score_out, idx_out, stream);
+    default: return launch_merge<16>(score, idx, parts, qa, score_out, idx_out, stream);
+  }
+}
+
+extern "C" int sf_match_rerank(const double* a, const int64_t* rows_a, int64_t qa, const double* b,
+                               const int64_t* rows_b, int32_t width, const int32_t* cand, int32_t k, int32_t* nn,
+                               double* d1, double* d2, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(a && b && cand && nn && width > 0 && k >= 1, SF_ERR_ARG, "sf_match_rerank: bad arguments");
+  if (qa == 0) return SF_OK;
+  rerank_kernel<<<unsigned((qa + 127) / 128), 128, 0, stream>>>(a, rows_a, qa, b, rows_b, width, cand, k, nn, d1, d2);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}

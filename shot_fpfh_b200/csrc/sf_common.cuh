@@ -1,0 +1,171 @@
+// Shared declarations of the sm_100a library behind include/shotfpfh_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/shotfpfh_b200.h"
+#include "sf_math.cuh"
+
+namespace sf {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Last error text, readable through sf_last_error(). No exceptions cross the C ABI.
+void set_error(const char* fmt, ...);
+
+#define SF_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess) {                                                                    \
+      sf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__));      \
+      return SF_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define SF_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      sf::set_error(__VA_ARGS__);        \
+      return code;                       \
+    }                                    \
+  } while (0)
+
+// Device-side view of a built grid (passed by value to kernels).
+struct GridView {
+  const double4* pts;       // cell-sorted coordinates; .w carries the original index (bit pattern of an int64)
+  const double4* nrm;       // cell-sorted normals (may be null)
+  const int32_t* cell_start;  // [ncells + 1], exclusive prefix of the per-cell counts
+  int64_t n;
+  double origin[3];
+  double inv_cell;
+  int dims[3];
+};
+
+}  // namespace sf
+
+// The opaque handle of the C ABI.
+struct sf_grid {
+  int64_t n = 0;
+  int64_t capacity = 0;
+  double cell = 0.0;
+  double origin[3] = {0, 0, 0};
+  int dims[3] = {0, 0, 0};
+  int64_t ncells = 0;
+  int64_t cells_capacity = 0;
+  bool has_normals = false;
+  int device = 0;
+  double4* pts = nullptr;
+  double4* nrm = nullptr;
+  int32_t* perm = nullptr;      // sorted position -> original index
+  int32_t* inv_perm = nullptr;  // original index -> sorted position
+  int32_t* cell_start = nullptr;
+  int32_t* cell_count = nullptr;
+  uint32_t* keys_in = nullptr;
+  uint32_t* keys_out = nullptr;
+  int32_t* vals_in = nullptr;
+  double* bbox = nullptr;  // 6 doubles, device
+  void* cub_temp = nullptr;
+  size_t cub_bytes = 0;
+  sf::GridView view() const {
+    sf::GridView v;
+    v.pts = pts;
+    v.nrm = has_normals ? nrm : nullptr;
+    v.cell_start = cell_start;
+    v.n = n;
+    for (int i = 0; i < 3; ++i) {
+      v.origin[i] = origin[i];
+      v.dims[i] = dims[i];
+    }
+    v.inv_cell = 1.0 / cell;
+    return v;
+  }
+};
+
+namespace sf {
+
+// ---- warp helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// 16-byte-pair load of one cell-sorted record through the read-only path.
+__device__ __forceinline__ double4 load_pt(const double4* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// ---- the candidate set of one query: 9 contiguous runs of the cell-sorted array ----------------------------
+// Cells are keyed (z * ny + y) * nx + x, so the three x-adjacent cells of a row are one contiguous run.
+// Each warp builds the runs once (lane j < 9 owns run j) and then walks the concatenation of the runs with all
+// 32 lanes busy: lane l visits virtual positions l, l + 32, ... and maps each to (run, offset).
+struct Runs {
+  int start[9];
+  int pref[10];  // pref[j] = number of candidates before run j; pref[9] = total
+};
+
+__device__ __forceinline__ int cell_coord(double q, double origin, double inv_cell, int dim) {
+  double c = floor((q - origin) * inv_cell);
+  c = fmax(-2.0, fmin(c, double(dim) + 1.0));
+  return int(c);
+}
+
+__device__ __forceinline__ Runs build_runs(const GridView& g, double qx, double qy, double qz, int lane) {
+  const int cx = cell_coord(qx, g.origin[0], g.inv_cell, g.dims[0]);
+  const int cy = cell_coord(qy, g.origin[1], g.inv_cell, g.dims[1]);
+  const int cz = cell_coord(qz, g.origin[2], g.inv_cell, g.dims[2]);
+  int s = 0, len = 0;
+  if (lane < 9) {
+    const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+    if (yy >= 0 && yy < g.dims[1] && zz >= 0 && zz < g.dims[2] && x0 <= x1) {
+      const int64_t base = (int64_t(zz) * g.dims[1] + yy) * g.dims[0];
+      s = __ldg(g.cell_start + base + x0);
+      len = __ldg(g.cell_start + base + x1 + 1) - s;
+    }
+  }
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  Runs r;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    r.start[j] = __shfl_sync(kFull, s, j);
+    r.pref[j + 1] = __shfl_sync(kFull, incl, j);
+  }
+  r.pref[0] = 0;
+  return r;
+}
+
+// Position in the cell-sorted array of virtual candidate v (0 <= v < pref[9]).
+__device__ __forceinline__ int run_position(const Runs& r, int v) {
+  int pos = r.start[0] + v;
+#pragma unroll
+  for (int j = 1; j < 9; ++j)
+    if (v >= r.pref[j]) pos = r.start[j] + (v - r.pref[j]);
+  return pos;
+}
+
+}  // namespace sf

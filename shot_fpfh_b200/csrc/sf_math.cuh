@@ -1,0 +1,243 @@
+// Per-neighbour / per-query arithmetic of the SHOT and FPFH kernels, written as __host__ __device__ inline
+// functions so that the exact same code is (a) inlined into the sm_100a kernels and (b) compiled by g++ into the
+// CPU-only unit test tests/host_math (which checks it against the oracle without a GPU). It is NOT a CPU
+// fallback: nothing in the product calls the host instantiation.
+//
+// Precision policy (DESIGN.md "Precision"): everything that DECIDES something (neighbour predicate, bin indices,
+// interpolation signs, LRF sign votes, distance ordering) is evaluated in float64 from the float64 inputs, with
+// explicit non-fused operations where the reference's result depends on the rounding of individual operations.
+// Only the interpolation WEIGHTS (continuous in their inputs) go through float32 transcendental functions.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SF_HD __host__ __device__ __forceinline__
+#else
+#define SF_HD inline
+#endif
+
+#include "sf_eigh3.cuh"  // eigh3(): LAPACK-path 3x3 eigen-solver (replaces np.linalg.eigh at shot.py:36)
+
+namespace sf {
+
+constexpr int kShotCos = 11, kShotAz = 8, kShotEl = 2, kShotRad = 2;
+constexpr int kShotLen = kShotCos * kShotAz * kShotEl * kShotRad;  // 352
+
+// a*b and a+b rounded separately (never contracted into an FMA), as NumPy / scikit-learn / SciPy compute them.
+SF_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double p = a * b;
+  return p;
+#endif
+}
+SF_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  volatile double s = a + b;
+  return s;
+#endif
+}
+
+// Reduced squared distance exactly as sklearn's euclidean rdist accumulates it: ((dx*dx + dy*dy) + dz*dz).
+// (sklearn/metrics/_dist_metrics: `for j: tmp = x1[j] - x2[j]; d += tmp * tmp`, d starting at 0.)
+SF_HD double rdist3(double dx, double dy, double dz) {
+  return add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// SHOT: one neighbour -> its own bin, the five "other" targets and the six values.
+// ----------------------------------------------------------------------------------------------------------
+// Azimuth octant by comparisons only (shot.py:60-70); octant 0 starts at -pi.
+SF_HD int azimuth_octant(double x, double y) {
+  const bool upper = (y > 0.0) || (y == 0.0 && x < 0.0);
+  const bool right = (x > 0.0) || (x == 0.0 && y > 0.0);
+  const bool second = ((x * y > 0.0) || (x == 0.0)) ? (fabs(x) < fabs(y)) : (fabs(x) > fabs(y));
+  return 4 * int(upper) + 2 * int(right != upper) + int(second);
+}
+
+struct ShotRecord {
+  int own;        // flat bin ((ci*8 + ti)*2 + ei)*2 + ri
+  int cos_nb;     // statement 1 target (cosine neighbour bin, or `own` when the cosine sits on a bin centre)
+  int az_nb;      // statement 9 target (azimuth neighbour bin, or `own`)
+  float v_own;    // statements 2 + 5 + 8 + 10 (all address `own`, hence share one winner)
+  float v_cos;    // statement 1
+  float v_az;     // statement 9
+  float v_rad;    // statement 3 or 4, whichever targets the OTHER radial shell (the one targeting `own` writes 0)
+  float v_el;     // statement 6 or 7, whichever targets the OTHER elevation half
+  uint32_t key;   // distance order: larger = later in the reference's ascending-rho order = wins
+};
+
+SF_HD int shot_flat(int ci, int ti, int ei, int ri) { return ((ci * kShotAz + ti) * kShotEl + ei) * kShotRad + ri; }
+
+// Unit vectors of the octant centre directions, angle = -pi + (t + 0.5) * pi/4.
+SF_HD void octant_centre(int t, double& cx, double& cy) {
+  const double c = 0.92387953251128673848;  // cos(pi/8)
+  const double s = 0.38268343236508978178;  // sin(pi/8)
+  switch (t) {
+    case 0: cx = -c; cy = -s; break;
+    case 1: cx = -s; cy = -c; break;
+    case 2: cx = s; cy = -c; break;
+    case 3: cx = c; cy = -s; break;
+    case 4: cx = c; cy = s; break;
+    case 5: cx = s; cy = c; break;
+    case 6: cx = -s; cy = c; break;
+    default: cx = -c; cy = s; break;
+  }
+}
+
+// local = (X, Y, Z) coordinates in the LRF (float64), cosine = clip(n . z_axis) (float64), rho > 0, radius.
+SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double rho, double radius) {
+  ShotRecord r;
+  const float kPi = 3.14159265358979323846f;
+  // ---- decisions, float64 -------------------------------------------------------------------------------
+  const double pos = (cosine + 1.0) * double(kShotCos) / 2.0 - 0.5;  // shot.py:228
+  const double ci_f = rint(pos);                                      // round-half-even like np.rint
+  const int ci = int(ci_f);
+  const double dcos = pos - ci_f;
+  const int scos = (dcos > 0.0) - (dcos < 0.0);
+  const int ti = azimuth_octant(X, Y);
+  const int ei = Z > 0.0;
+  const int ri = rho > radius / 2;
+  r.own = shot_flat(ci, ti, ei, ri);
+  int cnb = ci + scos;
+  cnb = cnb < 0 ? cnb + kShotCos : (cnb >= kShotCos ? cnb - kShotCos : cnb);
+  r.cos_nb = shot_flat(cnb, ti, ei, ri);
+  // sign of the azimuth offset from the octant centre: cross(centre, (X, Y)) instead of a float64 atan2
+  double cx, cy;
+  octant_centre(ti, cx, cy);
+  const double cr = cx * Y - cy * X;
+  // on the LRF's z axis (X == Y == 0) the reference gets theta = atan2(0, 0) = 0 in octant 0: offset clipped to +0.5
+  const int saz = (X == 0.0 && Y == 0.0) ? 1 : (cr > 0.0) - (cr < 0.0);
+  r.az_nb = shot_flat(ci, (ti + saz + kShotAz) & (kShotAz - 1), ei, ri);
+  // ---- weights ------------------------------------------------------------------------------------------
+  const float a_cos = float(fabs(dcos));
+  r.v_cos = a_cos;
+  // radial (shot.py:95-118); rho == radius/2 exactly gives 0 everywhere, as in the reference
+  const double half = radius / 2, quarter = radius / 4, three_q = radius * 3 / 4;
+  float own_shell, other_shell;
+  if (ri) {  // rho > r/2: statement 4 carries `inner`, statement 3 writes 0 to `own`
+    own_shell = float(1.0 - fabs(rho - three_q) / half);
+    other_shell = rho < three_q ? float((three_q - rho) / half) : 0.0f;
+  } else {
+    own_shell = rho < half ? float(1.0 - fabs(rho - quarter) / half) : 0.0f;
+    other_shell = (rho < half && rho > quarter) ? float((rho - quarter) / half) : 0.0f;
+  }
+  r.v_rad = other_shell;
+  // elevation (shot.py:142-171): phi < pi/2 <=> Z > 0; weights are continuous -> float32
+  float ratio = float(Z / rho);
+  ratio = fminf(1.0f, fmaxf(-1.0f, ratio));
+  const float phi = acosf(ratio);
+  const float h = 0.5f * kPi;
+  float own_vol, other_vol;
+  if (ei) {  // upper half-space, elevation bin 1, centre pi/4; statement 7 carries `lower`
+    own_vol = 1.0f - fabsf(phi - 0.25f * kPi) / h;
+    other_vol = phi >= 0.25f * kPi ? (phi - 0.25f * kPi) / h : 0.0f;
+  } else {   // Z <= 0, elevation bin 0, centre 3pi/4; statement 6 carries `upper`
+    own_vol = 1.0f - fabsf(phi - 0.75f * kPi) / h;
+    other_vol = phi <= 0.75f * kPi ? (0.75f * kPi - phi) / h : 0.0f;
+  }
+  r.v_el = fmaxf(other_vol, 0.0f);
+  // azimuth (shot.py:282-298)
+  const float theta = atan2f(float(Y), float(X));
+  const float q = 0.25f * kPi;
+  float daz = (theta - (-kPi + float(ti) * q)) / q - 0.5f;
+  daz = fminf(0.5f, fmaxf(-0.5f, daz));
+  const float a_az = saz == 0 ? 0.0f : fabsf(daz);
+  r.v_az = a_az;
+  r.v_own = (1.0f - a_cos) + own_shell + own_vol + (1.0f - a_az);
+  // ---- order key: rho / radius in 32-bit fixed point (monotone in rho; resolution radius * 2^-32) ---------
+  double scaled = rho / radius * 4294967296.0;
+  r.key = scaled >= 4294967295.0 ? 0xFFFFFFFFu : (scaled < 1.0 ? 1u : uint32_t(scaled));
+  return r;
+}
+
+// Slot layout of the winner tables (per query, 64-bit words (key << 32) | float bits):
+//   [0, 352)          own-bin group (statements 2, 5, 8, 10)
+//   [352, 704)        statement 1
+//   [704, 1056)       statement 9
+//   [1056, 1232)      statement 3  (target radial 1)      index = flat >> 1
+//   [1232, 1408)      statement 4  (target radial 0)
+//   [1408, 1584)      statement 6  (target elevation 1)   index = ((flat >> 2) << 1) | (flat & 1)
+//   [1584, 1760)      statement 7  (target elevation 0)
+constexpr int kSlotOwn = 0, kSlotCos = 352, kSlotAz = 704, kSlotRad1 = 1056, kSlotRad0 = 1232, kSlotEl1 = 1408,
+              kSlotEl0 = 1584, kSlotCount = 1760;
+
+SF_HD int drop_rad(int flat) { return flat >> 1; }
+SF_HD int drop_el(int flat) { return ((flat >> 2) << 1) | (flat & 1); }
+
+// The seven slot writes of one neighbour: slot index and value. Every neighbour performs all ten statements
+// of the reference, even with value 0 (that is how a later neighbour erases an earlier contribution).
+SF_HD void shot_slots(const ShotRecord& r, int slot[7], float val[7]) {
+  const int ri = r.own & 1, ei = (r.own >> 1) & 1;
+  slot[0] = kSlotOwn + r.own;                    val[0] = r.v_own;
+  slot[1] = kSlotCos + r.cos_nb;                 val[1] = r.v_cos;
+  slot[2] = kSlotAz + r.az_nb;                   val[2] = r.v_az;
+  // statement 3 targets radial 1: carries `outer` when the neighbour is in shell 0, else writes 0 to its own bin
+  slot[3] = kSlotRad1 + drop_rad(r.own);         val[3] = ri == 0 ? r.v_rad : 0.0f;
+  slot[4] = kSlotRad0 + drop_rad(r.own);         val[4] = ri == 1 ? r.v_rad : 0.0f;
+  slot[5] = kSlotEl1 + drop_el(r.own);           val[5] = ei == 0 ? r.v_el : 0.0f;
+  slot[6] = kSlotEl0 + drop_el(r.own);           val[6] = ei == 1 ? r.v_el : 0.0f;
+}
+
+SF_HD unsigned long long pack_slot(uint32_t key, float v) {
+#if defined(__CUDA_ARCH__)
+  return (static_cast<unsigned long long>(key) << 32) | __float_as_uint(v);
+#else
+  union { float f; uint32_t u; } c; c.f = v;
+  return (static_cast<unsigned long long>(key) << 32) | c.u;
+#endif
+}
+SF_HD float slot_value(unsigned long long w) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(static_cast<uint32_t>(w));
+#else
+  union { float f; uint32_t u; } c; c.u = static_cast<uint32_t>(w);
+  return c.f;
+#endif
+}
+
+// Value of descriptor bin `flat` from the winner tables.
+SF_HD float shot_bin_value(const unsigned long long* slots, int flat) {
+  const int ri = flat & 1, ei = (flat >> 1) & 1;
+  float v = slot_value(slots[kSlotOwn + flat]) + slot_value(slots[kSlotCos + flat]) +
+            slot_value(slots[kSlotAz + flat]);
+  v += slot_value(slots[(ri ? kSlotRad1 : kSlotRad0) + drop_rad(flat)]);
+  v += slot_value(slots[(ei ? kSlotEl1 : kSlotEl0) + drop_el(flat)]);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// FPFH pair features (fpfh.py:47-57), float64. rel = p_j - p_i (dist > 0), u = n_i, nj = n_j.
+// ----------------------------------------------------------------------------------------------------------
+SF_HD void fpfh_features(const double rel[3], double dist, const double u[3], const double nj[3], double& alpha,
+                         double& phi, double& theta) {
+  // v = rel x u ; w = u x v   (np.cross: each component is a*b - c*d, products rounded separately)
+  const double v0 = add_rn(mul_rn(rel[1], u[2]), -mul_rn(rel[2], u[1]));
+  const double v1 = add_rn(mul_rn(rel[2], u[0]), -mul_rn(rel[0], u[2]));
+  const double v2 = add_rn(mul_rn(rel[0], u[1]), -mul_rn(rel[1], u[0]));
+  const double w0 = add_rn(mul_rn(u[1], v2), -mul_rn(u[2], v1));
+  const double w1 = add_rn(mul_rn(u[2], v0), -mul_rn(u[0], v2));
+  const double w2 = add_rn(mul_rn(u[0], v1), -mul_rn(u[1], v0));
+  alpha = add_rn(add_rn(mul_rn(v0, nj[0]), mul_rn(v1, nj[1])), mul_rn(v2, nj[2]));
+  phi = add_rn(add_rn(mul_rn(rel[0], u[0]), mul_rn(rel[1], u[1])), mul_rn(rel[2], u[2])) / dist;
+  const double ny = add_rn(add_rn(mul_rn(nj[0], w0), mul_rn(nj[1], w1)), mul_rn(nj[2], w2));
+  const double nx = add_rn(add_rn(mul_rn(nj[0], u[0]), mul_rn(nj[1], u[1])), mul_rn(nj[2], u[2]));
+  theta = atan2(ny, nx);
+}
+
+// NumPy histogram bin of `x` for n equal bins with float64 edges e[0..n] (= np.linspace(lo, hi, n + 1)):
+// a value on an interior edge goes to the upper bin, e[n] belongs to the last bin, outside -> -1.
+SF_HD int histogram_bin(double x, const double* e, int n) {
+  if (!(x >= e[0]) || !(x <= e[n])) return -1;  // also drops NaN
+  int idx = int((x - e[0]) / (e[n] - e[0]) * n);
+  idx = idx < 0 ? 0 : (idx > n - 1 ? n - 1 : idx);
+  while (idx > 0 && x < e[idx]) --idx;
+  while (idx < n - 1 && x >= e[idx + 1]) ++idx;
+  return idx;
+}
+
+}  // namespace sf

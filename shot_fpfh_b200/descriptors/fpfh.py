@@ -1,0 +1,57 @@
+"""
+`compute_fpfh_descriptor` with the reference's signature (shot_fpfh/descriptors/fpfh.py:16-25), computed by the
+sm_100a kernels of csrc/grid.cu (radius search over ALL cloud points) and csrc/fpfh.cu (SPFH, then FPFH).
+
+`decorrelated=True` (the 3 * n_bins layout, e.g. (N, 33) for n_bins = 11) RAISES in the reference because a
+(n_bins, 3) array is assigned into a (3 * n_bins,) row (fpfh.py:59-79). Here it works and returns
+the concatenated layout `[alpha bins | phi bins | theta bins]` — what the reference yields once the single token
+`).T` at fpfh.py:78 is replaced by `).ravel()`.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import numpy.typing as npt
+import torch
+
+from .. import ops
+from ..device import Grid, upload
+
+
+def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
+                out_dtype: torch.dtype = torch.float64):
+    """search over every cloud point -> SPFH (cell-sorted rows) -> FPFH on the keypoints. Returns (fpfh, mean K)."""
+    offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
+    spfh_rows = ops.spfh(grid, offsets, nbr, n_bins, decorrelated)
+    out = ops.fpfh(grid, offsets, nbr, dist, spfh_rows, keypoints_dev, out_dtype=out_dtype)
+    return out, float(offsets[-1].item()) / max(grid.n, 1)
+
+
+def compute_fpfh_descriptor(
+    keypoints_indices: npt.NDArray[np.int64],
+    cloud_points: npt.NDArray[np.float64],
+    normals: npt.NDArray[np.float64],
+    radius: float,
+    n_bins: int,
+    decorrelated: bool = False,
+    verbose: bool = True,
+    disable_progress_bars: bool = True,
+) -> npt.NDArray[np.float64]:
+    """
+    FPFH on the points `cloud_points[keypoints_indices]` -> (Q, n_bins**3) float64, or (Q, 3 * n_bins) when
+    `decorrelated`. `keypoints_indices` are INDICES into the cloud (pipeline.py:330), unlike SHOT's coordinates.
+    """
+    kp = np.asarray(keypoints_indices)
+    if kp.size and (kp.min() < -cloud_points.shape[0] or kp.max() >= cloud_points.shape[0]):
+        raise IndexError("keypoints_indices out of bounds for the point cloud")
+    kp = np.where(kp < 0, kp + cloud_points.shape[0], kp).astype(np.int64)
+    pts, nrm = upload(cloud_points), upload(normals)
+    grid = Grid().build(pts, nrm, radius)
+    out, mean_k = fpfh_device(grid, upload(kp, torch.int64), float(radius), int(n_bins), bool(decorrelated))
+    if verbose:
+        logging.info(f"Mean neighborhood size over the whole point cloud: {mean_k:.2f}")
+    result = out.cpu().numpy()
+    grid.close()
+    return result

@@ -1,0 +1,86 @@
+"""
+Device plumbing: PyTorch owns device memory and streams, the C ABI (see _lib.py) does the work.
+Everything here fails loudly when no CUDA device is present — there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "shot_fpfh_b200 needs a CUDA device (built for NVIDIA B200, sm_100a); there is no CPU fallback."
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return int(t.data_ptr())
+
+
+def upload(a, dtype=torch.float64) -> torch.Tensor:
+    """Host array (or tensor already on the device) -> contiguous device tensor of `dtype`."""
+    dev = require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=dtype).contiguous()
+    np_dtype = {torch.float64: np.float64, torch.float32: np.float32, torch.int64: np.int64, torch.int32: np.int32}[dtype]
+    host = np.ascontiguousarray(a, dtype=np_dtype)
+    return torch.from_numpy(host).to(dev, non_blocking=True)
+
+
+class Grid:
+    """Owner of one `sf_grid` handle (uniform grid over a cloud, see csrc/grid.cu)."""
+
+    def __init__(self) -> None:
+        import ctypes
+
+        require_cuda()
+        self._h = ctypes.c_void_p()
+        check(lib.sf_grid_create(ctypes.byref(self._h)))
+        self.n = 0
+        self.radius = 0.0
+        self.has_normals = False
+        self._keep = ()
+
+    def build(self, xyz: torch.Tensor, normals: torch.Tensor | None, radius: float) -> "Grid":
+        assert xyz.dtype == torch.float64 and xyz.dim() == 2 and xyz.shape[1] == 3
+        if normals is not None:
+            assert normals.dtype == torch.float64 and normals.shape == xyz.shape
+        check(lib.sf_grid_build(self._h, ptr(xyz), ptr(normals), xyz.shape[0], float(radius), stream_ptr()))
+        self.n, self.radius, self.has_normals = int(xyz.shape[0]), float(radius), normals is not None
+        return self
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        import ctypes
+
+        n, ncells, cell = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+        dims = (ctypes.c_int32 * 3)()
+        check(lib.sf_grid_info(self._h, ctypes.byref(n), ctypes.byref(ncells), ctypes.byref(cell), dims))
+        return {"n": n.value, "ncells": ncells.value, "cell": cell.value, "dims": tuple(dims)}
+
+    def close(self) -> None:
+        if self._h:
+            lib.sf_grid_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # noqa: D105
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -1,0 +1,136 @@
+"""
+Descriptor matching with the reference's signatures (shot_fpfh/matching/matching.py:9-146, :149-169, :172-221).
+
+The reference materialises the full float64 `cdist` matrix and takes `argmin`. Here (csrc/match.cu, match_tc.cu):
+non-empty rows are compacted on the device, a tensor-core distance GEMM on float16 copies of the rows keeps a
+k-candidate shortlist per query without ever writing the matrix, and the shortlist is re-ranked with the exact
+float64 distance accumulated in SciPy's order — so the returned indices and nearest-neighbour distances are the
+reference's, provided the true nearest neighbour is among the k float16 candidates (k = 4 already
+gives 100 % on real SHOT rows; the default here is 8, and `exhaustive_check` in the tests measures it).
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Callable
+
+import numpy as np
+import numpy.typing as npt
+import torch
+
+from .. import ops
+from ..device import upload
+
+DEFAULT_SHORTLIST = 8
+
+
+class DeviceMatch:
+    """Result of one directed nearest-neighbour search, on the host."""
+
+    def __init__(self, rows_a, rows_b, nn, d1, d2):
+        self.rows_a, self.rows_b, self.nn, self.d1, self.d2 = rows_a, rows_b, nn, d1, d2
+
+
+def _prepare(desc) -> tuple[torch.Tensor, torch.Tensor]:
+    dev = upload(desc)
+    if dev.dim() != 2:
+        raise ValueError("descriptors must be a 2-D (n, width) array")
+    return dev, ops.nonempty_rows(dev)
+
+
+def nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k: int = DEFAULT_SHORTLIST, tensor_cores: bool = True):
+    """
+    For every non-empty row of a: the nearest and second-nearest non-empty rows of b (float64 distances, lowest
+    index on ties). Returns device tensors (nn positions in rows_b, d1, d2).
+    """
+    qa, qb = int(rows_a.shape[0]), int(rows_b.shape[0])
+    if qa == 0:
+        e = torch.empty(0, device=a_dev.device)
+        return e.to(torch.int32), e.to(torch.float64), e.to(torch.float64)
+    if qb == 0:
+        raise ValueError("attempt to get argmin of an empty sequence")  # what NumPy raises in the reference
+    scale = 1.0 / max(float(a_dev.abs().max().item()), float(b_dev.abs().max().item()), 1e-300)
+    a_packed, _ = ops.match_pack(a_dev, rows_a, scale)
+    b_packed, b_sqnorm = ops.match_pack(b_dev, rows_b, scale)
+    _, cand = ops.match_topk(a_packed, b_packed, b_sqnorm, k, 0, tensor_cores)
+    return ops.match_rerank(a_dev, rows_a, b_dev, rows_b, cand)
+
+
+def _match(scan, ref, k=DEFAULT_SHORTLIST, reverse=False, tensor_cores=True):
+    a_dev, rows_a = _prepare(scan)
+    b_dev, rows_b = _prepare(ref)
+    if a_dev.shape[1] != b_dev.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")
+    nn, d1, d2 = nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k, tensor_cores)
+    fwd = DeviceMatch(rows_a.cpu().numpy(), rows_b.cpu().numpy(), nn.cpu().numpy().astype(np.int64), d1.cpu().numpy(),
+                      d2.cpu().numpy())
+    if not reverse:
+        return fwd, None
+    nn_r, _, _ = nearest_neighbors_device(b_dev, rows_b, a_dev, rows_a, k, tensor_cores)
+    return fwd, nn_r.cpu().numpy().astype(np.int64)
+
+
+def basic_matching(
+    scan_descriptors: npt.NDArray[np.float64], ref_descriptors: npt.NDArray[np.float64]
+) -> tuple[npt.NDArray[np.int64], npt.NDArray[np.int64]]:
+    """Each non-empty scan descriptor with its nearest non-empty reference descriptor (matching.py:149-169)."""
+    m, _ = _match(scan_descriptors, ref_descriptors)
+    return m.rows_a, m.rows_b[m.nn]
+
+
+def match_descriptors(
+    scan_descriptors: npt.NDArray[np.float64],
+    ref_descriptors: npt.NDArray[np.float64],
+    filter_callback: Callable[..., npt.NDArray[np.bool_]] | None = None,
+    filter_nonreciprocal: bool = False,
+    verbose: bool = True,
+    n_min_matches: int = 100,
+    **kwargs: bool | int | float | tuple[float, float],
+) -> tuple[npt.NDArray[np.int64], npt.NDArray[np.int64]]:
+    """
+    Nearest-neighbour matching with an optional filter on the nearest-neighbour distances and an optional
+    reciprocity filter (matching.py:9-74, :138-146). The reciprocity check `D.argmin(0)[idx] == arange` is a second
+    nearest-neighbour search with the roles swapped. Only the 2-D (Euclidean) branch is on the GPU; the 3-D
+    multi-scale branch (matching.py:76-136), which the pipeline never reaches, is not implemented.
+    """
+    if np.ndim(scan_descriptors) != 2:
+        raise NotImplementedError(
+            "multi-scale (3-D) infinite-norm matching is outside this round's hot path (SURVEY.md §8f row 3)"
+        )
+    logging.info("")
+    logging.info("-- Matching descriptors based on Euclidian-norm proximity --")
+    m, nn_reverse = _match(scan_descriptors, ref_descriptors, reverse=filter_nonreciprocal)
+    distances = m.d1
+    filtered = (
+        filter_callback(distances, **kwargs) if filter_callback is not None else np.ones(distances.shape[0], dtype=bool)
+    )
+    if filter_nonreciprocal:
+        reciprocal = nn_reverse[m.nn] == np.arange(m.nn.shape[0])
+        if (final_mask := filtered & reciprocal).sum() >= n_min_matches:
+            filtered = final_mask
+        elif verbose:
+            logging.warning("Too few reciprocal matches, keeping non-reciprocal matches.")
+    if verbose:
+        logging.info(f"Kept {filtered.sum()} matches out of {np.shape(scan_descriptors)[-2]} descriptors.")
+    return m.rows_a[filtered], m.rows_b[m.nn[filtered]]
+
+
+def double_matching_with_rejects(
+    scan_descriptors: npt.NDArray[np.float64],
+    ref_descriptors: npt.NDArray[np.float64],
+    threshold: float,
+    verbose: bool = True,
+) -> tuple[npt.NDArray[np.int64], npt.NDArray[np.int64]]:
+    """
+    Ratio test (matching.py:172-221). The reference raises on every input (three independent indexing bugs,
+    SURVEY.md F3); this is what its code and docstring intend: with d1 <= d2 the distances to the nearest and
+    second-nearest reference descriptors, keep the scan descriptors whose ratio d1 / d2 (1 where d2 == 0) is
+    `>= threshold` — the comparison as written at matching.py:203-211 — and match them to their nearest neighbour.
+    """
+    m, _ = _match(scan_descriptors, ref_descriptors)
+    d2 = np.where(np.isfinite(m.d2), m.d2, 0.0)  # a single candidate: no second neighbour -> ratio 1
+    ratio = np.divide(m.d1, d2, out=np.ones_like(m.d1), where=d2 != 0)
+    mask = ratio >= threshold
+    if verbose:
+        logging.info(f"Kept {mask.sum()} matches out of {np.shape(scan_descriptors)[0]} descriptors.")
+    return m.rows_a[mask], m.rows_b[m.nn[mask]]

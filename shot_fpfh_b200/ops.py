@@ -1,0 +1,185 @@
+"""
+Thin device-level wrappers: one Python function per C-ABI entry point (include/shotfpfh_b200.h), taking and
+returning CUDA tensors. No arithmetic happens here.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .device import Grid, ptr, require_cuda, stream_ptr
+
+SHOT_LEN = 352
+FPFH_RANGES = ((-1.0, 1.0), (-1.0, 1.0), (-np.pi / 2, np.pi / 2))
+
+
+def radius_csr(
+    grid: Grid,
+    queries: torch.Tensor | None,
+    radius: float,
+    want_sorted: bool = True,
+    want_index: bool = False,
+    want_dist: bool = False,
+):
+    """
+    Fixed-radius search (sf_radius_count + sf_radius_fill). `queries=None` searches around the cloud's own
+    points in cell-sorted order. Returns (offsets int64[q+1], nbr_sorted|None, nbr_index|None, dist|None).
+    """
+    dev = require_cuda()
+    nq = grid.n if queries is None else int(queries.shape[0])
+    offsets = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+    total = ctypes.c_int64(0)
+    check(lib.sf_radius_count(grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ctypes.byref(total), stream_ptr()))
+    p = int(total.value)
+    nbr_sorted = torch.empty(p, dtype=torch.int32, device=dev) if want_sorted else None
+    nbr_index = torch.empty(p, dtype=torch.int32, device=dev) if want_index else None
+    dist = torch.empty(p, dtype=torch.float64, device=dev) if want_dist else None
+    check(
+        lib.sf_radius_fill(
+            grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ptr(nbr_sorted), ptr(nbr_index), ptr(dist),
+            stream_ptr(),
+        )
+    )
+    return offsets, nbr_sorted, nbr_index, dist
+
+
+def grid_permutation(grid: Grid) -> tuple[torch.Tensor, torch.Tensor]:
+    """(perm, inv_perm) as int32 CUDA tensors (copies; the grid keeps the originals)."""
+    dev = require_cuda()
+    perm = torch.empty(grid.n, dtype=torch.int32, device=dev)
+    inv = torch.empty(grid.n, dtype=torch.int32, device=dev)
+    check(lib.sf_grid_permutation(grid.handle, ptr(perm), ptr(inv), stream_ptr()))
+    return perm, inv
+
+
+def shot_lrf(grid: Grid, queries: torch.Tensor, radius: float, offsets: torch.Tensor, nbr_sorted: torch.Tensor):
+    nq = int(queries.shape[0])
+    lrf = torch.empty((nq, 3, 3), dtype=torch.float64, device=queries.device)
+    check(lib.sf_shot_lrf(grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ptr(nbr_sorted), ptr(lrf), stream_ptr()))
+    return lrf
+
+
+def shot_descriptor(
+    grid: Grid,
+    queries: torch.Tensor,
+    radius: float,
+    offsets: torch.Tensor,
+    nbr_sorted: torch.Tensor,
+    lrf: torch.Tensor,
+    min_neighborhood_size: int,
+    normalize: bool,
+    out_dtype: torch.dtype = torch.float64,
+    out: torch.Tensor | None = None,
+):
+    nq = int(queries.shape[0])
+    if out is None:
+        out = torch.empty((nq, SHOT_LEN), dtype=out_dtype, device=queries.device)
+    assert out.shape == (nq, SHOT_LEN) and out.dtype in (torch.float32, torch.float64)
+    check(
+        lib.sf_shot_descriptor(
+            grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ptr(nbr_sorted), ptr(lrf),
+            int(min_neighborhood_size), int(bool(normalize)), ptr(out), int(out.dtype == torch.float64), stream_ptr(),
+        )
+    )
+    return out
+
+
+def fpfh_edges(n_bins: int) -> np.ndarray:
+    """(3, n_bins + 1) float64 histogram edges, built on the host exactly as NumPy builds them."""
+    return np.ascontiguousarray(np.stack([np.linspace(lo, hi, n_bins + 1) for lo, hi in FPFH_RANGES]))
+
+
+def spfh(grid: Grid, offsets: torch.Tensor, nbr_sorted: torch.Tensor, n_bins: int, decorrelated: bool):
+    width = 3 * n_bins if decorrelated else n_bins**3
+    out = torch.empty((grid.n, width), dtype=torch.float32, device=offsets.device)
+    edges = fpfh_edges(n_bins)
+    check(
+        lib.sf_spfh(
+            grid.handle, ptr(offsets), ptr(nbr_sorted), int(n_bins), int(bool(decorrelated)),
+            edges.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ptr(out), stream_ptr(),
+        )
+    )
+    return out
+
+
+def fpfh(
+    grid: Grid,
+    offsets: torch.Tensor,
+    nbr_sorted: torch.Tensor,
+    dist: torch.Tensor,
+    spfh_rows: torch.Tensor,
+    keypoints: torch.Tensor,
+    out_dtype: torch.dtype = torch.float64,
+):
+    nq, width = int(keypoints.shape[0]), int(spfh_rows.shape[1])
+    out = torch.empty((nq, width), dtype=out_dtype, device=offsets.device)
+    check(
+        lib.sf_fpfh(
+            grid.handle, ptr(offsets), ptr(nbr_sorted), ptr(dist), ptr(spfh_rows), width, ptr(keypoints), nq, ptr(out),
+            int(out_dtype == torch.float64), stream_ptr(),
+        )
+    )
+    return out
+
+
+# ---- matching -------------------------------------------------------------------------------------------------
+def nonempty_rows(desc: torch.Tensor) -> torch.Tensor:
+    n, width = int(desc.shape[0]), int(desc.shape[1])
+    rows = torch.empty(max(n, 1), dtype=torch.int64, device=desc.device)
+    count = ctypes.c_int64(0)
+    check(lib.sf_nonempty_rows(ptr(desc), n, width, ptr(rows), ctypes.byref(count), stream_ptr()))
+    return rows[: int(count.value)]
+
+
+def padded_width(width: int) -> int:
+    return (width + 63) // 64 * 64
+
+
+def match_pack(desc: torch.Tensor, rows: torch.Tensor, scale: float):
+    """-> (float16 (count, padded_width) operand, float32 squared norms of the rounded rows)."""
+    width, count = int(desc.shape[1]), int(rows.shape[0])
+    wp = padded_width(width)
+    packed = torch.empty((count, wp), dtype=torch.float16, device=desc.device)
+    sqnorm = torch.empty(count, dtype=torch.float32, device=desc.device)
+    check(lib.sf_match_pack(ptr(desc), width, ptr(rows), count, float(scale), ptr(packed), wp, ptr(sqnorm), stream_ptr()))
+    return packed, sqnorm
+
+
+def match_topk(a_packed, b_packed, b_sqnorm, k: int, index_offset: int = 0, tensor_cores: bool = True):
+    qa, qb, wp = int(a_packed.shape[0]), int(b_packed.shape[0]), int(a_packed.shape[1])
+    score = torch.empty((qa, k), dtype=torch.float32, device=a_packed.device)
+    idx = torch.empty((qa, k), dtype=torch.int32, device=a_packed.device)
+    check(
+        lib.sf_match_topk(
+            ptr(a_packed), qa, ptr(b_packed), ptr(b_sqnorm), qb, wp, int(k), int(index_offset), ptr(score), ptr(idx),
+            int(bool(tensor_cores)), stream_ptr(),
+        )
+    )
+    return score, idx
+
+
+def topk_merge(score: torch.Tensor, idx: torch.Tensor):
+    """(parts, qa, k) -> (qa, k)."""
+    parts, qa, k = (int(s) for s in score.shape)
+    so = torch.empty((qa, k), dtype=torch.float32, device=score.device)
+    io = torch.empty((qa, k), dtype=torch.int32, device=score.device)
+    check(lib.sf_topk_merge(ptr(score.contiguous()), ptr(idx.contiguous()), parts, qa, k, ptr(so), ptr(io), stream_ptr()))
+    return so, io
+
+
+def match_rerank(a_desc, rows_a, b_desc, rows_b, cand_idx):
+    qa, k, width = int(cand_idx.shape[0]), int(cand_idx.shape[1]), int(a_desc.shape[1])
+    nn = torch.empty(qa, dtype=torch.int32, device=a_desc.device)
+    d1 = torch.empty(qa, dtype=torch.float64, device=a_desc.device)
+    d2 = torch.empty(qa, dtype=torch.float64, device=a_desc.device)
+    check(
+        lib.sf_match_rerank(
+            ptr(a_desc), ptr(rows_a), qa, ptr(b_desc), ptr(rows_b), width, ptr(cand_idx.contiguous()), k, ptr(nn),
+            ptr(d1), ptr(d2), stream_ptr(),
+        )
+    )
+    return nn, d1, d2

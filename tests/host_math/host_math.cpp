@@ -1,0 +1,125 @@
+// TEST INFRASTRUCTURE ONLY. g++ host instantiation of shot_fpfh_b200/csrc/sf_math.cuh, the header the sm_100a
+// kernels inline, so that the per-neighbour arithmetic (bin decisions, interpolation weights, winner tables, 3x3
+// eigen-solver, FPFH features and NumPy-compatible binning) is checked against the oracle on machines without
+// a GPU (tests/test_host_math.py). The loops below mirror the kernels' control flow sequentially; the product
+// never loads this library.
+#include <cstring>
+#include <vector>
+
+#include "../../shot_fpfh_b200/csrc/sf_math.cuh"
+
+using namespace sf;
+
+extern "C" {
+
+double hm_rdist3(double dx, double dy, double dz) { return rdist3(dx, dy, dz); }
+
+void hm_eigh3(const double* m, double* eval, double* evec9) {
+  double e[3], v[3][3];
+  eigh3(m, e, v);
+  for (int c = 0; c < 3; ++c) {
+    eval[c] = e[c];
+    for (int k = 0; k < 3; ++k) evec9[3 * c + k] = v[c][k];
+  }
+}
+
+int hm_azimuth_octant(double x, double y) { return azimuth_octant(x, y); }
+
+// Mirrors shot_lrf_kernel: lrf9 row-major, columns [x y z].
+void hm_lrf(const double* point, const double* nbrs, int k, double radius, double* lrf9) {
+  if (k == 0) {
+    for (int i = 0; i < 9; ++i) lrf9[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < k; ++i) {
+    const double cx = nbrs[3 * i] - point[0], cy = nbrs[3 * i + 1] - point[1], cz = nbrs[3 * i + 2] - point[2];
+    const double w = radius - sqrt(rdist3(cx, cy, cz));
+    sw += w;
+    m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
+    m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
+  }
+  for (int j = 0; j < 6; ++j) m[j] /= sw;
+  double eval[3], evec[3][3];
+  eigh3(m, eval, evec);
+  double x[3] = {evec[2][0], evec[2][1], evec[2][2]}, z[3] = {evec[0][0], evec[0][1], evec[0][2]};
+  int neg_x = 0, neg_z = 0;
+  for (int i = 0; i < k; ++i) {
+    const double cx = nbrs[3 * i] - point[0], cy = nbrs[3 * i + 1] - point[1], cz = nbrs[3 * i + 2] - point[2];
+    neg_x += (cx * x[0] + cy * x[1] + cz * x[2]) < 0.0;
+    neg_z += (cx * z[0] + cy * z[1] + cz * z[2]) < 0.0;
+  }
+  if (neg_x > k - neg_x) for (int a = 0; a < 3; ++a) x[a] = -x[a];
+  if (neg_z > k - neg_z) for (int a = 0; a < 3; ++a) z[a] = -z[a];
+  const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+  for (int a = 0; a < 3; ++a) {
+    lrf9[3 * a + 0] = x[a];
+    lrf9[3 * a + 1] = y[a];
+    lrf9[3 * a + 2] = z[a];
+  }
+}
+
+// Mirrors shot_descriptor_kernel for one query (atomicMax replaced by a sequential max).
+void hm_shot_descriptor(const double* point, const double* nbrs, const double* normals, int k, double radius,
+                        const double* f, int normalize, int min_nb, float* out352) {
+  std::vector<unsigned long long> slots(kSlotCount, 0ull);
+  int positive = 0;
+  for (int i = 0; i < k; ++i) {
+    const double cx = nbrs[3 * i] - point[0], cy = nbrs[3 * i + 1] - point[1], cz = nbrs[3 * i + 2] - point[2];
+    const double d2 = rdist3(cx, cy, cz);
+    if (!(d2 > 0.0)) continue;
+    ++positive;
+    const double rho = sqrt(d2);
+    const double X = cx * f[0] + cy * f[3] + cz * f[6];
+    const double Y = cx * f[1] + cy * f[4] + cz * f[7];
+    const double Z = cx * f[2] + cy * f[5] + cz * f[8];
+    double cosine = normals[3 * i] * f[2] + normals[3 * i + 1] * f[5] + normals[3 * i + 2] * f[8];
+    cosine = fmin(1.0, fmax(-1.0, cosine));
+    const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius);
+    int slot[7];
+    float val[7];
+    shot_slots(rec, slot, val);
+    for (int s = 0; s < 7; ++s) {
+      const unsigned long long w = pack_slot(rec.key, val[s]);
+      if (w > slots[slot[s]]) slots[slot[s]] = w;
+    }
+  }
+  double sq = 0.0;
+  float v[kShotLen];
+  for (int b = 0; b < kShotLen; ++b) {
+    v[b] = shot_bin_value(slots.data(), b);
+    sq += double(v[b]) * double(v[b]);
+  }
+  const double norm = sqrt(sq);
+  const bool keep = positive > min_nb && norm > 0.0;
+  const float inv = keep ? (normalize ? float(1.0 / norm) : 1.0f) : 0.0f;
+  for (int b = 0; b < kShotLen; ++b) out352[b] = v[b] * inv;
+}
+
+// Mirrors spfh_kernel for one point: integer histogram of width 3n or n^3.
+void hm_spfh_counts(const double* point, const double* normal, const double* nbrs, const double* nbr_normals, int k,
+                    int n_bins, int decorrelated, const double* edges, int* hist) {
+  const int width = decorrelated ? 3 * n_bins : n_bins * n_bins * n_bins;
+  std::memset(hist, 0, sizeof(int) * width);
+  for (int i = 0; i < k; ++i) {
+    const double rel[3] = {nbrs[3 * i] - point[0], nbrs[3 * i + 1] - point[1], nbrs[3 * i + 2] - point[2]};
+    const double d2 = rdist3(rel[0], rel[1], rel[2]);
+    if (!(d2 > 0.0)) continue;
+    double alpha, phi, theta;
+    fpfh_features(rel, sqrt(d2), normal, nbr_normals + 3 * i, alpha, phi, theta);
+    const int ia = histogram_bin(alpha, edges, n_bins);
+    const int ip = histogram_bin(phi, edges + (n_bins + 1), n_bins);
+    const int it = histogram_bin(theta, edges + 2 * (n_bins + 1), n_bins);
+    if (decorrelated) {
+      if (ia >= 0) ++hist[ia];
+      if (ip >= 0) ++hist[n_bins + ip];
+      if (it >= 0) ++hist[2 * n_bins + it];
+    } else if (ia >= 0 && ip >= 0 && it >= 0) {
+      ++hist[(ia * n_bins + ip) * n_bins + it];
+    }
+  }
+}
+
+int hm_histogram_bin(double x, const double* edges, int n) { return histogram_bin(x, edges, n); }
+
+}  // extern "C"

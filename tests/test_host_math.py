@@ -1,0 +1,172 @@
+"""
+CPU check of the arithmetic the sm_100a kernels inline (shot_fpfh_b200/csrc/sf_math.cuh), through its g++ host
+instantiation tests/host_math/libhost_math.so, against the oracle (which is pinned bit-exactly to the reference).
+This is what can be verified about the kernels without a GPU: bin decisions, interpolation weights, the
+winner-table formulation of the reference's last-writer-wins binning, the Jacobi eigen-solver, the FPFH features
+and the NumPy-compatible histogram binning. Tolerance for descriptors: 1e-4 relative L2 per row (north_star).
+"""
+
+import ctypes
+import os
+
+import numpy as np
+import pytest
+from conftest import ROOT, rel_l2
+
+from oracle import fpfh_oracle, shot_oracle
+from shot_fpfh_b200 import synthetic
+from sklearn.neighbors import KDTree
+
+DP = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(DP)
+
+
+@pytest.fixture(scope="module")
+def hm():
+    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "host_math", "libhost_math.so"))
+    lib.hm_rdist3.restype = ctypes.c_double
+    lib.hm_rdist3.argtypes = [ctypes.c_double] * 3
+    lib.hm_azimuth_octant.argtypes = [ctypes.c_double] * 2
+    lib.hm_histogram_bin.argtypes = [ctypes.c_double, DP, ctypes.c_int]
+    lib.hm_eigh3.argtypes = [DP, DP, DP]
+    lib.hm_lrf.argtypes = [DP, DP, ctypes.c_int, ctypes.c_double, DP]
+    lib.hm_shot_descriptor.argtypes = [DP, DP, DP, ctypes.c_int, ctypes.c_double, DP, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_float)]
+    lib.hm_spfh_counts.argtypes = [DP, DP, DP, DP, ctypes.c_int, ctypes.c_int, ctypes.c_int, DP,
+                                   ctypes.POINTER(ctypes.c_int)]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def cloud():
+    n = 6000
+    pts, normals = synthetic.bumpy_sphere(n, seed=5)
+    rng = np.random.default_rng(0)
+    normals = normals + 0.2 * rng.normal(size=normals.shape)
+    normals /= np.linalg.norm(normals, axis=1, keepdims=True)
+    radius = 5.0 * synthetic.mean_spacing(n)
+    return pts, normals, radius, KDTree(pts)
+
+
+def test_eigh3_matches_lapack(hm):
+    rng = np.random.default_rng(1)
+    for trial in range(500):
+        a = rng.normal(size=(20, 3)) * rng.uniform(0.01, 1.0, size=3) * 10.0 ** rng.integers(-4, 2)
+        m = a.T @ a / 20
+        packed = np.array([m[0, 0], m[0, 1], m[0, 2], m[1, 1], m[1, 2], m[2, 2]])
+        ev, vec = np.zeros(3), np.zeros(9)
+        hm.hm_eigh3(_p(packed), _p(ev), _p(vec))
+        w, v = np.linalg.eigh(m)
+        assert np.allclose(ev, w, rtol=1e-12, atol=1e-14 * np.abs(w).max())
+        vec = vec.reshape(3, 3)
+        for c in range(3):
+            gap = min(abs(w[c] - w[o]) for o in range(3) if o != c) / max(np.abs(w).max(), 1e-300)
+            if gap > 1e-6:
+                assert abs(abs(vec[c] @ v[:, c]) - 1.0) < 1e-10 / gap * 1e-4 + 1e-12
+
+
+def test_azimuth_octant_table(hm):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "edge_cases.npz"))
+    got = [hm.hm_azimuth_octant(float(x), float(y)) for x, y in zip(g["azimuth_x"], g["azimuth_y"])]
+    assert np.array_equal(got, g["azimuth_idx"])
+    rng = np.random.default_rng(2)
+    xy = rng.normal(size=(20000, 2))
+    got = np.array([hm.hm_azimuth_octant(float(x), float(y)) for x, y in xy])
+    assert np.array_equal(got, shot_oracle.azimuth_octant(xy[:, 0], xy[:, 1]))
+    assert np.array_equal(got, np.floor((np.arctan2(xy[:, 1], xy[:, 0]) + np.pi) / (np.pi / 4)).astype(int))
+
+
+def test_rdist_is_sklearn_order(hm):
+    rng = np.random.default_rng(3)
+    for d in rng.normal(size=(2000, 3)):
+        sq = d * d
+        assert hm.hm_rdist3(*map(float, d)) == (sq[0] + sq[1]) + sq[2]
+
+
+def test_lrf_matches_oracle(hm, cloud):
+    pts, _, radius, tree = cloud
+    worst = 0.0
+    for i in range(0, pts.shape[0], 40):
+        nb = tree.query_radius(pts[i : i + 1], radius)[0]
+        want = shot_oracle.local_reference_frame(pts[i], pts[nb], radius)
+        got = np.zeros(9)
+        hm.hm_lrf(_p(pts[i].copy()), _p(np.ascontiguousarray(pts[nb])), nb.shape[0], radius, _p(got))
+        worst = max(worst, np.abs(got.reshape(3, 3) - want).max())
+    assert worst < 1e-9, worst
+    got = np.zeros(9)
+    hm.hm_lrf(_p(pts[0].copy()), _p(np.zeros((0, 3))), 0, radius, _p(got))
+    assert np.array_equal(got.reshape(3, 3), np.eye(3))
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_shot_winner_tables_match_oracle(hm, cloud, normalize):
+    """The winner-table formulation (7 tables, packed 64-bit max) against the bit-exact oracle."""
+    pts, normals, radius, tree = cloud
+    errs = []
+    for i in range(0, pts.shape[0], 12):
+        nb = tree.query_radius(pts[i : i + 1], radius)[0]
+        lrf = shot_oracle.local_reference_frame(pts[i], pts[nb], radius)
+        want = shot_oracle.shot_descriptor(pts[i], pts[nb], normals[nb], radius, lrf, normalize, 10)
+        got = np.zeros(352, dtype=np.float32)
+        hm.hm_shot_descriptor(
+            _p(pts[i].copy()), _p(np.ascontiguousarray(pts[nb])), _p(np.ascontiguousarray(normals[nb])), nb.shape[0],
+            radius, _p(np.ascontiguousarray(lrf)), int(normalize), 10, got.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+        )
+        errs.append(float(rel_l2(got.astype(np.float64), want)))
+    errs = np.array(errs)
+    assert errs.shape[0] == 500
+    assert (errs > 1e-4).sum() == 0, f"{(errs > 1e-4).sum()} rows above 1e-4, max {errs.max():.3e}"
+    assert np.median(errs) < 1e-6
+
+
+def test_shot_sparse_neighbourhood_is_zero(hm, cloud):
+    pts, normals, radius, tree = cloud
+    nb = tree.query_radius(pts[:1], radius)[0][:8]
+    got = np.ones(352, dtype=np.float32)
+    hm.hm_shot_descriptor(
+        _p(pts[0].copy()), _p(np.ascontiguousarray(pts[nb])), _p(np.ascontiguousarray(normals[nb])), nb.shape[0],
+        radius, _p(np.eye(3)), 1, 10, got.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+    )
+    assert not got.any()
+
+
+def test_histogram_bin_is_numpy(hm):
+    rng = np.random.default_rng(4)
+    for n_bins in (5, 11, 7):
+        edges = fpfh_oracle.bin_edges(n_bins)
+        for f in range(3):
+            e = np.ascontiguousarray(edges[f])
+            lo, hi = e[0], e[-1]
+            vals = np.concatenate([
+                rng.uniform(lo * 1.2, hi * 1.2, 4000), e, np.nextafter(e, np.inf), np.nextafter(e, -np.inf),
+                [np.nan, np.inf, -np.inf],
+            ])
+            got = np.array([hm.hm_histogram_bin(float(v), _p(e), n_bins) for v in vals])
+            finite = np.isfinite(vals)
+            assert np.array_equal(got[finite], fpfh_oracle.bin_index(vals[finite], e))
+            assert (got[~finite] == -1).all()
+            counts = np.bincount(got[got >= 0], minlength=n_bins)
+            assert np.array_equal(counts, np.histogram(vals[finite], bins=n_bins, range=(lo, hi))[0])
+
+
+@pytest.mark.parametrize("n_bins,decorrelated", [(5, False), (11, True), (11, False)])
+def test_spfh_counts_match_oracle(hm, cloud, n_bins, decorrelated):
+    pts, normals, radius, tree = cloud
+    edges = np.ascontiguousarray(fpfh_oracle.bin_edges(n_bins))
+    width = 3 * n_bins if decorrelated else n_bins**3
+    mismatched = 0
+    for i in range(0, pts.shape[0], 15):
+        nb = tree.query_radius(pts[i : i + 1], radius)[0]
+        a, p, t = fpfh_oracle.pair_features(pts[i], normals[i], pts[nb], normals[nb])
+        want = fpfh_oracle.spfh_row(a, p, t, nb.shape[0], n_bins, decorrelated, edges) * nb.shape[0]
+        hist = np.zeros(width, dtype=np.int32)
+        hm.hm_spfh_counts(
+            _p(pts[i].copy()), _p(normals[i].copy()), _p(np.ascontiguousarray(pts[nb])),
+            _p(np.ascontiguousarray(normals[nb])), nb.shape[0], n_bins, int(decorrelated), _p(edges),
+            hist.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+        )
+        mismatched += int(not np.array_equal(hist, np.rint(want).astype(np.int32)))
+    assert mismatched == 0
