@@ -269,6 +269,19 @@ static int launch_merge(const float* score, const int32_t* idx, int parts, int64
   return SF_OK;
 }
 
+namespace sf {
+int launch_merge_partials(const float* score, const int32_t* idx, int parts, int64_t qa, int k, float* score_out,
+                          int32_t* idx_out, cudaStream_t stream) {
+  switch (k) {
+    case 1: return launch_merge<1>(score, idx, parts, qa, score_out, idx_out, stream);
+    case 2: return launch_merge<2>(score, idx, parts, qa, score_out, idx_out, stream);
+    case 4: return launch_merge<4>(score, idx, parts, qa, score_out, idx_out, stream);
+    case 8: return launch_merge<8>(score, idx, parts, qa, score_out, idx_out, stream);
+    default: return launch_merge<16>(score, idx, parts, qa, score_out, idx_out, stream);
+  }
+}
+}  // namespace sf
+
 extern "C" int sf_topk_merge(const float* score, const int32_t* idx, int32_t parts, int64_t qa, int32_t k,
                              float* score_out, int32_t* idx_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -31,6 +31,14 @@ def radius_csr(
     """
     dev = require_cuda()
     nq = grid.n if queries is None else int(queries.shape[0])
+    if nq == 0:  # an empty query set (a NULL pointer would mean "the cloud itself" to the C ABI)
+        e32 = torch.empty(0, dtype=torch.int32, device=dev)
+        return (
+            torch.zeros(1, dtype=torch.int64, device=dev),
+            e32 if want_sorted else None,
+            e32.clone() if want_index else None,
+            torch.empty(0, dtype=torch.float64, device=dev) if want_dist else None,
+        )
     offsets = torch.empty(nq + 1, dtype=torch.int64, device=dev)
     total = ctypes.c_int64(0)
     check(lib.sf_radius_count(grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ctypes.byref(total), stream_ptr()))
@@ -117,6 +125,8 @@ def fpfh(
 ):
     nq, width = int(keypoints.shape[0]), int(spfh_rows.shape[1])
     out = torch.empty((nq, width), dtype=out_dtype, device=offsets.device)
+    if nq == 0:
+        return out
     check(
         lib.sf_fpfh(
             grid.handle, ptr(offsets), ptr(nbr_sorted), ptr(dist), ptr(spfh_rows), width, ptr(keypoints), nq, ptr(out),

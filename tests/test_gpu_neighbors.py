@@ -1,0 +1,129 @@
+"""
+GPU parity, kernel group G: the uniform-grid radius search against sklearn's KDTree.query_radius (what the
+reference calls) and against the golden neighbour lists. Bar: neighbour SETS bit-exact, distances bit-exact.
+"""
+
+import numpy as np
+import pytest
+from conftest import edge_case_inputs, golden_pair_inputs, load_golden
+
+from oracle import neighbors_oracle
+from shot_fpfh_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _csr_sets(search, queries, radius=None, return_distance=False):
+    out = search.query_radius(queries, radius, return_distance=return_distance)
+    return out
+
+
+def _assert_same_sets(got, want):
+    assert len(got) == len(want)
+    for i in range(len(got)):
+        assert np.array_equal(np.sort(got[i]), np.sort(want[i])), f"query {i}: neighbour sets differ"
+
+
+def test_golden_neighbour_lists():
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    g = load_golden("small_pair_4k")
+    clouds, radius = golden_pair_inputs(g)
+    for tag, (cloud, _) in clouds.items():
+        kp = g[f"{tag}_kp_grid"]
+        s = RadiusSearch(cloud, radius)
+        got = s.query_radius(cloud[kp])
+        offs, idx = g[f"{tag}_nbr_offsets"], g[f"{tag}_nbr_indices"]
+        assert np.array_equal(np.cumsum([0] + [len(n) for n in got]), offs)
+        for i in range(len(got)):
+            assert np.array_equal(np.sort(got[i]), idx[offs[i] : offs[i + 1]])
+        s.close()
+
+
+def test_lattice_inclusive_boundary():
+    """Distances exactly equal to the radius are inside (<=), as in sklearn."""
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    g = load_golden("edge_cases")
+    pts, q = g["lattice_points"], g["lattice_queries"]
+    for name in ("half", "quarter", "diag"):
+        r = float(g[f"lattice_{name}_r"])
+        s = RadiusSearch(pts, r)
+        got = s.query_radius(q)
+        offs, idx = g[f"lattice_{name}_offsets"], g[f"lattice_{name}_indices"]
+        for i in range(len(got)):
+            assert np.array_equal(np.sort(got[i]), idx[offs[i] : offs[i + 1]]), (name, i)
+        s.close()
+
+
+def test_edge_queries_off_cloud_empty_and_duplicates():
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    g = load_golden("edge_cases")
+    pts, _, queries, radius = edge_case_inputs(g)
+    s = RadiusSearch(pts, radius)
+    got, dist = s.query_radius(queries, return_distance=True)
+    offs, idx = g["edge_nbr_offsets"], g["edge_nbr_indices"]
+    for i in range(len(got)):
+        assert np.array_equal(np.sort(got[i]), idx[offs[i] : offs[i + 1]]), i
+    assert len(got[90]) == 0 and len(got[91]) == 0  # the two far-away queries
+    # distances: sqrt of the sequential float64 reduced distance, bit for bit
+    for i in (0, 7, 65, 95):
+        d = pts[got[i]] - queries[i]
+        sq = d * d
+        assert np.array_equal(dist[i], np.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2]))
+    s.close()
+
+
+@pytest.mark.parametrize("n,seed", [(30000, 0), (200000, 4)])
+def test_against_kdtree_all_points(n, seed):
+    """Every cloud point as a query (the FPFH case) against the KD-tree, sets and distances."""
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    pts, _ = synthetic.bumpy_sphere(n, seed)
+    radius = 5.0 * synthetic.mean_spacing(n)
+    stride = max(1, n // 20000)
+    q = pts[::stride]
+    want, wdist = neighbors_oracle.kdtree_radius(pts, q, radius, return_distance=True)
+    s = RadiusSearch(pts, radius)
+    got, gdist = s.query_radius(q, return_distance=True)
+    _assert_same_sets(got, want)
+    for i in range(0, len(got), 97):
+        assert np.array_equal(gdist[i][np.argsort(got[i])], wdist[i][np.argsort(want[i])])
+    # self-CSR (queries=None): counts agree with the explicit query path
+    offsets, nbr_sorted, _, _ = s.csr(None, want_index=False, want_sorted=True)
+    assert int(offsets[-1]) == sum(len(x) for x in s.query_radius(pts))
+    s.close()
+
+
+def test_smaller_radius_on_same_grid_and_random_box_cloud():
+    """A volumetric (non-surface) cloud, queries outside the bounding box, radius below the build radius."""
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    rng = np.random.default_rng(12)
+    pts = rng.uniform(-1, 1, size=(50000, 3)) * np.array([1.0, 0.5, 2.0])
+    q = np.concatenate([rng.uniform(-1.2, 1.2, size=(3000, 3)) * np.array([1.0, 0.5, 2.0]), pts[:500]])
+    s = RadiusSearch(pts, 0.08)
+    for r in (0.08, 0.05, 0.011):
+        want = neighbors_oracle.kdtree_radius(pts, q, r)
+        _assert_same_sets(s.query_radius(q, r), want)
+    with pytest.raises(Exception):
+        s.query_radius(q, 0.2)  # larger than the cell edge the grid was built for: refused, not silently wrong
+    s.close()
+
+
+def test_degenerate_clouds():
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    one = np.array([[0.5, -1.0, 2.0]])
+    s = RadiusSearch(one, 0.1)
+    got = s.query_radius(np.array([[0.5, -1.0, 2.0], [0.5, -1.0, 2.2]]))
+    assert np.array_equal(got[0], [0]) and len(got[1]) == 0
+    s.close()
+    flat = np.zeros((1000, 3))
+    flat[:, 0] = np.linspace(0, 1, 1000)  # all points on a line: two grid dimensions collapse to one cell
+    s = RadiusSearch(flat, 0.01)
+    want = neighbors_oracle.kdtree_radius(flat, flat[::10], 0.01)
+    _assert_same_sets(s.query_radius(flat[::10]), want)
+    assert len(s.query_radius(np.zeros((0, 3)))) == 0
+    s.close()

@@ -1,0 +1,207 @@
+"""
+GPU parity, kernel group S: SHOT local reference frames and descriptors through the reference-shaped API
+(`ShotMultiprocessor`), against the golden fixtures (outputs of the unmodified reference) and against the oracle on
+seeded inputs. Bar (north_star): <= 1e-4 relative L2 per descriptor in float32; the fraction of rows above it is
+COUNTED and must stay below 0.2 % (bin-boundary flips / exact-distance ties; DESIGN.md "Tolerances").
+"""
+
+import numpy as np
+import pytest
+from conftest import edge_case_inputs, golden_pair_inputs, load_golden, rel_l2
+
+from oracle import shot_oracle
+from shot_fpfh_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # relative L2 per descriptor (BASELINE.json north_star)
+MAX_EXEMPT_FRACTION = 0.002
+
+
+def _check_rows(got, want, what):
+    assert got.shape == want.shape and got.dtype == np.float64
+    zero_want = ~want.any(axis=1)
+    assert np.array_equal(~got.any(axis=1), zero_want), f"{what}: all-zero rows differ"
+    err = rel_l2(got[~zero_want], want[~zero_want])
+    bad = int((err > TOL).sum())
+    print(f"{what}: rows {err.shape[0]}, median {np.median(err):.2e}, max {err.max():.2e}, above {TOL:g}: {bad}")
+    assert bad <= max(1, int(MAX_EXEMPT_FRACTION * err.shape[0])), f"{what}: {bad} rows above {TOL}"
+    return err
+
+
+@pytest.mark.parametrize("name", ["small_pair_4k", "c1_pair_30k"])
+def test_golden_shot_single_scale(name):
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+
+    g = load_golden(name)
+    clouds, radius = golden_pair_inputs(g)
+    with ShotMultiprocessor(min_neighborhood_size=int(g["min_neighborhood_size"]), verbose=False) as shot:
+        for tag, (cloud, normals) in clouds.items():
+            kp = g[f"{tag}_kp_grid"]
+            got = shot.compute_descriptor_single_scale(cloud, normals, cloud[kp], radius)
+            _check_rows(got, g[f"{tag}_shot_grid"], f"{name}/{tag}/grid")
+    with ShotMultiprocessor(normalize=False, min_neighborhood_size=10, verbose=False) as shot:
+        cloud, normals = clouds["scan"]
+        got = shot.compute_descriptor_single_scale(cloud, normals, cloud[g["scan_kp_grid"]], radius)
+        _check_rows(got, g["scan_shot_grid_raw"], f"{name}/scan/raw")
+
+
+def test_golden_lrf_including_tied_sign_votes():
+    """Frames must agree INCLUDING the sign LAPACK leaves when the vote is tied (sf_eigh3.cuh)."""
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+    from shot_fpfh_b200.neighbors import RadiusSearch
+
+    g = load_golden("c1_pair_30k")
+    clouds, radius = golden_pair_inputs(g)
+    for tag, (cloud, _) in clouds.items():
+        kp = cloud[g[f"{tag}_kp_grid"]]
+        s = RadiusSearch(cloud, radius)
+        nbh = s.query_radius(kp)
+        s.close()
+        with ShotMultiprocessor(verbose=False) as shot:
+            got = shot.compute_local_rf(kp, nbh, cloud, radius)
+        want = g[f"{tag}_lrf_grid"]
+        diff = np.abs(got - want).reshape(len(kp), -1).max(axis=1)
+        print(f"{tag}: LRF max abs diff {diff.max():.2e}, frames off by > 1e-6: {(diff > 1e-6).sum()} of {len(kp)}")
+        assert (diff > 1e-6).sum() == 0
+
+
+def test_default_min_neighborhood_size_zeroes_everything():
+    """the reference default (100, strict >) zeroes every row at K ~ 72."""
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+
+    g = load_golden("small_pair_4k")
+    clouds, radius = golden_pair_inputs(g)
+    cloud, normals = clouds["scan"]
+    with ShotMultiprocessor(verbose=False) as shot:
+        got = shot.compute_descriptor_single_scale(cloud, normals, cloud[g["scan_kp_grid"]][:40], radius)
+    assert got.shape == (40, 352) and not got.any()
+
+
+def test_edge_cases_empty_sparse_duplicates_offcloud():
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+    from shot_fpfh_b200.descriptors.shot import compute_shot_descriptor
+
+    g = load_golden("edge_cases")
+    pts, nrm, queries, radius = edge_case_inputs(g)
+    for min_nb in (10, 40):
+        with ShotMultiprocessor(min_neighborhood_size=min_nb, verbose=False) as shot:
+            got = shot.compute_descriptor_single_scale(pts, nrm, queries, radius)
+        _check_rows(got, g[f"edge_shot_minnb{min_nb}"], f"edge/minnb{min_nb}")
+    assert not got[90].any() and not got[91].any()  # empty neighbourhoods
+    # the serial twin (distance-0 neighbours dropped before the frame)
+    _check_rows(compute_shot_descriptor(queries, pts, nrm, radius, min_neighborhood_size=10), g["edge_shot_serial"],
+                "edge/serial")
+
+
+def test_single_query_functions_match_batch():
+    from shot_fpfh_b200.descriptors.shot import compute_single_shot_descriptor, get_local_rf
+    from sklearn.neighbors import KDTree
+
+    g = load_golden("small_pair_4k")
+    clouds, radius = golden_pair_inputs(g)
+    cloud, normals = clouds["scan"]
+    kp = g["scan_kp_grid"][:6]
+    nbh = KDTree(cloud).query_radius(cloud[kp], radius)
+    for row, i in enumerate(kp):
+        lrf = get_local_rf((cloud[i], cloud[nbh[row]], radius))
+        assert np.abs(lrf - g["scan_lrf_grid"][row]).max() < 1e-9
+        d = compute_single_shot_descriptor((cloud[i], cloud[nbh[row]], normals[nbh[row]], radius, lrf, True, 10))
+        assert rel_l2(d, g["scan_shot_grid"][row]) < TOL
+    assert np.array_equal(get_local_rf((cloud[0], np.zeros((0, 3)), radius)), np.eye(3))
+
+
+def test_oracle_parity_dense_queries_100k_cloud():
+    """Seeded 100k-point cloud, 3 000 queries: the oracle finishes in seconds, the GPU path must agree."""
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+
+    n = 100_000
+    pts, dirs = synthetic.bumpy_sphere(n, seed=21)
+    rng = np.random.default_rng(5)
+    normals = dirs + 0.1 * rng.normal(size=dirs.shape)
+    normals /= np.linalg.norm(normals, axis=1, keepdims=True)
+    radius = 5.0 * synthetic.mean_spacing(n)
+    kp = pts[rng.choice(n, 3000, replace=False)]
+    want = shot_oracle.shot_single_scale(pts, normals, kp, radius, True, 10)
+    with ShotMultiprocessor(min_neighborhood_size=10, verbose=False) as shot:
+        got = shot.compute_descriptor_single_scale(pts, normals, kp, radius)
+    _check_rows(got, want, "oracle/100k")
+
+
+def test_bi_scale_and_multiscale_against_oracle():
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+    from sklearn.neighbors import KDTree
+
+    n = 20000
+    pts, normals = synthetic.bumpy_sphere(n, seed=8)
+    r1 = 4.0 * synthetic.mean_spacing(n)
+    r2 = 1.5 * r1
+    kp = pts[::100]
+    # oracle: frames from r1 neighbourhoods, descriptors from r2 neighbourhoods (shot_parallelization.py:220-239)
+    tree = KDTree(pts)
+    n1, n2 = tree.query_radius(kp, r1), tree.query_radius(kp, r2)
+    want = np.zeros((kp.shape[0], 352))
+    want_ms = np.zeros((2, kp.shape[0], 352))
+    for i, p in enumerate(kp):
+        lrf = shot_oracle.local_reference_frame(p, pts[n1[i]], r1)
+        want[i] = shot_oracle.shot_descriptor(p, pts[n2[i]], normals[n2[i]], r2, lrf, True, 10)
+        want_ms[0, i] = shot_oracle.shot_descriptor(p, pts[n1[i]], normals[n1[i]], r1, lrf, True, 10)
+        want_ms[1, i] = want[i] * 0.5
+    with ShotMultiprocessor(min_neighborhood_size=10, verbose=False) as shot:
+        got = shot.compute_descriptor_bi_scale(pts, normals, kp, r1, r2)
+        got_ms = shot.compute_descriptor_multiscale(pts, normals, kp, [r1, r2], weights=[1.0, 0.5])
+    _check_rows(got, want, "bi_scale")
+    # the reference reshapes (S, Q, 352) -> (Q, 352 S) without transposing; same here
+    _check_rows(got_ms.reshape(2 * kp.shape[0], 352), want_ms.reshape(2 * kp.shape[0], 352), "multiscale")
+
+
+def test_subsampled_support_matches_oracle_on_the_same_support():
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+    from shot_fpfh_b200.subsampling import grid_subsampling
+
+    n = 30000
+    pts, normals = synthetic.bumpy_sphere(n, seed=9)
+    radius = 6.0 * synthetic.mean_spacing(n)
+    voxel = radius / 4.0
+    kp = pts[::150]
+    support = grid_subsampling(pts, voxel)
+    want = shot_oracle.shot_single_scale(pts[support], normals[support], kp, radius, True, 5)
+    with ShotMultiprocessor(min_neighborhood_size=5, verbose=False) as shot:
+        got = shot.compute_descriptor_single_scale(pts, normals, kp, radius, subsampling_voxel_size=voxel)
+    _check_rows(got, want, "subsampled support")
+
+
+def test_large_size_properties_1m():
+    """C2 size (1M points, ~100k queries): size-independent properties instead of the (too slow) oracle."""
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+
+    n = 1_000_000
+    pts, normals = synthetic.bumpy_sphere(n, seed=0)
+    s = synthetic.mean_spacing(n)
+    radius = 5.0 * s
+    kp_idx = synthetic.voxel_first_point_queries(pts, 3.75 * s)
+    kp = pts[kp_idx]
+    with ShotMultiprocessor(min_neighborhood_size=10, verbose=False) as shot:
+        d = shot.compute_descriptor_single_scale(pts, normals, kp, radius)
+        # (1) rows are unit-norm or exactly zero; (2) non-negative, finite
+        norms = np.linalg.norm(d, axis=1)
+        assert np.isfinite(d).all() and (d >= 0).all()
+        assert np.all((np.abs(norms - 1.0) < 1e-5) | (norms == 0.0))
+        assert (norms > 0).mean() > 0.99
+        # (3) determinism + independence from the query order: a permuted query set gives permuted rows
+        perm = np.random.default_rng(3).permutation(kp.shape[0])[:20000]
+        d2 = shot.compute_descriptor_single_scale(pts, normals, kp[perm], radius)
+        assert np.array_equal(d2, d[perm])
+        # (4) rigid-motion invariance: rotate + translate cloud, normals and queries -> same descriptors
+        rot = synthetic.rotation_from_rotvec(np.array([0.3, -0.2, 0.5]))
+        sub = perm[:5000]
+        d3 = shot.compute_descriptor_single_scale(pts @ rot.T + 0.5, normals @ rot.T, kp[sub] @ rot.T + 0.5, radius)
+    err = rel_l2(d3, d[sub])
+    print(f"1M rigid invariance: median {np.median(err):.2e}, rows above 1e-3: {(err > 1e-3).sum()} of {err.shape[0]}")
+    # NOT an exact invariance, in the reference either: when the sign vote of an axis is tied (5-9 % of the queries,
+    # sf_eigh3.cuh) the frame keeps LAPACK's eigenvector sign, which changes with the rotated covariance matrix
+    assert np.median(err) < 1e-5 and (err > 1e-3).mean() < 0.15
+    # (5) spot check of 300 rows against the oracle
+    rows = np.random.default_rng(4).choice(kp.shape[0], 300, replace=False)
+    want = shot_oracle.shot_single_scale(pts, normals, kp[rows], radius, True, 10)
+    _check_rows(d[rows], want, "1M spot check")
