@@ -1,0 +1,480 @@
+"""
+Benchmark of the hot path on B200 (contract: see the task statement; summary in DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--skip-extra]
+
+Headline workload (BASELINE.json configs[1], "C2"): SHOT single-scale on a seeded 1M-point synthetic surface scan,
+~100k grid-selected query points, radius = 5 x mean spacing, min_neighborhood_size = 10.
+One step = one pass of the whole entry point over one batch: grid build -> radius search (count, scan, fill)
+-> local reference frames -> 352-bin descriptors.
+  value : descriptors/s, inputs already resident in HBM, timed with CUDA events per step (L2 flushed between steps)
+  e2e   : the same through the reference-shaped API `ShotMultiprocessor.compute_descriptor_single_scale` with HOST
+          float64 arrays in pinned memory: H2D of cloud/normals/keypoints and D2H of the (Q, 352) float64 result
+          are inside the timed region
+  roofline    : dominant kernel, algorithmic bytes (SURVEY.md §8d formulas) / its CUDA-event duration vs measured HBM
+  cpu_baseline: the oracle port (NumPy restatement of the reference, multiprocessing like the reference) on a bounded
+                sample of the same workload on this host's cores
+`--impl reference` times that CPU arm alone (rank 0 only under torchrun).
+Multi-GPU (torchrun, one rank per GPU): queries shard by blocks with a replicated cloud and no data-path
+collective; each rank processes a full-size block (weak scaling), value = all ranks' descriptors / max time.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 1_000_000
+QUERY_VOXEL_IN_SPACINGS = 3.75
+RADIUS_IN_SPACINGS = 5.0
+MIN_NB = 10
+OWN_KERNELS_PER_SHOT_STEP = 9  # bbox_init, bbox, key, reorder, radius<count>, widen_total, radius<fill>, shot_lrf, shot_descriptor
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--skip-extra", action="store_true", help="only the headline SHOT workload")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "tflops": float(d["bf16_tflops"]),
+                "tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_shot_workload(rank: int = 0):
+    from shot_fpfh_b200 import synthetic
+
+    pts, normals = synthetic.bumpy_sphere(N_POINTS, seed=0)
+    s = synthetic.mean_spacing(N_POINTS)
+    kp_idx = synthetic.voxel_first_point_queries(pts, QUERY_VOXEL_IN_SPACINGS * s)
+    if rank:  # weak scaling: every rank gets its own full-size block of queries on the replicated cloud
+        kp_idx = np.sort(np.random.default_rng(100 + rank).choice(N_POINTS, kp_idx.shape[0], replace=False))
+    return pts, normals, np.ascontiguousarray(pts[kp_idx]), RADIUS_IN_SPACINGS * s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_shot_sample(pts, normals, kp, radius, seconds: float):
+    """Oracle port on a bounded sample. Returns (descriptors/s extrapolated to the full query set, info)."""
+    from sklearn.neighbors import KDTree
+
+    from oracle import shot_oracle
+
+    cores = os.cpu_count() or 1
+    n_procs = max(1, min(cores, 64))
+    t0 = time.perf_counter()
+    KDTree(pts)  # the reference builds the tree once per call (shot_parallelization.py:167)
+    t_tree = time.perf_counter() - t0
+    rng = np.random.default_rng(0)
+    n_cal = min(kp.shape[0], 250 * n_procs)
+    t0 = time.perf_counter()
+    shot_oracle.shot_single_scale_pool(pts, normals, kp[rng.choice(kp.shape[0], n_cal, replace=False)], radius, True,
+                                       MIN_NB, n_procs)
+    t_cal = time.perf_counter() - t0 - t_tree  # the pool driver rebuilds the tree
+    rate = n_cal / max(t_cal, 1e-6)
+    n_sample = int(min(kp.shape[0], max(n_cal, rate * max(seconds - t_cal - 2 * t_tree, 1.0))))
+    t0 = time.perf_counter()
+    shot_oracle.shot_single_scale_pool(pts, normals, kp[rng.choice(kp.shape[0], n_sample, replace=False)], radius, True,
+                                       MIN_NB, n_procs)
+    t_sample = time.perf_counter() - t0 - t_tree
+    full_time = t_tree + kp.shape[0] * t_sample / n_sample
+    info = {
+        "cores": n_procs,
+        "kind": "port",
+        "sample": (
+            f"oracle port (NumPy restatement of shot_parallelization.py:135-183, multiprocessing.Pool of {n_procs}) on "
+            f"{n_sample} of {kp.shape[0]} queries of the same 1M-point cloud: {t_sample:.2f} s + KDTree build "
+            f"{t_tree:.2f} s; value = Q / (tree + Q * per-query time)"
+        ),
+    }
+    return kp.shape[0] / full_time, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts, normals, kp, radius = make_shot_workload()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_shot_sample(pts, normals, kp, radius, seconds=max(4.0, args.cpu_seconds / 2))
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference",
+        "metric": "SHOT descriptors/sec",
+        "value": value,
+        "unit": "descriptors/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * kp.shape[0] / value,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: SHOT single-scale, 1M-point synthetic scan, %d queries, radius 5x spacing" % kp.shape[0]},
+        "cpu_baseline": {"value": value, "unit": "descriptors/s", **info},
+        "e2e": {"value": value, "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.file, stderr=subprocess.DEVNULL,
+            )
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        self.file.flush()
+        self.file.seek(0)
+        sm, mx, reasons = [], [], set()
+        for row in self.file.read().strip().splitlines():
+            f = [c.strip() for c in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.file.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c in sm if c >= 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def timed_steps(step_fn, steps: int, warmup: int, flush, dist=None):
+    """W untimed steps, then K steps each bracketed by CUDA events (L2 flushed, untimed, in between).
+    Returns (ms per step = max over ranks of the mean, list of per-stage event dicts)."""
+    import torch
+
+    for _ in range(warmup):
+        flush()
+        step_fn(None)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    marks = []
+    pairs = []
+    for _ in range(steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {}
+        a.record()
+        step_fn(stage)
+        b.record()
+        pairs.append((a, b))
+        marks.append(stage)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stages = {}
+    for st in marks:
+        for name, (e0, e1) in st.items():
+            stages.setdefault(name, []).append(e0.elapsed_time(e1))
+    return ms, {k: float(np.mean(v)) for k, v in stages.items()}
+
+
+def mark(stage, name):
+    """Context manager recording a CUDA-event pair on the current stream when `stage` is a dict."""
+    import contextlib
+
+    import torch
+
+    @contextlib.contextmanager
+    def cm():
+        if stage is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        stage[name] = (e0, e1)
+
+    return cm()
+
+
+def bench_shot(args, dist, rank, world, pk):
+    import torch
+
+    from shot_fpfh_b200 import ops
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+    from shot_fpfh_b200.device import Grid, upload
+
+    pts, normals, kp, radius = make_shot_workload(rank)
+    n, q = pts.shape[0], kp.shape[0]
+    dev = torch.device("cuda")
+    p_dev, n_dev, k_dev = upload(pts), upload(normals), upload(kp)
+    grid = Grid()
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 4x the 126 MB L2
+    out = torch.empty((q, 352), dtype=torch.float32, device=dev)
+    counts = {}
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def step(stage):
+        with mark(stage, "grid_build"):
+            grid.build(p_dev, n_dev, radius)
+        with mark(stage, "radius_search"):
+            offsets, nbr, _, _ = ops.radius_csr(grid, k_dev, radius)
+        with mark(stage, "shot_lrf"):
+            lrf = ops.shot_lrf(grid, k_dev, radius, offsets, nbr)
+        with mark(stage, "shot_descriptor"):
+            ops.shot_descriptor(grid, k_dev, radius, offsets, nbr, lrf, MIN_NB, True, out=out)
+        counts["pairs"] = int(nbr.shape[0])
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    ms, stages = timed_steps(step, args.steps, args.warmup, flush, dist)
+    clocks = sampler.stop()
+    pairs = counts["pairs"]
+    nonzero_rows = int((out.abs().sum(dim=1) > 0).sum().item())
+    value = world * q / (ms * 1e-3)
+
+    # algorithmic bytes per launch (float32 payloads, int32 indices)
+    alg = {
+        "grid_build": 52 * n,
+        "radius_search": 12 * n + 12 * q + 4 * pairs + 4 * (q + 1),
+        "shot_lrf": 16 * pairs + 12 * q + 36 * q,
+        "shot_descriptor": 28 * pairs + 48 * q + 4 * 352 * q,
+    }
+    dominant = max(stages, key=stages.get)
+    achieved = alg[dominant] / (stages[dominant] * 1e-3) / 1e9
+    roofline = {
+        "kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+        "algorithmic_bytes": alg[dominant], "kernel_ms": stages[dominant],
+        "per_stage": {k: {"ms": stages[k], "algorithmic_GBps": alg[k] / (stages[k] * 1e-3) / 1e9} for k in stages},
+    }
+
+    # ---- end to end through the reference-shaped API, host buffers in pinned memory ----
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+
+    h_pts, h_nrm, h_kp = pinned(pts), pinned(normals), pinned(kp)
+    e2e_times = []
+    with ShotMultiprocessor(min_neighborhood_size=MIN_NB, verbose=False) as shot:
+        for i in range(args.warmup + args.steps):
+            flush()
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            d = shot.compute_descriptor_single_scale(h_pts, h_nrm, h_kp, radius)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e2e_times.append(dt)
+    assert d.shape == (q, 352) and d.dtype == np.float64
+    e2e_ms = float(np.mean(e2e_times)) * 1e3
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {
+        "value": world * q / (e2e_ms * 1e-3), "unit": "descriptors/s", "ms_per_step": e2e_ms,
+        "h2d_bytes_per_step": int(h_pts.nbytes + h_nrm.nbytes + h_kp.nbytes), "d2h_bytes_per_step": int(d.nbytes),
+        "api": "ShotMultiprocessor.compute_descriptor_single_scale(point_cloud, normals, keypoints, radius) -> float64 (Q,352)",
+    }
+    config = {
+        "workload": f"C2: SHOT single-scale, 1M-point synthetic surface scan, {q} queries per GPU, radius 5x mean spacing",
+        "n_points": n, "queries_per_gpu": q, "neighbour_pairs": pairs, "mean_neighbours": pairs / q,
+        "min_neighborhood_size": MIN_NB, "nonzero_rows": nonzero_rows, "l2": "flushed between steps (512 MB write)",
+        "sharding": "queries by block, replicated cloud, no data-path collective" if world > 1 else "single GPU",
+        "output": "float32 (Q,352) resident in HBM for `value`; float64 on the host for `e2e`",
+    }
+    grid.close()
+    return {"ms": ms, "value": value, "roofline": roofline, "e2e": e2e, "config": config, "clocks": clocks,
+            "host": (pts, normals, kp, radius), "launches": OWN_KERNELS_PER_SHOT_STEP * args.steps}
+
+
+def bench_fpfh(args, pk):
+    """C3: FPFH 33-d on the full 1M-point cloud, every point a query."""
+    import torch
+
+    from shot_fpfh_b200 import ops, synthetic
+    from shot_fpfh_b200.device import Grid, upload
+
+    pts, normals = synthetic.bumpy_sphere(N_POINTS, seed=0)
+    radius = RADIUS_IN_SPACINGS * synthetic.mean_spacing(N_POINTS)
+    p_dev, n_dev = upload(pts), upload(normals)
+    kp = torch.arange(N_POINTS, dtype=torch.int64, device="cuda")
+    grid = Grid()
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    info = {}
+
+    def step(stage):
+        with mark(stage, "grid_build"):
+            grid.build(p_dev, n_dev, radius)
+        with mark(stage, "radius_search"):
+            offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
+        with mark(stage, "spfh"):
+            rows = ops.spfh(grid, offsets, nbr, 11, True)
+        with mark(stage, "fpfh"):
+            ops.fpfh(grid, offsets, nbr, dist, rows, kp, out_dtype=torch.float32)
+        info["pairs"] = int(nbr.shape[0])
+
+    steps = max(3, args.steps // 2)
+    ms, stages = timed_steps(step, steps, args.warmup, lambda: flush_buf.fill_(1))
+    p, n, d = info["pairs"], N_POINTS, 33
+    alg = {"grid_build": 52 * n, "radius_search": 12 * n + 12 * n + 12 * p + 4 * (n + 1), "spfh": 28 * p + 24 * n + 4 * d * n,
+           "fpfh": (4 * d + 8) * p + 4 * d * n + 4 * n}
+    dominant = max(stages, key=stages.get)
+    grid.close()
+    return {
+        "workload": "C3: FPFH 33-d (n_bins=11, decorrelated), 1M-point cloud, every point a query, 1 GPU",
+        "value": n / (ms * 1e-3), "unit": "descriptors/s", "ms_per_step": ms, "steps": steps, "neighbour_pairs": p,
+        "roofline": {"kernel": dominant, "bound": "hbm", "achieved": alg[dominant] / (stages[dominant] * 1e-3) / 1e9,
+                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg[dominant] / (stages[dominant] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "per_stage": {k: {"ms": stages[k], "algorithmic_GBps": alg[k] / (stages[k] * 1e-3) / 1e9} for k in stages}},
+    }
+
+
+def bench_match(args, pk, q: int = 200_000):
+    """C4: 200k x 200k 352-d exact NN (+ second NN for the ratio test): shortlist GEMM on tensor cores + fp64 re-rank."""
+    import torch
+
+    from shot_fpfh_b200 import ops, synthetic
+
+    a = torch.from_numpy(synthetic.sparse_unit_rows(q, 352, seed=2)).cuda().double()
+    b = torch.from_numpy(synthetic.sparse_unit_rows(q, 352, seed=3)).cuda().double()
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step(stage):
+        with mark(stage, "nonempty_pack"):
+            ra, rb = ops.nonempty_rows(a), ops.nonempty_rows(b)
+            ap, _ = ops.match_pack(a, ra, 1.0)
+            bp, bn = ops.match_pack(b, rb, 1.0)
+        with mark(stage, "shortlist_gemm"):
+            _, cand = ops.match_topk(ap, bp, bn, 8, 0, True)
+        with mark(stage, "rerank_f64"):
+            ops.match_rerank(a, ra, b, rb, cand)
+
+    steps = max(3, args.steps // 3)
+    ms, stages = timed_steps(step, steps, min(args.warmup, 3), lambda: flush_buf.fill_(1))
+    flops = 2.0 * q * q * 352
+    tf = flops / (stages["shortlist_gemm"] * 1e-3) / 1e12
+    return {
+        "workload": f"C4: {q} x {q} x 352 exact nearest + second-nearest neighbour, synthetic sparse unit rows, 1 GPU",
+        "value": q / (ms * 1e-3), "unit": "match queries/s", "ms_per_step": ms, "steps": steps,
+        "roofline": {"kernel": "topk_tc_kernel", "bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": tf / pk["tflops"], "flops": flops,
+                     "per_stage_ms": stages},
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk = peaks()
+    res = bench_shot(args, dist, rank, world, pk)
+    extra = {}
+    cpu = None
+    if rank == 0 and world == 1:
+        pts, normals, kp, radius = res["host"]
+        v, info = cpu_shot_sample(pts, normals, kp, radius, args.cpu_seconds)
+        cpu = {"value": v, "unit": "descriptors/s", **info}
+        if not args.skip_extra:
+            for name, fn in (("fpfh_c3", bench_fpfh), ("match_c4", bench_match)):
+                try:
+                    extra[name] = fn(args, pk)
+                except Exception as exc:  # noqa: BLE001  (the headline line must still be printed)
+                    extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    if rank == 0:
+        line = {
+            "metric": "SHOT descriptors/sec",
+            "value": res["value"],
+            "unit": "descriptors/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": res["ms"],
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": res["config"],
+            "roofline": res["roofline"],
+            "cpu_baseline": cpu,
+            "e2e": res["e2e"],
+            "gpu_launches": res["launches"],
+            "clocks": res["clocks"],
+            "extra": extra,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
