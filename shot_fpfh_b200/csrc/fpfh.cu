@@ -57,38 +57,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int kRegs, typename OutT>
+// One warp per keypoint. The neighbour list is consumed in chunks of 32: each lane loads one (index, 1/d) pair,
+// then the pairs are broadcast by shuffle and every lane accumulates its own bins — the row loads of consecutive
+// neighbours are independent, so several are in flight at once. Column blocks of 32 bins are register tiles;
+// a remainder of at most 4 columns (e.g. bin 32 of the 33-bin layout) is handled lane-per-neighbour and reduced.
+template <int kBlocks, typename OutT>
 __global__ void __launch_bounds__(256)
     fpfh_kernel(const int32_t* __restrict__ inv_perm, const int64_t* __restrict__ offsets,
                 const int32_t* __restrict__ nbr, const double* __restrict__ dist, const float* __restrict__ spfh,
-                int width, int bin_base, const int64_t* __restrict__ keypoints, int64_t nq, OutT* __restrict__ out) {
+                int width, int bin_base, int rem, const int64_t* __restrict__ keypoints, int64_t nq,
+                OutT* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (q >= nq) return;
   const int64_t s = inv_perm[keypoints[q]];
   const int64_t begin = offsets[s], end = offsets[s + 1];
-  double acc[kRegs];
+  float acc[kBlocks];
 #pragma unroll
-  for (int r = 0; r < kRegs; ++r) acc[r] = 0.0;
-  for (int64_t i = begin; i < end; ++i) {
-    const double d = __ldg(dist + i);
-    if (d > 0.0) {  // fpfh.py:112-114: the tree's own distances decide
-      const double w = 1.0 / d;
-      const float* row = spfh + int64_t(__ldg(nbr + i)) * width + bin_base;
+  for (int r = 0; r < kBlocks; ++r) acc[r] = 0.0f;
+  float tail[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const int rem_base = bin_base + 32 * kBlocks;
+  const bool last_ok = bin_base + lane + 32 * (kBlocks - 1) < width;
+  for (int64_t base = begin; base < end; base += 32) {
+    const int64_t i = base + lane;
+    int my_j = 0;
+    float my_w = 0.0f;
+    if (i < end) {
+      const double d = __ldg(dist + i);
+      my_j = __ldg(nbr + i);
+      my_w = d > 0.0 ? float(1.0 / d) : 0.0f;  // fpfh.py:112-114: the tree's own distances decide
+    }
+    const int cnt = int(end - base < 32 ? end - base : 32);
+    if (rem > 0 && my_w != 0.0f) {
+      const float* row = spfh + int64_t(my_j) * width + rem_base;
+      for (int c = 0; c < rem; ++c) tail[c] += __ldg(row + c) * my_w;
+    }
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const int j = __shfl_sync(kFull, my_j, t);
+      const float w = __shfl_sync(kFull, my_w, t);
+      const float* row = spfh + int64_t(j) * width + bin_base + lane;
 #pragma unroll
-      for (int r = 0; r < kRegs; ++r) {
-        const int b = lane + 32 * r;
-        if (bin_base + b < width) acc[r] += double(__ldg(row + b)) * w;
-      }
+      for (int r = 0; r < kBlocks; ++r)  // w == 0 contributes 0; the last block may be partially masked
+        if (r < kBlocks - 1 || last_ok) acc[r] = fmaf(__ldg(row + 32 * r), w, acc[r]);
     }
   }
-  const double k_all = double(end - begin);
-  const float* own = spfh + s * width + bin_base;
+  const float k_all = float(end - begin);
+  const float* own = spfh + s * width;
+  OutT* dst = out + q * int64_t(width);
 #pragma unroll
-  for (int r = 0; r < kRegs; ++r) {
-    const int b = lane + 32 * r;
-    if (bin_base + b < width)
-      out[q * int64_t(width) + bin_base + b] = OutT(end > begin ? double(own[b]) + acc[r] / k_all : 0.0);
+  for (int r = 0; r < kBlocks; ++r) {
+    const int b = bin_base + lane + 32 * r;
+    if (b < width) dst[b] = OutT(end > begin ? own[b] + acc[r] / k_all : 0.0f);
+  }
+  for (int c = 0; c < rem; ++c) {
+    const float total = warp_sum(tail[c]);
+    if (lane == 0) dst[rem_base + c] = OutT(end > begin ? own[rem_base + c] + total / k_all : 0.0f);
   }
 }
 
@@ -127,14 +151,28 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
                        int width, const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
   const int64_t threads = nq * 32;
   const unsigned blocks = unsigned((threads + 255) / 256);
-  for (int base = 0; base < width; base += 128) {
+  // Passes of up to 4 column blocks of 32 bins (register tiles). A final partial block is masked, except when it
+  // is at most 4 columns wide and follows a full block (the 33-bin layout): then it rides along as the "tail".
+  int base = 0;
+  while (base < width) {
     const int left = width - base;
-    if (left <= 32)
-      fpfh_kernel<1, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, keypoints, nq, out);
-    else if (left <= 64)
-      fpfh_kernel<2, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, keypoints, nq, out);
-    else
-      fpfh_kernel<4, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, keypoints, nq, out);
+    int blocks_n = left / 32 < 4 ? left / 32 : 4;
+    int rem = 0;
+    if (blocks_n < 4) {
+      const int r = left - blocks_n * 32;
+      if (r > 0 && r <= 4 && blocks_n >= 1) rem = r;
+      else if (r > 0) blocks_n += 1;
+    }
+#define SF_LAUNCH_FPFH(B) \
+  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, rem, keypoints, nq, out)
+    switch (blocks_n) {
+      case 1: SF_LAUNCH_FPFH(1); break;
+      case 2: SF_LAUNCH_FPFH(2); break;
+      case 3: SF_LAUNCH_FPFH(3); break;
+      default: SF_LAUNCH_FPFH(4); break;
+    }
+#undef SF_LAUNCH_FPFH
+    base += blocks_n * 32 + rem;
   }
   SF_CUDA(cudaGetLastError());
   return SF_OK;

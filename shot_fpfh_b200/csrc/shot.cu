@@ -12,54 +12,86 @@
 namespace sf {
 
 // ---- S1 ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// One warp owns a batch of 32 consecutive queries. Phase A: the 32 lanes stride over the neighbours of query j and
+// reduce its 7 weighted moments, which lane j keeps. Phase B: every lane solves ITS OWN query's 3x3 eigenproblem
+// (the LAPACK-path solver is a long serial chain: one per lane = 32 in flight, instead of 32 lanes redundantly
+// solving one). Phase C: the axes of lane j are broadcast and the warp counts the sign votes of query j.
+__global__ void __launch_bounds__(128)
     shot_lrf_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
                     const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr, double* __restrict__ lrf) {
   const int lane = threadIdx.x & 31;
-  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
-  if (q >= nq) return;
-  const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
-  const int64_t begin = offsets[q], end = offsets[q + 1];
-  double* out = lrf + 9 * q;
-  if (end == begin) {  // shot.py:24-25
-    if (lane < 9) out[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
-    return;
-  }
-  // weighted covariance, weights (radius - distance), over ALL neighbours incl. the query itself (F5)
-  double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
-  for (int64_t i = begin + lane; i < end; i += 32) {
-    const double4 p = load_pt(g.pts + __ldg(nbr + i));
-    const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
-    const double w = radius - sqrt(rdist3(cx, cy, cz));
-    sw += w;
-    m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
-    m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
-  }
-  sw = warp_sum(sw);
+  const int64_t q0 = ((blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5) * 32;
+  if (q0 >= nq) return;
+  const int batch = int(nq - q0 < 32 ? nq - q0 : 32);
+  // this lane's query
+  const int64_t mine = q0 + (lane < batch ? lane : 0);
+  const int64_t my_begin = __ldg(offsets + mine), my_end = __ldg(offsets + mine + 1);
+  const double my_qx = __ldg(queries + 3 * mine), my_qy = __ldg(queries + 3 * mine + 1), my_qz = __ldg(queries + 3 * mine + 2);
+  // ---- phase A: weighted covariance, weights (radius - distance), over ALL neighbours incl. the query itself (F5)
+  double mom[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < batch; ++j) {
+    const int64_t begin = __shfl_sync(kFull, my_begin, j), end = __shfl_sync(kFull, my_end, j);
+    const double qx = __shfl_sync(kFull, my_qx, j), qy = __shfl_sync(kFull, my_qy, j), qz = __shfl_sync(kFull, my_qz, j);
+    double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = begin + lane; i < end; i += 32) {
+      const double4 p = load_pt(g.pts + __ldg(nbr + i));
+      const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+      const double w = radius - sqrt(rdist3(cx, cy, cz));
+      sw += w;
+      m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
+      m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
+    }
+    sw = warp_sum(sw);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) m[k] = warp_sum(m[k]) / sw;
-  double eval[3], evec[3][3];
-  eigh3(m, eval, evec);  // every lane computes the same decomposition
-  double x[3] = {evec[2][0], evec[2][1], evec[2][2]};  // largest eigenvalue
-  double z[3] = {evec[0][0], evec[0][1], evec[0][2]};  // smallest eigenvalue
-  // sign votes (shot.py:40-45): flip when strictly more neighbours project negatively than non-negatively
-  int neg_x = 0, neg_z = 0;
-  for (int64_t i = begin + lane; i < end; i += 32) {
-    const double4 p = load_pt(g.pts + __ldg(nbr + i));
-    const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
-    neg_x += (cx * x[0] + cy * x[1] + cz * x[2]) < 0.0;
-    neg_z += (cx * z[0] + cy * z[1] + cz * z[2]) < 0.0;
+    for (int k = 0; k < 6; ++k) {
+      const double v = warp_sum(m[k]) / sw;
+      if (lane == j) mom[k] = v;
+    }
   }
-  neg_x = warp_sum(neg_x);
-  neg_z = warp_sum(neg_z);
-  const int k_all = int(end - begin);
-  if (neg_x > k_all - neg_x) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
-  if (neg_z > k_all - neg_z) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
-  const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
-  if (lane < 3) {  // row `lane` of the matrix whose columns are [x y z]
-    out[3 * lane + 0] = x[lane];
-    out[3 * lane + 1] = y[lane];
-    out[3 * lane + 2] = z[lane];
+  // ---- phase B: one eigen-decomposition per lane
+  double x[3] = {1, 0, 0}, z[3] = {0, 0, 1};
+  const bool has_neighbours = lane < batch && my_end > my_begin;
+  if (has_neighbours) {
+    double eval[3], evec[3][3];
+    eigh3(mom, eval, evec);
+    x[0] = evec[2][0]; x[1] = evec[2][1]; x[2] = evec[2][2];  // largest eigenvalue
+    z[0] = evec[0][0]; z[1] = evec[0][1]; z[2] = evec[0][2];  // smallest eigenvalue
+  }
+  // ---- phase C: sign votes (shot.py:40-45): flip when strictly more neighbours project negatively than not
+  int my_neg_x = 0, my_neg_z = 0;
+  for (int j = 0; j < batch; ++j) {
+    const int64_t begin = __shfl_sync(kFull, my_begin, j), end = __shfl_sync(kFull, my_end, j);
+    const double qx = __shfl_sync(kFull, my_qx, j), qy = __shfl_sync(kFull, my_qy, j), qz = __shfl_sync(kFull, my_qz, j);
+    const double x0 = __shfl_sync(kFull, x[0], j), x1 = __shfl_sync(kFull, x[1], j), x2 = __shfl_sync(kFull, x[2], j);
+    const double z0 = __shfl_sync(kFull, z[0], j), z1 = __shfl_sync(kFull, z[1], j), z2 = __shfl_sync(kFull, z[2], j);
+    int neg_x = 0, neg_z = 0;
+    for (int64_t i = begin + lane; i < end; i += 32) {
+      const double4 p = load_pt(g.pts + __ldg(nbr + i));
+      const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+      neg_x += (cx * x0 + cy * x1 + cz * x2) < 0.0;
+      neg_z += (cx * z0 + cy * z1 + cz * z2) < 0.0;
+    }
+    neg_x = warp_sum(neg_x);
+    neg_z = warp_sum(neg_z);
+    if (lane == j) { my_neg_x = neg_x; my_neg_z = neg_z; }
+  }
+  if (lane < batch) {
+    double* out = lrf + 9 * mine;
+    if (!has_neighbours) {  // shot.py:24-25
+#pragma unroll
+      for (int k = 0; k < 9; ++k) out[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    } else {
+      const int k_all = int(my_end - my_begin);
+      if (my_neg_x > k_all - my_neg_x) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
+      if (my_neg_z > k_all - my_neg_z) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
+      const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {  // row a of the matrix whose columns are [x y z]
+        out[3 * a + 0] = x[a];
+        out[3 * a + 1] = y[a];
+        out[3 * a + 2] = z[a];
+      }
+    }
   }
 }
 
@@ -151,9 +183,8 @@ extern "C" int sf_shot_lrf(sf_grid* g, const double* queries, int64_t nq, double
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_shot_lrf: grid not built");
   SF_REQUIRE(queries && offsets && lrf && nq >= 0, SF_ERR_ARG, "sf_shot_lrf: bad arguments");
   if (nq == 0) return SF_OK;
-  const int64_t threads = nq * 32;
-  shot_lrf_kernel<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(g->view(), queries, nq, radius, offsets, nbr,
-                                                                      lrf);
+  const int64_t warps = (nq + 31) / 32;  // one warp per batch of 32 queries
+  shot_lrf_kernel<<<unsigned((warps + 3) / 4), 128, 0, stream>>>(g->view(), queries, nq, radius, offsets, nbr, lrf);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -17,7 +17,7 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import Grid, upload
+from ..device import Grid, download, upload
 
 
 def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
@@ -52,6 +52,6 @@ def compute_fpfh_descriptor(
     out, mean_k = fpfh_device(grid, upload(kp, torch.int64), float(radius), int(n_bins), bool(decorrelated))
     if verbose:
         logging.info(f"Mean neighborhood size over the whole point cloud: {mean_k:.2f}")
-    result = out.cpu().numpy()
+    result = download(out)
     grid.close()
     return result

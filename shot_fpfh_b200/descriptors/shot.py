@@ -15,7 +15,7 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import Grid, upload
+from ..device import Grid, download, upload
 from ..neighbors import explicit_csr
 
 
@@ -106,7 +106,7 @@ def compute_shot_descriptor(
     nbr_pos = nbr[keep].contiguous()
     lrf = ops.shot_lrf(grid, kp, radius, offsets_pos, nbr_pos)
     desc = ops.shot_descriptor(grid, kp, radius, offsets_pos, nbr_pos, lrf, int(min_neighborhood_size), True)
-    out = desc.cpu().numpy()
+    out = download(desc)
     grid.close()
     return out
 

@@ -21,7 +21,7 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import Grid, require_cuda, upload
+from ..device import Grid, download, require_cuda, upload
 from ..subsampling import grid_subsampling
 
 
@@ -88,8 +88,7 @@ class ShotMultiprocessor:
 
     @staticmethod
     def _to_host(t: torch.Tensor) -> npt.NDArray[np.float64]:
-        out = t.cpu().numpy()
-        return out if out.dtype == np.float64 else out.astype(np.float64)
+        return download(t if t.dtype == torch.float64 else t.double())
 
     # ------------------------------------------------------------------------------------------------------
     def compute_local_rf(

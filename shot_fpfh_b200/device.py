@@ -40,6 +40,19 @@ def upload(a, dtype=torch.float64) -> torch.Tensor:
     return torch.from_numpy(host).to(dev, non_blocking=True)
 
 
+def download(t: torch.Tensor) -> np.ndarray:
+    """
+    Device tensor -> fresh host NumPy array, through page-locked memory: a pageable destination makes the driver
+    stage the copy and costs ~10x (measured: 288 MB of SHOT rows, 100+ ms pageable vs ~12 ms pinned). The array
+    is backed by a block of PyTorch's caching pinned allocator; the block goes back to the cache when the array
+    (and every view of it) is released, so repeated calls do not re-pin memory.
+    """
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 class Grid:
     """Owner of one `sf_grid` handle (uniform grid over a cloud, see csrc/grid.cu)."""
 

@@ -1,0 +1,73 @@
+"""
+Drop-in installation: rebinds the hot-path names of an importable reference `shot_fpfh` package to the B200
+implementations, so that its `RegistrationPipeline` (pipeline.py) and `scripts/register_point_clouds.py` run
+UNCHANGED on top of the CUDA kernels.
+
+    import shot_fpfh_b200.dropin as dropin
+    dropin.install()                      # before or after `import shot_fpfh`
+    from shot_fpfh import RegistrationPipeline   # the reference's own orchestration, untouched
+
+What is replaced (SURVEY.md §8b — exactly what pipeline.py imports at :15 and :24-30, plus the deeper helpers):
+    shot_fpfh.descriptors.ShotMultiprocessor / compute_fpfh_descriptor   (and in shot_fpfh.pipeline's namespace)
+    shot_fpfh.descriptors.shot.{get_local_rf, compute_single_shot_descriptor, compute_shot_descriptor}
+    shot_fpfh.matching.{basic_matching, match_descriptors, double_matching_with_rejects}
+Everything else (keypoint selection, RANSAC, ICP, I/O, configuration, analysis) stays the reference's code.
+"""
+
+from __future__ import annotations
+
+import importlib
+import sys
+
+_REPLACED: dict[tuple[str, str], object] = {}
+
+
+def _bind(module_name: str, attr: str, value) -> None:
+    module = importlib.import_module(module_name)
+    key = (module_name, attr)
+    if key not in _REPLACED:
+        _REPLACED[key] = getattr(module, attr, None)
+    setattr(module, attr, value)
+
+
+def install() -> list[str]:
+    """Rebinds the names; returns the list of `module.attr` that were replaced. Needs the built CUDA library."""
+    from . import descriptors as d
+    from . import matching as m
+    from .descriptors import shot as s
+
+    importlib.import_module("shot_fpfh")  # raises ImportError if the reference package is not importable
+    plan = [
+        ("shot_fpfh.descriptors.shot_parallelization", "ShotMultiprocessor", d.ShotMultiprocessor),
+        ("shot_fpfh.descriptors", "ShotMultiprocessor", d.ShotMultiprocessor),
+        ("shot_fpfh.descriptors.fpfh", "compute_fpfh_descriptor", d.compute_fpfh_descriptor),
+        ("shot_fpfh.descriptors", "compute_fpfh_descriptor", d.compute_fpfh_descriptor),
+        ("shot_fpfh.descriptors.shot", "get_local_rf", s.get_local_rf),
+        ("shot_fpfh.descriptors.shot", "compute_single_shot_descriptor", s.compute_single_shot_descriptor),
+        ("shot_fpfh.descriptors.shot", "compute_shot_descriptor", s.compute_shot_descriptor),
+        ("shot_fpfh.matching.matching", "basic_matching", m.basic_matching),
+        ("shot_fpfh.matching.matching", "match_descriptors", m.match_descriptors),
+        ("shot_fpfh.matching.matching", "double_matching_with_rejects", m.double_matching_with_rejects),
+        ("shot_fpfh.matching", "basic_matching", m.basic_matching),
+        ("shot_fpfh.matching", "match_descriptors", m.match_descriptors),
+        ("shot_fpfh.matching", "double_matching_with_rejects", m.double_matching_with_rejects),
+        # pipeline.py did `from shot_fpfh.descriptors import ...` / `from shot_fpfh.matching import ...`
+        ("shot_fpfh.pipeline", "ShotMultiprocessor", d.ShotMultiprocessor),
+        ("shot_fpfh.pipeline", "compute_fpfh_descriptor", d.compute_fpfh_descriptor),
+        ("shot_fpfh.pipeline", "basic_matching", m.basic_matching),
+        ("shot_fpfh.pipeline", "match_descriptors", m.match_descriptors),
+        ("shot_fpfh.pipeline", "double_matching_with_rejects", m.double_matching_with_rejects),
+    ]
+    done = []
+    for module_name, attr, value in plan:
+        _bind(module_name, attr, value)
+        done.append(f"{module_name}.{attr}")
+    return done
+
+
+def uninstall() -> None:
+    """Restores the reference's own functions."""
+    for (module_name, attr), value in _REPLACED.items():
+        if module_name in sys.modules and value is not None:
+            setattr(sys.modules[module_name], attr, value)
+    _REPLACED.clear()
