@@ -44,8 +44,8 @@ OWN_KERNELS_PER_SHOT_STEP = 9  # bbox_init, bbox, key, reorder, radius<count>, w
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=40)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--skip-extra", action="store_true", help="only the headline SHOT workload")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
@@ -157,7 +157,7 @@ class ClockSampler:
         self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.file, stderr=subprocess.DEVNULL,
             )
         except OSError:
@@ -185,8 +185,8 @@ class ClockSampler:
         os.unlink(self.file.name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c in sm if c >= 0.5 * max(sm)]
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def timed_steps(step_fn, steps: int, warmup: int, flush, dist=None):

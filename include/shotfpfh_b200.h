@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 1
+#define SF_ABI_VERSION 2
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -60,17 +60,19 @@ int sf_grid_permutation(const sf_grid* grid, int32_t* perm_out_dev, int32_t* inv
  * G — fixed-radius search.  Replaces `KDTree.query_radius(X, r[, return_distance=True])`
  * (shot_parallelization.py:167-169, fpfh.py:28-30). Predicate: ((dx*dx + dy*dy) + dz*dz) <= r*r in float64,
  * inclusive, the query point itself included when it belongs to the cloud — sklearn's, bit for bit.
- * queries_dev == NULL means "the cloud's own points in cell-sorted order" (nq is then the cloud size).
+ * queries_dev == NULL means "the cloud's own points at cell-sorted positions [self_first, self_first + nq)" (the
+ * FPFH case; a sub-range is what one rank of a multi-GPU job searches); self_first is ignored otherwise.
  * ---------------------------------------------------------------------------------------------------------- */
 /* Pass 1: offsets_dev[0..nq] (exclusive prefix of the neighbour counts). When total_host != NULL the total is
  * copied to the host and `stream` is synchronised. */
-int sf_radius_count(sf_grid* grid, const double* queries_dev, int64_t nq, double radius, int64_t* offsets_dev,
-                    int64_t* total_host, void* stream);
+int sf_radius_count(sf_grid* grid, const double* queries_dev, int64_t self_first, int64_t nq, double radius,
+                    int64_t* offsets_dev, int64_t* total_host, void* stream);
 /* Pass 2: any of the three outputs may be NULL. nbr_sorted_dev: cell-sorted positions (what the descriptor
  * kernels consume); nbr_index_dev: original point indices (what query_radius returns, in grid-walk order);
  * dist_dev: float64 sqrt of the reduced distance (what return_distance=True returns). */
-int sf_radius_fill(sf_grid* grid, const double* queries_dev, int64_t nq, double radius, const int64_t* offsets_dev,
-                   int32_t* nbr_sorted_dev, int32_t* nbr_index_dev, double* dist_dev, void* stream);
+int sf_radius_fill(sf_grid* grid, const double* queries_dev, int64_t self_first, int64_t nq, double radius,
+                   const int64_t* offsets_dev, int32_t* nbr_sorted_dev, int32_t* nbr_index_dev, double* dist_dev,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * S — SHOT.
@@ -91,15 +93,19 @@ int sf_shot_descriptor(sf_grid* grid, const double* queries_dev, int64_t nq, dou
 /* ------------------------------------------------------------------------------------------------------------
  * P — FPFH.  Replaces `compute_fpfh_descriptor` (fpfh.py:16-117).
  * ---------------------------------------------------------------------------------------------------------- */
-/* Stage 1 (fpfh.py:38-90): SPFH of every cloud point, rows in CELL-SORTED order. offsets/nbr_sorted: the CSR of
- * sf_radius_* called with queries_dev == NULL. edges_host: float64 (3, n_bins + 1) histogram edges
+/* Stage 1 (fpfh.py:38-90): SPFH of the cloud points at cell-sorted positions [first, first + count), rows written
+ * in that order to spfh_dev (count, width). offsets/nbr_sorted: the CSR of sf_radius_* called with
+ * queries_dev == NULL on the same range. edges_host: float64 (3, n_bins + 1) histogram edges
  * (np.linspace(lo, hi, n_bins + 1) for alpha, phi, theta). width = 3*n_bins (decorrelated) or n_bins^3. */
-int sf_spfh(sf_grid* grid, const int64_t* offsets_dev, const int32_t* nbr_sorted_dev, int32_t n_bins,
-            int32_t decorrelated, const double* edges_host, float* spfh_dev, void* stream);
-/* Stage 2 (fpfh.py:97-116) on keypoints given as ORIGINAL point indices. dist_dev: the CSR distances. */
+int sf_spfh(sf_grid* grid, int64_t first, int64_t count, const int64_t* offsets_dev, const int32_t* nbr_sorted_dev,
+            int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh_dev, void* stream);
+/* Stage 2 (fpfh.py:97-116) on keypoints given as ORIGINAL point indices. spfh_dev: the SPFH rows of the WHOLE
+ * cloud in cell-sorted order. The CSR (with its distances) is either the self-search of the whole cloud
+ * (csr_by_keypoint = 0: row = cell-sorted position of the keypoint) or a search around the keypoints'
+ * coordinates (csr_by_keypoint = 1: row q belongs to keypoint q). */
 int sf_fpfh(sf_grid* grid, const int64_t* offsets_dev, const int32_t* nbr_sorted_dev, const double* dist_dev,
-            const float* spfh_dev, int32_t width, const int64_t* keypoint_index_dev, int64_t nq, void* out_dev,
-            int32_t out_is_f64, void* stream);
+            int32_t csr_by_keypoint, const float* spfh_dev, int32_t width, const int64_t* keypoint_index_dev,
+            int64_t nq, void* out_dev, int32_t out_is_f64, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * M — descriptor matching.  Replaces `cdist(...).argmin(axis=1)` in `basic_matching` (matching.py:162-169),

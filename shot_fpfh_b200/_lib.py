@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libshotfpfh_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SF_OK, SF_ERR_CUDA, SF_ERR_ARG, SF_ERR_CAPACITY = 0, 1, 2, 3
 
@@ -41,16 +41,19 @@ def _load() -> ctypes.CDLL:
         "sf_grid_build": [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p],
         "sf_grid_info": [c_void_p, p_i64, p_i64, p_f64, p_i32],
         "sf_grid_permutation": [c_void_p, c_void_p, c_void_p, c_void_p],
-        "sf_radius_count": [c_void_p, c_void_p, c_int64, c_double, c_void_p, p_i64, c_void_p],
-        "sf_radius_fill": [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+        "sf_radius_count": [c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, p_i64, c_void_p],
+        "sf_radius_fill": [
+            c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+        ],
         "sf_shot_lrf": [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p],
         "sf_shot_descriptor": [
             c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
             c_void_p,
         ],
-        "sf_spfh": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, p_f64, c_void_p, c_void_p],
+        "sf_spfh": [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, p_f64, c_void_p, c_void_p],
         "sf_fpfh": [
-            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
+            c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32,
+            c_void_p,
         ],
         "sf_nonempty_rows": [c_void_p, c_int64, c_int32, c_void_p, p_i64, c_void_p],
         "sf_match_pack": [c_void_p, c_int32, c_void_p, c_int64, c_double, c_void_p, c_int32, c_void_p, c_void_p],

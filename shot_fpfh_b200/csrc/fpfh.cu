@@ -12,19 +12,19 @@ constexpr int kMaxBins = 64;
 __constant__ double c_edges[3][kMaxBins + 1];
 
 __global__ void __launch_bounds__(256)
-    spfh_kernel(GridView g, const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr, int n_bins,
-                int decorrelated, int width, float* __restrict__ spfh) {
+    spfh_kernel(GridView g, int64_t first, int64_t count, const int64_t* __restrict__ offsets,
+                const int32_t* __restrict__ nbr, int n_bins, int decorrelated, int width, float* __restrict__ spfh) {
   extern __shared__ int hist_mem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   int* hist = hist_mem + warp * width;
   const int64_t warps_total = int64_t(gridDim.x) * warps_per_block;
-  for (int64_t s = blockIdx.x * int64_t(warps_per_block) + warp; s < g.n; s += warps_total) {
+  for (int64_t s = blockIdx.x * int64_t(warps_per_block) + warp; s < count; s += warps_total) {
     for (int b = lane; b < width; b += 32) hist[b] = 0;
     __syncwarp();
-    const double4 p = load_pt(g.pts + s);
-    const double4 un = load_pt(g.nrm + s);
+    const double4 p = load_pt(g.pts + first + s);
+    const double4 un = load_pt(g.nrm + first + s);
     const double u[3] = {un.x, un.y, un.z};
     const int64_t begin = offsets[s], end = offsets[s + 1];
     for (int64_t i = begin + lane; i < end; i += 32) {
@@ -64,14 +64,15 @@ __global__ void __launch_bounds__(256)
 template <int kBlocks, typename OutT>
 __global__ void __launch_bounds__(256)
     fpfh_kernel(const int32_t* __restrict__ inv_perm, const int64_t* __restrict__ offsets,
-                const int32_t* __restrict__ nbr, const double* __restrict__ dist, const float* __restrict__ spfh,
-                int width, int bin_base, int rem, const int64_t* __restrict__ keypoints, int64_t nq,
-                OutT* __restrict__ out) {
+                const int32_t* __restrict__ nbr, const double* __restrict__ dist, int csr_by_keypoint,
+                const float* __restrict__ spfh, int width, int bin_base, int rem,
+                const int64_t* __restrict__ keypoints, int64_t nq, OutT* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (q >= nq) return;
   const int64_t s = inv_perm[keypoints[q]];
-  const int64_t begin = offsets[s], end = offsets[s + 1];
+  const int64_t row_id = csr_by_keypoint ? q : s;  // CSR rows follow the keypoints, or every cell-sorted point
+  const int64_t begin = offsets[row_id], end = offsets[row_id + 1];
   float acc[kBlocks];
 #pragma unroll
   for (int r = 0; r < kBlocks; ++r) acc[r] = 0.0f;
@@ -120,11 +121,13 @@ __global__ void __launch_bounds__(256)
 
 using namespace sf;
 
-extern "C" int sf_spfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, int32_t n_bins, int32_t decorrelated,
-                       const double* edges_host, float* spfh, void* stream_) {
+extern "C" int sf_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* offsets, const int32_t* nbr,
+                       int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_spfh: grid built without normals");
   SF_REQUIRE(offsets && nbr && edges_host && spfh, SF_ERR_ARG, "sf_spfh: null argument");
+  SF_REQUIRE(first >= 0 && count >= 0 && first + count <= g->n, SF_ERR_ARG, "sf_spfh: point range outside the cloud");
+  if (count == 0) return SF_OK;
   SF_REQUIRE(n_bins >= 1 && n_bins <= kMaxBins, SF_ERR_CAPACITY, "sf_spfh: n_bins must be in [1, %d]", kMaxBins);
   const int64_t width64 = decorrelated ? 3 * int64_t(n_bins) : int64_t(n_bins) * n_bins * n_bins;
   SF_REQUIRE(width64 <= 8192, SF_ERR_CAPACITY, "sf_spfh: histogram width %lld exceeds 8192", (long long)width64);
@@ -139,16 +142,17 @@ extern "C" int sf_spfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, i
   const size_t smem = size_t(warps) * width * sizeof(int);
   if (smem > 48 * 1024)
     SF_CUDA(cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int64_t blocks_needed = (g->n + warps - 1) / warps;
+  const int64_t blocks_needed = (count + warps - 1) / warps;
   const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
-  spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), offsets, nbr, n_bins, decorrelated, width, spfh);
+  spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, nbr, n_bins, decorrelated, width,
+                                                    spfh);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
 
 template <typename OutT>
-static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist, const float* spfh,
-                       int width, const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
+static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist, int by_kp,
+                       const float* spfh, int width, const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
   const int64_t threads = nq * 32;
   const unsigned blocks = unsigned((threads + 255) / 256);
   // Passes of up to 4 column blocks of 32 bins (register tiles). A final partial block is masked, except when it
@@ -164,7 +168,7 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
       else if (r > 0) blocks_n += 1;
     }
 #define SF_LAUNCH_FPFH(B) \
-  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, spfh, width, base, rem, keypoints, nq, out)
+  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, by_kp, spfh, width, base, rem, keypoints, nq, out)
     switch (blocks_n) {
       case 1: SF_LAUNCH_FPFH(1); break;
       case 2: SF_LAUNCH_FPFH(2); break;
@@ -178,13 +182,13 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
   return SF_OK;
 }
 
-extern "C" int sf_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist, const float* spfh,
-                       int32_t width, const int64_t* keypoints, int64_t nq, void* out, int32_t out_is_f64,
+extern "C" int sf_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist,
+                       int32_t csr_by_keypoint, const float* spfh, int32_t width, const int64_t* keypoints, int64_t nq, void* out, int32_t out_is_f64,
                        void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_fpfh: grid not built");
   SF_REQUIRE(offsets && nbr && dist && spfh && keypoints && out && width > 0, SF_ERR_ARG, "sf_fpfh: null argument");
   if (nq == 0) return SF_OK;
-  return out_is_f64 ? launch_fpfh(g, offsets, nbr, dist, spfh, width, keypoints, nq, static_cast<double*>(out), stream)
-                    : launch_fpfh(g, offsets, nbr, dist, spfh, width, keypoints, nq, static_cast<float*>(out), stream);
+  return out_is_f64 ? launch_fpfh(g, offsets, nbr, dist, csr_by_keypoint, spfh, width, keypoints, nq, static_cast<double*>(out), stream)
+                    : launch_fpfh(g, offsets, nbr, dist, csr_by_keypoint, spfh, width, keypoints, nq, static_cast<float*>(out), stream);
 }

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256)
 // queries == nullptr means "the cloud's own points, in cell-sorted order" (the FPFH case, fpfh.py:28-30).
 template <bool kFill>
 __global__ void __launch_bounds__(256)
-    radius_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double r2,
+    radius_kernel(GridView g, const double* __restrict__ queries, int64_t self_first, int64_t nq, double r2,
                   int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
                   int32_t* __restrict__ nbr_sorted, int32_t* __restrict__ nbr_index, double* __restrict__ dist) {
   const int lane = threadIdx.x & 31;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256)
     qy = __ldg(queries + 3 * q + 1);
     qz = __ldg(queries + 3 * q + 2);
   } else {
-    const double4 p = load_pt(g.pts + q);
+    const double4 p = load_pt(g.pts + self_first + q);
     qx = p.x; qy = p.y; qz = p.z;
   }
   const Runs runs = build_runs(g, qx, qy, qz, lane);
@@ -309,14 +309,17 @@ extern "C" int sf_grid_permutation(const sf_grid* g, int32_t* perm_out, int32_t*
   return SF_OK;
 }
 
-extern "C" int sf_radius_count(sf_grid* g, const double* queries, int64_t nq, double radius, int64_t* offsets,
+extern "C" int sf_radius_count(sf_grid* g, const double* queries, int64_t self_first, int64_t nq, double radius,
+                               int64_t* offsets,
                                int64_t* total_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_radius_count: grid not built");
   SF_REQUIRE(offsets != nullptr && nq >= 0, SF_ERR_ARG, "sf_radius_count: bad arguments");
   SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
              "sf_radius_count: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
-  if (queries == nullptr) nq = g->n;
+  if (queries == nullptr)
+    SF_REQUIRE(self_first >= 0 && self_first + nq <= g->n, SF_ERR_ARG, "self-query range [%lld, %lld) outside the cloud",
+               (long long)self_first, (long long)(self_first + nq));
   if (nq == 0) {
     SF_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int64_t), stream));
     if (total_host) *total_host = 0;
@@ -332,7 +335,7 @@ extern "C" int sf_radius_count(sf_grid* g, const double* queries, int64_t nq, do
   void* scan_temp = static_cast<char*>(g->cub_temp) + counts_bytes;
   const double r2 = radius * radius;
   const int64_t threads = nq * 32;
-  radius_kernel<false><<<unsigned((threads + 255) / 256), 256, 0, stream>>>(g->view(), queries, nq, r2, counts,
+  radius_kernel<false><<<unsigned((threads + 255) / 256), 256, 0, stream>>>(g->view(), queries, self_first, nq, r2, counts,
                                                                            nullptr, nullptr, nullptr, nullptr);
   cub::TransformInputIterator<int64_t, CountToI64, const int32_t*> in(counts, CountToI64());
   size_t bytes = scan_bytes + 256;
@@ -346,17 +349,20 @@ extern "C" int sf_radius_count(sf_grid* g, const double* queries, int64_t nq, do
   return SF_OK;
 }
 
-extern "C" int sf_radius_fill(sf_grid* g, const double* queries, int64_t nq, double radius, const int64_t* offsets,
+extern "C" int sf_radius_fill(sf_grid* g, const double* queries, int64_t self_first, int64_t nq, double radius,
+                              const int64_t* offsets,
                               int32_t* nbr_sorted, int32_t* nbr_index, double* dist, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_radius_fill: grid not built");
   SF_REQUIRE(offsets != nullptr && nq >= 0, SF_ERR_ARG, "sf_radius_fill: bad arguments");
   SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG, "sf_radius_fill: radius exceeds the cell edge");
-  if (queries == nullptr) nq = g->n;
+  if (queries == nullptr)
+    SF_REQUIRE(self_first >= 0 && self_first + nq <= g->n, SF_ERR_ARG, "self-query range [%lld, %lld) outside the cloud",
+               (long long)self_first, (long long)(self_first + nq));
   if (nq == 0) return SF_OK;
   const int64_t threads = nq * 32;
   radius_kernel<true><<<unsigned((threads + 255) / 256), 256, 0, stream>>>(
-      g->view(), queries, nq, radius * radius, nullptr, offsets, nbr_sorted, nbr_index, dist);
+      g->view(), queries, self_first, nq, radius * radius, nullptr, offsets, nbr_sorted, nbr_index, dist);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -70,6 +70,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// Same wait with a back-off, for the two single-thread roles (TMA producer, MMA issuer): they share a scheduler
+// with an epilogue warp each, and a tight try_wait loop would steal its issue slots (ncu: 37 M spins per launch).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t phase = (it / kStages) & 1;
-        mbar_wait(bar_b_empty(s), phase ^ 1);
+        mbar_wait_relaxed(bar_b_empty(s), phase ^ 1);
         mbar_expect_tx(bar_b_full(s), kBStageBytes);
         tma_load_2d(smem_base + kSmemB + s * kBStageBytes, &map_b, bar_b_full(s), kb * kBK, n0);
       }
@@ -200,12 +218,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     int it = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      mbar_wait(bar_t_empty(acc), ((t >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(bar_t_empty(acc), ((t >> 1) & 1) ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + uint32_t(acc * kBN);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % kStages;
-        mbar_wait(bar_b_full(s), (it / kStages) & 1);
+        mbar_wait_relaxed(bar_b_full(s), (it / kStages) & 1);
         tcgen05_fence_after();
         const uint64_t da = make_desc(smem_base + kSmemA + kb * kABlockBytes);
         const uint64_t db = make_desc(smem_base + kSmemB + s * kBStageBytes);
@@ -235,15 +253,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         float v[32];
         tmem_ld32(taddr + c, v);
         if (full_tile) {
+          // Branch-free common path: scores of 8 columns and their minimum; only when the minimum beats the
+          // row's current k-th best (rare after the first few thousand columns) are the 8 columns pushed.
           const float4* bn4 = reinterpret_cast<const float4*>(bnorm + n0 + c);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bn = __ldg(bn4 + j4);
-            const float sc[4] = {fmaf(-2.0f, v[4 * j4], bn.x), fmaf(-2.0f, v[4 * j4 + 1], bn.y),
-                                 fmaf(-2.0f, v[4 * j4 + 2], bn.z), fmaf(-2.0f, v[4 * j4 + 3], bn.w)};
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const float4 b0 = __ldg(bn4 + 2 * g8), b1 = __ldg(bn4 + 2 * g8 + 1);
+            float sc[8];
+            sc[0] = fmaf(-2.0f, v[8 * g8 + 0], b0.x); sc[1] = fmaf(-2.0f, v[8 * g8 + 1], b0.y);
+            sc[2] = fmaf(-2.0f, v[8 * g8 + 2], b0.z); sc[3] = fmaf(-2.0f, v[8 * g8 + 3], b0.w);
+            sc[4] = fmaf(-2.0f, v[8 * g8 + 4], b1.x); sc[5] = fmaf(-2.0f, v[8 * g8 + 5], b1.y);
+            sc[6] = fmaf(-2.0f, v[8 * g8 + 6], b1.z); sc[7] = fmaf(-2.0f, v[8 * g8 + 7], b1.w);
+            const float lo = fminf(fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3])),
+                                   fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7])));
+            if (lo < thr) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (sc[u] < thr) { top.push(sc[u], n0 + c + 4 * j4 + u + index_offset); thr = top.s[K - 1]; }
+              for (int u = 0; u < 8; ++u)
+                if (sc[u] < thr) { top.push(sc[u], n0 + c + 8 * g8 + u + index_offset); thr = top.s[K - 1]; }
+            }
           }
         } else {
 #pragma unroll

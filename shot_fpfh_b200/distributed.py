@@ -1,0 +1,198 @@
+"""
+Multi-GPU drivers: one process per GPU (torchrun), `torch.distributed` for the plumbing (NCCL over NVLink on the
+box, gloo in the CPU tests). The hot path shards without any collective in the data path (BASELINE.json north_star,
+SURVEY.md §8e):
+
+  * SHOT:     query points by contiguous blocks, cloud replicated; rows are only all-gathered if the caller asks.
+  * FPFH:     SPFH of the cloud points by contiguous blocks of the cell-sorted order -> ONE all-gather of the SPFH
+              rows (they are needed for every neighbour) -> FPFH of the keypoints by contiguous blocks.
+  * matching: the TARGET (reference) descriptor set by contiguous blocks, every rank sees all queries; each rank
+              produces its exact (nearest index, d1, d2) against its shard -> ONE all-gather -> merge.
+
+The sharding / gathering / merging logic is written against callables that compute one block, so that the same
+code runs the CUDA kernels on the box and the NumPy oracle under gloo in tests/test_distributed_cpu.py.
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None) -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def block_bounds(n: int, parts: int, part: int) -> tuple[int, int]:
+    """Contiguous blocks whose sizes differ by at most one: [lo, hi) of block `part`."""
+    base, extra = divmod(n, parts)
+    lo = part * base + min(part, extra)
+    return lo, lo + base + (1 if part < extra else 0)
+
+
+def all_gather_blocks(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """
+    Concatenation over ranks of per-rank row blocks of sizes `block_bounds(n_total, world, r)`; one collective
+    (`all_gather_into_tensor`) on blocks padded to the largest size.
+    """
+    rank, size = world(group)
+    if size == 1:
+        return local
+    lo, hi = block_bounds(n_total, size, rank)
+    assert local.shape[0] == hi - lo, (local.shape, lo, hi)
+    pad = block_bounds(n_total, size, 0)[1]
+    padded = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: hi - lo] = local
+    out = torch.empty((size * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    pieces = []
+    for r in range(size):
+        rlo, rhi = block_bounds(n_total, size, r)
+        pieces.append(out[r * pad : r * pad + (rhi - rlo)])
+    return torch.cat(pieces, dim=0)
+
+
+def sharded_rows(n_items: int, compute_block: Callable[[int, int], torch.Tensor], gather: bool = True, group=None):
+    """Rows of items [0, n_items): every rank computes its block; optionally all-gathered to every rank."""
+    rank, size = world(group)
+    lo, hi = block_bounds(n_items, size, rank)
+    local = compute_block(lo, hi)
+    return all_gather_blocks(local, n_items, group) if gather else local
+
+
+def sharded_fpfh(
+    n_points: int,
+    n_keypoints: int,
+    spfh_block: Callable[[int, int], torch.Tensor],
+    fpfh_block: Callable[[torch.Tensor, int, int], torch.Tensor],
+    gather: bool = True,
+    group=None,
+):
+    """
+    `spfh_block(first, end)` -> SPFH rows of the cell-sorted points [first, end); one all-gather; then
+    `fpfh_block(spfh_all, lo, hi)` -> FPFH rows of the keypoints [lo, hi).
+    """
+    rank, size = world(group)
+    s0, s1 = block_bounds(n_points, size, rank)
+    spfh_all = all_gather_blocks(spfh_block(s0, s1), n_points, group)
+    lo, hi = block_bounds(n_keypoints, size, rank)
+    local = fpfh_block(spfh_all, lo, hi)
+    return all_gather_blocks(local, n_keypoints, group) if gather else local
+
+
+def merge_nearest(d1: torch.Tensor, nn: torch.Tensor, d2: torch.Tensor):
+    """
+    (parts, Q) exact results against disjoint target shards (shard p holds smaller target indices than shard
+    p + 1; nn are GLOBAL indices, -1 / +inf where a shard is empty) -> (nn, d1, d2) against the union:
+    nearest = smallest d1, lowest index on ties (= first shard among equals); second = second smallest of the
+    multiset of all shards' d1 and d2.
+    """
+    best, part = torch.min(d1, dim=0)  # first minimal value along dim 0 on ties
+    nearest = torch.gather(nn, 0, part.unsqueeze(0)).squeeze(0)
+    both = torch.cat([d1, d2], dim=0)
+    second = torch.sort(both, dim=0).values[1] if both.shape[0] > 1 else torch.full_like(best, float("inf"))
+    return nearest, best, second
+
+
+def sharded_nearest(
+    n_targets: int,
+    nearest_in_shard: Callable[[int, int], tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+    group=None,
+):
+    """
+    `nearest_in_shard(lo, hi)` -> (nn global int64 (Q,), d1 float64 (Q,), d2 float64 (Q,)) against the target rows
+    [lo, hi). One all-gather of a packed (Q, 3) float64 tensor per rank (indices < 2**53 are exact in float64).
+    """
+    rank, size = world(group)
+    lo, hi = block_bounds(n_targets, size, rank)
+    nn, d1, d2 = nearest_in_shard(lo, hi)
+    if size == 1:
+        return nn, d1, d2
+    packed = torch.stack([d1.double(), nn.double(), d2.double()], dim=1).contiguous()
+    flat = torch.empty((size * packed.shape[0], 3), dtype=torch.float64, device=packed.device)
+    dist.all_gather_into_tensor(flat, packed, group=group)  # concatenated along dim 0 (gloo and NCCL agree on this)
+    out = flat.view(size, packed.shape[0], 3)
+    nn_m, d1_m, d2_m = merge_nearest(out[:, :, 0], out[:, :, 1].long(), out[:, :, 2])
+    return nn_m, d1_m, d2_m
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA drivers (one process per GPU)
+# ---------------------------------------------------------------------------------------------------------------
+def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, min_neighborhood_size=100, gather=True,
+                      out_dtype=torch.float32, group=None) -> torch.Tensor:
+    """SHOT rows (device tensor) of the keypoint COORDINATES, queries sharded by block over the ranks."""
+    from . import ops
+    from .device import Grid, upload
+
+    pts, nrm, kp = upload(point_cloud), upload(normals), upload(keypoints)
+    grid = Grid().build(pts, nrm, radius)
+
+    def block(lo, hi):
+        q = kp[lo:hi].contiguous()
+        offsets, nbr, _, _ = ops.radius_csr(grid, q, radius)
+        lrf = ops.shot_lrf(grid, q, radius, offsets, nbr)
+        return ops.shot_descriptor(grid, q, radius, offsets, nbr, lrf, min_neighborhood_size, normalize, out_dtype=out_dtype)
+
+    out = sharded_rows(int(kp.shape[0]), block, gather, group)
+    torch.cuda.synchronize()
+    grid.close()
+    return out
+
+
+def fpfh(keypoints_indices, cloud_points, normals, radius, n_bins, decorrelated=False, gather=True,
+         out_dtype=torch.float32, group=None) -> torch.Tensor:
+    """FPFH rows (device tensor) of the keypoint INDICES; SPFH sharded over cell-sorted blocks, one all-gather."""
+    from . import ops
+    from .device import Grid, upload
+
+    pts, nrm = upload(cloud_points), upload(normals)
+    kp = upload(keypoints_indices, torch.int64)
+    grid = Grid().build(pts, nrm, radius)
+
+    def spfh_block(first, end):
+        offsets, nbr, _, _ = ops.radius_csr(grid, None, radius, self_range=(first, end - first))
+        return ops.spfh(grid, offsets, nbr, n_bins, decorrelated, self_range=(first, end - first))
+
+    def fpfh_block(spfh_all, lo, hi):
+        mine = kp[lo:hi].contiguous()
+        offsets, nbr, _, d = ops.radius_csr(grid, pts[mine].contiguous(), radius, want_dist=True)
+        return ops.fpfh(grid, offsets, nbr, d, spfh_all.contiguous(), mine, out_dtype=out_dtype, csr_by_keypoint=True)
+
+    out = sharded_fpfh(grid.n, int(kp.shape[0]), spfh_block, fpfh_block, gather, group)
+    torch.cuda.synchronize()
+    grid.close()
+    return out
+
+
+def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None):
+    """
+    Exact nearest / second-nearest reference row of every non-empty scan row, the reference set sharded over the
+    ranks. Returns host arrays (scan row ids, ref row ids of the nearest, d1, d2) identical on every rank.
+    """
+    from . import ops
+    from .device import upload
+
+    a, b = upload(scan_descriptors), upload(ref_descriptors)
+    rows_a, rows_b = ops.nonempty_rows(a), ops.nonempty_rows(b)
+    scale = 1.0 / max(float(a.abs().max().item()), float(b.abs().max().item()), 1e-300)
+    a_packed, _ = ops.match_pack(a, rows_a, scale)
+    qa = int(rows_a.shape[0])
+
+    def shard(lo, hi):
+        if hi == lo:
+            inf = torch.full((qa,), float("inf"), dtype=torch.float64, device=a.device)
+            return torch.full((qa,), -1, dtype=torch.int64, device=a.device), inf, inf.clone()
+        rb = rows_b[lo:hi].contiguous()
+        b_packed, b_sqnorm = ops.match_pack(b, rb, scale)
+        _, cand = ops.match_topk(a_packed, b_packed, b_sqnorm, k, 0, True)
+        nn, d1, d2 = ops.match_rerank(a, rows_a, b, rb, cand)
+        return nn.long() + lo, d1, d2
+
+    nn, d1, d2 = sharded_nearest(int(rows_b.shape[0]), shard, group)
+    torch.cuda.synchronize()
+    return rows_a.cpu().numpy(), rows_b[nn].cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()

@@ -24,13 +24,16 @@ def radius_csr(
     want_sorted: bool = True,
     want_index: bool = False,
     want_dist: bool = False,
+    self_range: tuple[int, int] | None = None,
 ):
     """
     Fixed-radius search (sf_radius_count + sf_radius_fill). `queries=None` searches around the cloud's own
-    points in cell-sorted order. Returns (offsets int64[q+1], nbr_sorted|None, nbr_index|None, dist|None).
+    points at cell-sorted positions `self_range = (first, count)` (default: all of them).
+    Returns (offsets int64[q+1], nbr_sorted|None, nbr_index|None, dist|None).
     """
     dev = require_cuda()
-    nq = grid.n if queries is None else int(queries.shape[0])
+    first, count = self_range if self_range is not None else (0, grid.n)
+    nq = int(count) if queries is None else int(queries.shape[0])
     if nq == 0:  # an empty query set (a NULL pointer would mean "the cloud itself" to the C ABI)
         e32 = torch.empty(0, dtype=torch.int32, device=dev)
         return (
@@ -41,15 +44,19 @@ def radius_csr(
         )
     offsets = torch.empty(nq + 1, dtype=torch.int64, device=dev)
     total = ctypes.c_int64(0)
-    check(lib.sf_radius_count(grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ctypes.byref(total), stream_ptr()))
+    check(
+        lib.sf_radius_count(
+            grid.handle, ptr(queries), int(first), nq, float(radius), ptr(offsets), ctypes.byref(total), stream_ptr()
+        )
+    )
     p = int(total.value)
     nbr_sorted = torch.empty(p, dtype=torch.int32, device=dev) if want_sorted else None
     nbr_index = torch.empty(p, dtype=torch.int32, device=dev) if want_index else None
     dist = torch.empty(p, dtype=torch.float64, device=dev) if want_dist else None
     check(
         lib.sf_radius_fill(
-            grid.handle, ptr(queries), nq, float(radius), ptr(offsets), ptr(nbr_sorted), ptr(nbr_index), ptr(dist),
-            stream_ptr(),
+            grid.handle, ptr(queries), int(first), nq, float(radius), ptr(offsets), ptr(nbr_sorted), ptr(nbr_index),
+            ptr(dist), stream_ptr(),
         )
     )
     return offsets, nbr_sorted, nbr_index, dist
@@ -101,13 +108,22 @@ def fpfh_edges(n_bins: int) -> np.ndarray:
     return np.ascontiguousarray(np.stack([np.linspace(lo, hi, n_bins + 1) for lo, hi in FPFH_RANGES]))
 
 
-def spfh(grid: Grid, offsets: torch.Tensor, nbr_sorted: torch.Tensor, n_bins: int, decorrelated: bool):
+def spfh(
+    grid: Grid,
+    offsets: torch.Tensor,
+    nbr_sorted: torch.Tensor,
+    n_bins: int,
+    decorrelated: bool,
+    self_range: tuple[int, int] | None = None,
+):
+    """SPFH rows of the cell-sorted points `self_range = (first, count)` (default all), CSR from the same range."""
     width = 3 * n_bins if decorrelated else n_bins**3
-    out = torch.empty((grid.n, width), dtype=torch.float32, device=offsets.device)
+    first, count = self_range if self_range is not None else (0, grid.n)
+    out = torch.empty((int(count), width), dtype=torch.float32, device=offsets.device)
     edges = fpfh_edges(n_bins)
     check(
         lib.sf_spfh(
-            grid.handle, ptr(offsets), ptr(nbr_sorted), int(n_bins), int(bool(decorrelated)),
+            grid.handle, int(first), int(count), ptr(offsets), ptr(nbr_sorted), int(n_bins), int(bool(decorrelated)),
             edges.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ptr(out), stream_ptr(),
         )
     )
@@ -122,15 +138,21 @@ def fpfh(
     spfh_rows: torch.Tensor,
     keypoints: torch.Tensor,
     out_dtype: torch.dtype = torch.float64,
+    csr_by_keypoint: bool = False,
 ):
+    """
+    FPFH rows of the keypoints (original indices). `spfh_rows` covers the WHOLE cloud in cell-sorted order. The CSR
+    is the whole-cloud self-search (default) or, with `csr_by_keypoint`, a search around the keypoints' coordinates.
+    """
     nq, width = int(keypoints.shape[0]), int(spfh_rows.shape[1])
+    assert int(spfh_rows.shape[0]) == grid.n
     out = torch.empty((nq, width), dtype=out_dtype, device=offsets.device)
     if nq == 0:
         return out
     check(
         lib.sf_fpfh(
-            grid.handle, ptr(offsets), ptr(nbr_sorted), ptr(dist), ptr(spfh_rows), width, ptr(keypoints), nq, ptr(out),
-            int(out_dtype == torch.float64), stream_ptr(),
+            grid.handle, ptr(offsets), ptr(nbr_sorted), ptr(dist), int(bool(csr_by_keypoint)), ptr(spfh_rows), width,
+            ptr(keypoints), nq, ptr(out), int(out_dtype == torch.float64), stream_ptr(),
         )
     )
     return out

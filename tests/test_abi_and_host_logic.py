@@ -32,7 +32,9 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(raw, name), f"{name} is declared in the header but not exported"
     assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
-    assert _lib.lib.sf_abi_version() == 1
+    with open(os.path.join(ROOT, "include", "shotfpfh_b200.h")) as f:
+        declared_version = int(re.search(r"#define SF_ABI_VERSION (\d+)", f.read()).group(1))
+    assert _lib.lib.sf_abi_version() == declared_version == _lib.ABI_VERSION
     assert _lib.lib.sf_last_error() is not None
 
 

@@ -1,0 +1,135 @@
+"""
+CPU, world_size 2 and 3 over gloo: the multi-GPU host logic of shot_fpfh_b200/distributed.py (block sharding,
+padded all-gather, SPFH exchange, merge of per-shard nearest neighbours) with the NumPy oracle standing in for the
+CUDA kernels — sharded results must equal the unsharded ones exactly.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fpfh_oracle, matching_oracle, shot_oracle
+from shot_fpfh_b200 import distributed as sfd
+from shot_fpfh_b200 import synthetic
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, size: int, port: int, fn_name: str):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(size))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        globals()[fn_name](rank, size)
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(fn_name: str, size: int):
+    mp.spawn(_worker, args=(size, _free_port(), fn_name), nprocs=size, join=True)
+
+
+def _cloud():
+    pts, normals = synthetic.bumpy_sphere(1500, seed=41)
+    return pts, normals, 6.0 * synthetic.mean_spacing(1500)
+
+
+def _check_shot(rank, size):
+    pts, normals, radius = _cloud()
+    kp = pts[::7]  # 215 queries: not divisible by 2 or 3
+    full = shot_oracle.shot_single_scale(pts, normals, kp, radius, True, 5)
+
+    def block(lo, hi):
+        return torch.from_numpy(shot_oracle.shot_single_scale(pts, normals, kp[lo:hi], radius, True, 5))
+
+    got = sfd.sharded_rows(kp.shape[0], block, gather=True)
+    assert np.array_equal(got.numpy(), full)
+    local = sfd.sharded_rows(kp.shape[0], block, gather=False)
+    lo, hi = sfd.block_bounds(kp.shape[0], size, rank)
+    assert np.array_equal(local.numpy(), full[lo:hi])
+
+
+def _check_fpfh(rank, size):
+    from sklearn.neighbors import KDTree
+
+    pts, normals, radius = _cloud()
+    n = pts.shape[0]
+    kp = np.arange(0, n, 3)
+    full, spfh_full = fpfh_oracle.fpfh(kp, pts, normals, radius, 11, True, return_spfh=True)
+    tree = KDTree(pts)
+    edges = fpfh_oracle.bin_edges(11)
+
+    def spfh_block(first, end):  # "cell-sorted order" = original order here
+        rows = np.zeros((end - first, 33))
+        nbh = tree.query_radius(pts[first:end], radius)
+        for r, i in enumerate(range(first, end)):
+            a, p, t = fpfh_oracle.pair_features(pts[i], normals[i], pts[nbh[r]], normals[nbh[r]])
+            rows[r] = fpfh_oracle.spfh_row(a, p, t, nbh[r].shape[0], 11, True, edges)
+        return torch.from_numpy(rows)
+
+    def fpfh_block(spfh_all, lo, hi):
+        s = spfh_all.numpy()
+        assert np.array_equal(s, spfh_full)  # the exchange reproduced the whole table on every rank
+        nbh, d = tree.query_radius(pts[kp[lo:hi]], radius, return_distance=True)
+        out = np.zeros((hi - lo, 33))
+        for r, i in enumerate(kp[lo:hi]):
+            far = d[r] > 0
+            out[r] = s[i] + (s[nbh[r][far]] / d[r][far][:, None]).sum(axis=0) / nbh[r].shape[0]
+        return torch.from_numpy(out)
+
+    got = sfd.sharded_fpfh(n, kp.shape[0], spfh_block, fpfh_block, gather=True)
+    assert np.array_equal(got.numpy(), full)
+
+
+def _check_matching(rank, size):
+    rng = np.random.default_rng(3)
+    a = synthetic.sparse_unit_rows(90, 64, seed=1).astype(np.float64)
+    b = synthetic.sparse_unit_rows(131, 64, seed=2).astype(np.float64)
+    b[40] = b[7]  # duplicated target rows in different shards: the lowest index must win
+    b[100] = b[7]
+    a[3] = b[7]
+    a[::9] = 0.0
+    sa, sb, nn, d1, dmat = matching_oracle.nearest(a, b)
+    d2 = np.partition(dmat, 1, axis=1)[:, 1]
+
+    def shard(lo, hi):
+        sub = dmat[:, lo:hi]
+        if sub.shape[1] == 0:
+            inf = torch.full((sa.shape[0],), float("inf"), dtype=torch.float64)
+            return torch.full((sa.shape[0],), -1, dtype=torch.int64), inf, inf.clone()
+        local_nn = sub.argmin(axis=1)
+        local_d1 = sub[np.arange(sub.shape[0]), local_nn]
+        local_d2 = np.partition(sub, 1, axis=1)[:, 1] if sub.shape[1] > 1 else np.full(sub.shape[0], np.inf)
+        return torch.from_numpy(local_nn + lo), torch.from_numpy(local_d1), torch.from_numpy(local_d2)
+
+    got_nn, got_d1, got_d2 = sfd.sharded_nearest(sb.shape[0], shard)
+    assert np.array_equal(got_nn.numpy(), nn)
+    assert np.array_equal(got_d1.numpy(), d1) and np.array_equal(got_d2.numpy(), d2)
+    del rng
+
+
+@pytest.mark.parametrize("size", [2, 3])
+@pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_matching"])
+def test_sharded_equals_unsharded(fn, size):
+    _spawn(fn, size)
+
+
+def test_block_bounds_and_merge_single_process():
+    for n in (0, 1, 7, 100):
+        for parts in (1, 2, 3, 8):
+            b = [sfd.block_bounds(n, parts, p) for p in range(parts)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+    d1 = torch.tensor([[0.5, 0.2, 0.3], [0.5, 0.1, 0.4]], dtype=torch.float64)
+    nn = torch.tensor([[1, 2, 3], [11, 12, 13]])
+    d2 = torch.tensor([[0.6, 0.25, 0.9], [0.7, 0.15, 0.45]], dtype=torch.float64)
+    m_nn, m_d1, m_d2 = sfd.merge_nearest(d1, nn, d2)
+    assert m_nn.tolist() == [1, 12, 3] and m_d1.tolist() == [0.5, 0.1, 0.3] and m_d2.tolist() == [0.5, 0.15, 0.4]
