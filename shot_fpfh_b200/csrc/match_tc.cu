@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "sf_common.cuh"
 
@@ -36,13 +37,14 @@ constexpr int kBN = 256;        // target rows per accumulator tile (= TMEM colu
 constexpr int kBK = 64;         // halves per K block: 128 bytes = one swizzle-128B row
 constexpr int kStages = 3;      // B pipeline depth
 constexpr int kMaxKBlocks = 6;  // K <= 384 (SHOT: 352 padded to 384)
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
 constexpr uint32_t kABlockBytes = kBM * kBK * 2;  // 16 KB
 constexpr uint32_t kBStageBytes = kBN * kBK * 2;  // 32 KB
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemB = kMaxKBlocks * kABlockBytes;            // 96 KB
 constexpr uint32_t kSmemBar = kSmemB + kStages * kBStageBytes;     // 192 KB
-constexpr uint32_t kSmemBytes = kSmemBar + 256 + 1024;             // barriers + alignment slack
+constexpr uint32_t kSmemBnorm = 8 * 2 * 32 * 16;                   // per epilogue warp: 2 buffers of 128 floats
+constexpr uint32_t kSmemBytes = kSmemBar + 256 + kSmemBnorm + 1024;  // barriers + |b|^2 staging + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -111,8 +113,7 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
@@ -122,9 +123,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 8 consecutive columns of this warp's 32 lanes, loaded and waited for (slow path only).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Shared-memory matrix descriptor of a K-major tile stored as rows of 128 bytes with the 128-byte swizzle:
@@ -164,7 +170,9 @@ template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
     topk_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const float* __restrict__ bnorm, int64_t qa, int64_t qb, int num_kb, int tiles_per_split,
-                   int index_offset, float* __restrict__ score, int32_t* __restrict__ idx) {
+                   int index_offset, float* __restrict__ score, int32_t* __restrict__ idx, int debug) {
+  // `debug` (env SF_TC_DEBUG, profiling only; results are garbage when set): 1 = skip the MMAs, 2 = skip the
+  // epilogue's TMEM reads / top-k, 4 = skip the B loads. Used to attribute time to TMA / MMA / epilogue.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   const uint32_t bar_base = smem_base + kSmemBar;
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1 && lane == 0) {
     mbar_init(bar_a_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_t_full(a), 1); mbar_init(bar_t_empty(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_t_full(a), 1); mbar_init(bar_t_empty(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns (two 128 x 256 float32 accumulators)
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int s = it % kStages;
         const uint32_t phase = (it / kStages) & 1;
         mbar_wait_relaxed(bar_b_empty(s), phase ^ 1);
+        if (debug & 4) { mbar_arrive(bar_b_full(s)); continue; }
         mbar_expect_tx(bar_b_full(s), kBStageBytes);
         tma_load_2d(smem_base + kSmemB + s * kBStageBytes, &map_b, bar_b_full(s), kb * kBK, n0);
       }
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int s = it % kStages;
         mbar_wait_relaxed(bar_b_full(s), (it / kStages) & 1);
         tcgen05_fence_after();
+        if (debug & 1) { mbar_arrive(bar_b_empty(s)); continue; }
         const uint64_t da = make_desc(smem_base + kSmemA + kb * kABlockBytes);
         const uint64_t db = make_desc(smem_base + kSmemB + s * kBStageBytes);
 #pragma unroll
@@ -232,62 +242,95 @@ __global__ void __launch_bounds__(kThreads, 1)
           tcgen05_mma_f16(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), kIdesc, uint32_t((kb | k) != 0));
         tcgen05_commit(bar_b_empty(s));  // frees the B stage once the MMAs that read it have retired
       }
-      tcgen05_commit(bar_t_full(acc));   // accumulator tile complete
+      if (debug & 1) mbar_arrive(bar_t_full(acc));
+      else tcgen05_commit(bar_t_full(acc));  // accumulator tile complete
     }
   } else if (warp >= 4) {
-    // ===== epilogue: one query row (TMEM lane) per thread =====
+    // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32*(w%4).. (one query row per thread) and the column half
+    // (w-4)/4 of every accumulator tile, i.e. 4 chunks of 32 columns; the two halves of a row keep separate
+    // top-k lists that the merge kernel joins. Latency hiding (ncu round 1: the epilogue was pure exposed latency):
+    //   - |b|^2 of the NEXT tile is fetched into a register during the current tile and parked in shared memory,
+    //     so the inner loop reads it with broadcast LDS instead of waiting on L2;
+    //   - the TMEM load of chunk c+1 is in flight while chunk c is processed.
     const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = m0 + quarter * 32 + lane;
+    float4* bn_buf = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256) + (warp - 4) * 64;
+    const bool bn_aligned = (reinterpret_cast<uintptr_t>(bnorm) & 15) == 0;
+    auto load_bn = [&](int tile) -> float4 {  // |b|^2 of columns 4*lane .. +3 of this warp's half; +inf past the end
+      const int64_t col = int64_t(tile) * kBN + half * 128 + 4 * lane;
+      if (bn_aligned && col + 4 <= qb) return __ldg(reinterpret_cast<const float4*>(bnorm + col));
+      float4 r;
+      r.x = col + 0 < qb ? __ldg(bnorm + col + 0) : INFINITY;
+      r.y = col + 1 < qb ? __ldg(bnorm + col + 1) : INFINITY;
+      r.z = col + 2 < qb ? __ldg(bnorm + col + 2) : INFINITY;
+      r.w = col + 3 < qb ? __ldg(bnorm + col + 3) : INFINITY;
+      return r;
+    };
     TopK<K> top;
     top.init();
     float thr = INFINITY;
+    float4 bn_next = my_tiles > 0 ? load_bn(tile_begin) : make_float4(0, 0, 0, 0);
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      const int n0 = (tile_begin + t) * kBN;
+      const int n0 = (tile_begin + t) * kBN + half * 128;
+      float4* bn = bn_buf + acc * 32;
+      bn[lane] = bn_next;
+      __syncwarp();
+      if (t + 1 < my_tiles) bn_next = load_bn(tile_begin + t + 1);
       mbar_wait(bar_t_full(acc), (t >> 1) & 1);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kBN);
-      const bool full_tile = int64_t(n0) + kBN <= qb && (reinterpret_cast<uintptr_t>(bnorm) & 15) == 0;
+      if (debug & 2) { mbar_arrive(bar_t_empty(acc)); continue; }
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kBN + half * 128);
+      uint32_t va[32], vb[32];
+      tmem_ld32_issue(taddr, va);
+      // Pass 1, branch-free and fully unrolled: the minimum score of each group of 8 columns against the row's
+      // current k-th best -> one flag bit per group (16 groups in this warp's 128 columns).
+      // (ncu round 1: with the insertion code inlined at all 16 unrolled sites the kernel was 150 KB of SASS and
+      // every insertion missed the instruction cache, ~4 k cycles each: 74 ms instead of 20 ms at 200k x 200k.)
+      uint32_t flags = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        uint32_t(&v)[32] = (c & 1) ? vb : va;
+        if (c + 1 < 4) tmem_ld32_issue(taddr + 32 * (c + 1), (c & 1) ? va : vb);
+        if (debug & 8) continue;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const float4 b0 = bn[8 * c + 2 * g8], b1 = bn[8 * c + 2 * g8 + 1];  // same address in every lane: broadcast
+          const float s0 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 0]), b0.x), s1 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 1]), b0.y);
+          const float s2 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 2]), b0.z), s3 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 3]), b0.w);
+          const float s4 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 4]), b1.x), s5 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 5]), b1.y);
+          const float s6 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 6]), b1.z), s7 = fmaf(-2.0f, __uint_as_float(v[8 * g8 + 7]), b1.w);
+          const float lo = fminf(fminf(fminf(s0, s1), fminf(s2, s3)), fminf(fminf(s4, s5), fminf(s6, s7)));
+          flags |= (lo < thr ? 1u : 0u) << (4 * c + g8);
+        }
+      }
+      // Pass 2, ONE copy of the insertion code for the whole kernel: the groups flagged by any lane are read again
+      // from TMEM (the accumulator has not been released yet) and their 8 columns pushed in ascending order.
+      uint32_t pending = (debug & 16) ? 0u : __reduce_or_sync(kFull, flags);
 #pragma unroll 1
-      for (int c = 0; c < kBN; c += 32) {
-        float v[32];
-        tmem_ld32(taddr + c, v);
-        if (full_tile) {
-          // Branch-free common path: scores of 8 columns and their minimum; only when the minimum beats the
-          // row's current k-th best (rare after the first few thousand columns) are the 8 columns pushed.
-          const float4* bn4 = reinterpret_cast<const float4*>(bnorm + n0 + c);
+      while (pending) {
+        const int g = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint32_t r[8];
+        tmem_ld8(taddr + 8 * g, r);
+        const float4 b0 = bn[2 * g], b1 = bn[2 * g + 1];
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        if ((flags >> g) & 1) {
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const float4 b0 = __ldg(bn4 + 2 * g8), b1 = __ldg(bn4 + 2 * g8 + 1);
-            float sc[8];
-            sc[0] = fmaf(-2.0f, v[8 * g8 + 0], b0.x); sc[1] = fmaf(-2.0f, v[8 * g8 + 1], b0.y);
-            sc[2] = fmaf(-2.0f, v[8 * g8 + 2], b0.z); sc[3] = fmaf(-2.0f, v[8 * g8 + 3], b0.w);
-            sc[4] = fmaf(-2.0f, v[8 * g8 + 4], b1.x); sc[5] = fmaf(-2.0f, v[8 * g8 + 5], b1.y);
-            sc[6] = fmaf(-2.0f, v[8 * g8 + 6], b1.z); sc[7] = fmaf(-2.0f, v[8 * g8 + 7], b1.w);
-            const float lo = fminf(fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3])),
-                                   fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7])));
-            if (lo < thr) {
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (sc[u] < thr) { top.push(sc[u], n0 + c + 8 * g8 + u + index_offset); thr = top.s[K - 1]; }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t col = int64_t(n0) + c + j;
-            if (col < qb) {
-              const float sc = fmaf(-2.0f, v[j], __ldg(bnorm + col));
-              if (sc < thr) { top.push(sc, int(col) + index_offset); thr = top.s[K - 1]; }
-            }
+          for (int u = 0; u < 8; ++u) {
+            const float sc = fmaf(-2.0f, __uint_as_float(r[u]), bb[u]);
+            if (sc < thr) { top.push(sc, n0 + 8 * g + u + index_offset); thr = top.s[K - 1]; }
           }
         }
       }
       tcgen05_fence_before();
       mbar_arrive(bar_t_empty(acc));
+      __syncwarp();
     }
     if (row < qa) {
-      const int64_t o = (int64_t(blockIdx.y) * qa + row) * K;
+      const int64_t o = ((int64_t(blockIdx.y) * 2 + half) * qa + row) * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) { score[o + k] = top.s[k]; idx[o + k] = top.i[k]; }
     }
@@ -341,7 +384,9 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bno
     configured = true;
   }
   const dim3 grid(unsigned((qa + kBM - 1) / kBM), unsigned(splits));
-  topk_tc_kernel<K><<<grid, kThreads, kSmemBytes, stream>>>(ma, mb, bnorm, qa, qb, num_kb, tiles_per_split, off, score, idx);
+  static const int debug = getenv("SF_TC_DEBUG") ? atoi(getenv("SF_TC_DEBUG")) : 0;
+  topk_tc_kernel<K><<<grid, kThreads, kSmemBytes, stream>>>(ma, mb, bnorm, qa, qb, num_kb, tiles_per_split, off, score, idx,
+                                                            debug);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
@@ -370,12 +415,12 @@ int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bn
   if (m_tiles < 2 * 148) splits = std::min(n_tiles, std::max(1, (2 * 148 + m_tiles - 1) / m_tiles));
   const int tiles_per_split = (n_tiles + splits - 1) / splits;
   splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-  float* part_score = score;
-  int32_t* part_idx = idx;
-  if (splits > 1) {
-    SF_CUDA(cudaMallocAsync(&part_score, size_t(splits) * qa * k * sizeof(float), stream));
-    SF_CUDA(cudaMallocAsync(&part_idx, size_t(splits) * qa * k * sizeof(int32_t), stream));
-  }
+  // every CTA emits two partial shortlists per row (one per column half of its tiles): parts = 2 * splits
+  const int parts = 2 * splits;
+  float* part_score = nullptr;
+  int32_t* part_idx = nullptr;
+  SF_CUDA(cudaMallocAsync(&part_score, size_t(parts) * qa * k * sizeof(float), stream));
+  SF_CUDA(cudaMallocAsync(&part_idx, size_t(parts) * qa * k * sizeof(int32_t), stream));
   const int num_kb = wp / kBK;
   int rc = SF_OK;
   switch (k) {
@@ -385,11 +430,9 @@ int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bn
     case 8: rc = launch<8>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
     default: rc = launch<16>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
   }
-  if (rc == SF_OK && splits > 1) rc = launch_merge_partials(part_score, part_idx, splits, qa, k, score, idx, stream);
-  if (splits > 1) {
-    cudaFreeAsync(part_score, stream);
-    cudaFreeAsync(part_idx, stream);
-  }
+  if (rc == SF_OK) rc = launch_merge_partials(part_score, part_idx, parts, qa, k, score, idx, stream);
+  cudaFreeAsync(part_score, stream);
+  cudaFreeAsync(part_idx, stream);
   return rc;
 }
 
