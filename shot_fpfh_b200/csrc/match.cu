@@ -205,9 +205,9 @@ extern "C" int sf_nonempty_rows(const double* desc, int64_t n, int32_t width, in
   size_t temp_bytes = 0;
   cub::CountingInputIterator<int64_t> ids(0);
   cub::DeviceSelect::Flagged(nullptr, temp_bytes, ids, flags, rows, count_dev, int(n), stream);
-  SF_CUDA(cudaMallocAsync(&flags, size_t(n), stream));
-  SF_CUDA(cudaMallocAsync(&count_dev, sizeof(int64_t), stream));
-  SF_CUDA(cudaMallocAsync(&temp, temp_bytes + 16, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&flags), size_t(n), stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&count_dev), sizeof(int64_t), stream));
+  SF_CUDA(scratch_alloc(&temp, temp_bytes + 16, stream));
   nonempty_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, stream>>>(desc, n, width, flags);
   SF_CUDA(cub::DeviceSelect::Flagged(temp, temp_bytes, ids, flags, rows, count_dev, int(n), stream));
   SF_CUDA(cudaMemcpyAsync(count_host, count_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));

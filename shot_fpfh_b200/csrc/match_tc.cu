@@ -419,8 +419,8 @@ int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bn
   const int parts = 2 * splits;
   float* part_score = nullptr;
   int32_t* part_idx = nullptr;
-  SF_CUDA(cudaMallocAsync(&part_score, size_t(parts) * qa * k * sizeof(float), stream));
-  SF_CUDA(cudaMallocAsync(&part_idx, size_t(parts) * qa * k * sizeof(int32_t), stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&part_score), size_t(parts) * qa * k * sizeof(float), stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&part_idx), size_t(parts) * qa * k * sizeof(int32_t), stream));
   const int num_kb = wp / kBK;
   int rc = SF_OK;
   switch (k) {

@@ -89,8 +89,10 @@ SF_HD void octant_centre(int t, double& cx, double& cy) {
   }
 }
 
-// local = (X, Y, Z) coordinates in the LRF (float64), cosine = clip(n . z_axis) (float64), rho > 0, radius.
-SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double rho, double radius) {
+// local = (X, Y, Z) coordinates in the LRF (float64), cosine = clip(n . z_axis) (float64), rho > 0, radius and its
+// reciprocal (computed once per launch: the weights are continuous, so multiplying by 1/radius instead of
+// dividing moves them by an ulp at most, and it removes four float64 divisions per neighbour).
+SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double rho, double radius, double inv_radius) {
   ShotRecord r;
   const float kPi = 3.14159265358979323846f;
   // ---- decisions, float64 -------------------------------------------------------------------------------
@@ -117,40 +119,40 @@ SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double
   const float a_cos = float(fabs(dcos));
   r.v_cos = a_cos;
   // radial (shot.py:95-118); rho == radius/2 exactly gives 0 everywhere, as in the reference
-  const double half = radius / 2, quarter = radius / 4, three_q = radius * 3 / 4;
+  const double half = radius / 2, quarter = radius / 4, three_q = radius * 3 / 4, inv_half = 2.0 * inv_radius;
   float own_shell, other_shell;
   if (ri) {  // rho > r/2: statement 4 carries `inner`, statement 3 writes 0 to `own`
-    own_shell = float(1.0 - fabs(rho - three_q) / half);
-    other_shell = rho < three_q ? float((three_q - rho) / half) : 0.0f;
+    own_shell = float(1.0 - fabs(rho - three_q) * inv_half);
+    other_shell = rho < three_q ? float((three_q - rho) * inv_half) : 0.0f;
   } else {
-    own_shell = rho < half ? float(1.0 - fabs(rho - quarter) / half) : 0.0f;
-    other_shell = (rho < half && rho > quarter) ? float((rho - quarter) / half) : 0.0f;
+    own_shell = rho < half ? float(1.0 - fabs(rho - quarter) * inv_half) : 0.0f;
+    other_shell = (rho < half && rho > quarter) ? float((rho - quarter) * inv_half) : 0.0f;
   }
   r.v_rad = other_shell;
   // elevation (shot.py:142-171): phi < pi/2 <=> Z > 0; weights are continuous -> float32
-  float ratio = float(Z / rho);
+  float ratio = float(Z) / float(rho);
   ratio = fminf(1.0f, fmaxf(-1.0f, ratio));
   const float phi = acosf(ratio);
-  const float h = 0.5f * kPi;
+  const float inv_h = 0.63661977236758134308f;  // 1 / (pi / 2)
   float own_vol, other_vol;
   if (ei) {  // upper half-space, elevation bin 1, centre pi/4; statement 7 carries `lower`
-    own_vol = 1.0f - fabsf(phi - 0.25f * kPi) / h;
-    other_vol = phi >= 0.25f * kPi ? (phi - 0.25f * kPi) / h : 0.0f;
+    own_vol = 1.0f - fabsf(phi - 0.25f * kPi) * inv_h;
+    other_vol = phi >= 0.25f * kPi ? (phi - 0.25f * kPi) * inv_h : 0.0f;
   } else {   // Z <= 0, elevation bin 0, centre 3pi/4; statement 6 carries `upper`
-    own_vol = 1.0f - fabsf(phi - 0.75f * kPi) / h;
-    other_vol = phi <= 0.75f * kPi ? (0.75f * kPi - phi) / h : 0.0f;
+    own_vol = 1.0f - fabsf(phi - 0.75f * kPi) * inv_h;
+    other_vol = phi <= 0.75f * kPi ? (0.75f * kPi - phi) * inv_h : 0.0f;
   }
   r.v_el = fmaxf(other_vol, 0.0f);
   // azimuth (shot.py:282-298)
   const float theta = atan2f(float(Y), float(X));
-  const float q = 0.25f * kPi;
-  float daz = (theta - (-kPi + float(ti) * q)) / q - 0.5f;
+  const float q = 0.25f * kPi, inv_q = 1.27323954473516268615f;  // 1 / (pi / 4)
+  float daz = (theta - (-kPi + float(ti) * q)) * inv_q - 0.5f;
   daz = fminf(0.5f, fmaxf(-0.5f, daz));
   const float a_az = saz == 0 ? 0.0f : fabsf(daz);
   r.v_az = a_az;
   r.v_own = (1.0f - a_cos) + own_shell + own_vol + (1.0f - a_az);
   // ---- order key: rho / radius in 32-bit fixed point (monotone in rho; resolution radius * 2^-32) ---------
-  double scaled = rho / radius * 4294967296.0;
+  double scaled = rho * inv_radius * 4294967296.0;
   r.key = scaled >= 4294967295.0 ? 0xFFFFFFFFu : (scaled < 1.0 ? 1u : uint32_t(scaled));
   return r;
 }

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32)
   for (int i = lane; i < kSlotCount; i += 32) slots[i] = 0ull;
   __syncwarp();
   const int64_t warps_total = int64_t(gridDim.x) * kShotWarpsPerBlock;
+  const double inv_radius = 1.0 / radius;
   for (int64_t q = blockIdx.x * int64_t(kShotWarpsPerBlock) + warp; q < nq; q += warps_total) {
     const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
     const int64_t begin = offsets[q], end = offsets[q + 1];
@@ -117,21 +118,33 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32)
 #pragma unroll
     for (int k = 0; k < 9; ++k) f[k] = __ldg(lrf + 9 * q + k);
     int positive = 0;
-    for (int64_t i = begin + lane; i < end; i += 32) {
+    // software pipeline: the gathers of the lane's NEXT neighbour are issued before the current one is processed
+    // (ncu round 1: a quarter of the stall samples sat on the first use of the gathered point / normal)
+    int64_t i = begin + lane;
+    double4 p_next = make_double4(0, 0, 0, 0), n_next = p_next;
+    if (i < end) {
       const int s = __ldg(nbr + i);
-      const double4 p = load_pt(g.pts + s);
+      p_next = load_pt(g.pts + s);
+      n_next = load_pt(g.nrm + s);
+    }
+    for (; i < end; i += 32) {
+      const double4 p = p_next, n = n_next;
+      if (i + 32 < end) {
+        const int s = __ldg(nbr + i + 32);
+        p_next = load_pt(g.pts + s);
+        n_next = load_pt(g.nrm + s);
+      }
       const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
       const double d2 = rdist3(cx, cy, cz);
       if (d2 > 0.0) {  // shot.py:213: neighbours at distance 0 (the query itself, duplicates) are dropped
         ++positive;
-        const double4 n = load_pt(g.nrm + s);
         const double rho = sqrt(d2);
         const double X = cx * f[0] + cy * f[3] + cz * f[6];
         const double Y = cx * f[1] + cy * f[4] + cz * f[7];
         const double Z = cx * f[2] + cy * f[5] + cz * f[8];
         double cosine = n.x * f[2] + n.y * f[5] + n.z * f[8];
         cosine = fmin(1.0, fmax(-1.0, cosine));
-        const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius);
+        const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius, inv_radius);
         int slot[7];
         float val[7];
         shot_slots(rec, slot, val);

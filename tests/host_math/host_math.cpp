@@ -75,7 +75,7 @@ void hm_shot_descriptor(const double* point, const double* nbrs, const double* n
     const double Z = cx * f[2] + cy * f[5] + cz * f[8];
     double cosine = normals[3 * i] * f[2] + normals[3 * i + 1] * f[5] + normals[3 * i + 2] * f[8];
     cosine = fmin(1.0, fmax(-1.0, cosine));
-    const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius);
+    const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius, 1.0 / radius);
     int slot[7];
     float val[7];
     shot_slots(rec, slot, val);
