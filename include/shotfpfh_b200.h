@@ -75,6 +75,16 @@ int sf_radius_fill(sf_grid* grid, const double* queries_dev, int64_t self_first,
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * G3 — support reducer.  Replaces `grid_subsampling(points, voxel_size)` (core/subsampling.py:5-39) where the SHOT
+ * drivers call it on the support cloud (shot_parallelization.py:157-161, :210-214, :273-277).
+ * picked_dev: int32[n] capacity; the first *count_host entries receive, in lexicographic voxel order, the index of
+ * the point closest to each occupied voxel's barycentre (first on ties, members in ascending index order).
+ * Synchronises `stream` (the count is a host result).
+ * ---------------------------------------------------------------------------------------------------------- */
+int sf_voxel_subsample(const double* xyz_dev, int64_t n, double voxel_size, int32_t* picked_dev, int64_t* count_host,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * S — SHOT.
  * ---------------------------------------------------------------------------------------------------------- */
 /* Local reference frames. Replaces `get_local_rf` (shot.py:16-48) fanned out by

@@ -45,6 +45,7 @@ def _load() -> ctypes.CDLL:
         "sf_radius_fill": [
             c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
         ],
+        "sf_voxel_subsample": [c_void_p, c_int64, c_double, c_void_p, p_i64, c_void_p],
         "sf_shot_lrf": [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p],
         "sf_shot_descriptor": [
             c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
@@ -77,7 +78,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTS = (
     "sf_last_error sf_abi_version sf_grid_create sf_grid_destroy sf_grid_build sf_grid_info sf_grid_permutation "
-    "sf_radius_count sf_radius_fill sf_shot_lrf sf_shot_descriptor sf_spfh sf_fpfh sf_nonempty_rows sf_match_pack "
+    "sf_radius_count sf_radius_fill sf_voxel_subsample sf_shot_lrf sf_shot_descriptor sf_spfh sf_fpfh sf_nonempty_rows sf_match_pack "
     "sf_match_topk sf_topk_merge sf_match_rerank"
 ).split()
 

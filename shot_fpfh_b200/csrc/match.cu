@@ -149,27 +149,59 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// ---- M2: exact float64 re-rank, one thread per query row ---------------------------------------------------
-__global__ void __launch_bounds__(128)
+// ---- M2: exact float64 re-rank, one warp per query row -----------------------------------------------------
+// SciPy's cdist accumulates s += (u[e] - v[e])^2 sequentially in e, without FMA; the argmin (and the distances the
+// filters see) are only bit-identical if the sums are formed in that order. The squares are order-independent, so
+// the 32 lanes compute them for 32 columns at a time with coalesced row loads and park them in shared memory;
+// lane c then folds the 32 squares of candidate c in ascending column order. Columns past the width contribute
+// exact zeros (s + 0.0 == s).
+constexpr int kRerankWarps = 8;
+constexpr int kRerankMaxK = 16;
+
+__global__ void __launch_bounds__(kRerankWarps * 32)
     rerank_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a, int64_t qa,
                   const double* __restrict__ b, const int64_t* __restrict__ rows_b, int width,
                   const int32_t* __restrict__ cand, int k, int32_t* __restrict__ nn, double* __restrict__ d1,
                   double* __restrict__ d2) {
-  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  __shared__ double squares[kRerankWarps][kRerankMaxK][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x * int64_t(kRerankWarps) + warp;
   if (q >= qa) return;
   const double* ra = a + (rows_a ? rows_a[q] : q) * width;
+  int my_id = -1;
+  int64_t my_row = 0;
+  if (lane < k) {
+    my_id = cand[q * k + lane];
+    if (my_id >= 0) my_row = rows_b ? rows_b[my_id] : int64_t(my_id);
+  }
+  double s = 0.0;
+  for (int e0 = 0; e0 < width; e0 += 32) {
+    const int e = e0 + lane;
+    const double av = e < width ? ra[e] : 0.0;
+    for (int c = 0; c < k; ++c) {
+      const int id = __shfl_sync(kFull, my_id, c);
+      const int64_t row = __shfl_sync(kFull, my_row, c);
+      double sq = 0.0;
+      if (id >= 0 && e < width) {
+        const double d = av - b[row * width + e];
+        sq = mul_rn(d, d);
+      }
+      squares[warp][c][lane] = sq;
+    }
+    __syncwarp();
+    if (lane < k) {
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) s = add_rn(s, squares[warp][lane][t]);
+    }
+    __syncwarp();
+  }
+  const double my_dist = my_id >= 0 ? sqrt(s) : INFINITY;
   double best = INFINITY, second = INFINITY;
   int best_idx = -1;
-  for (int c = 0; c < k; ++c) {
-    const int id = cand[q * k + c];
+  for (int c = 0; c < k; ++c) {  // every lane runs the same selection on the broadcast results
+    const double dist = __shfl_sync(kFull, my_dist, c);
+    const int id = __shfl_sync(kFull, my_id, c);
     if (id < 0) continue;
-    const double* rb = b + (rows_b ? rows_b[id] : int64_t(id)) * width;
-    double s = 0.0;
-    for (int e = 0; e < width; ++e) {  // SciPy: s += (u[e] - v[e])^2, sequential, no FMA
-      const double d = ra[e] - rb[e];
-      s = add_rn(s, mul_rn(d, d));
-    }
-    const double dist = sqrt(s);
     if (dist < best || (dist == best && id < best_idx)) {
       second = best;
       best = dist;
@@ -178,9 +210,11 @@ __global__ void __launch_bounds__(128)
       second = dist;
     }
   }
-  nn[q] = best_idx;
-  if (d1) d1[q] = best;
-  if (d2) d2[q] = second;
+  if (lane == 0) {
+    nn[q] = best_idx;
+    if (d1) d1[q] = best;
+    if (d2) d2[q] = second;
+  }
 }
 
 struct IsSet {
@@ -303,7 +337,9 @@ extern "C" int sf_match_rerank(const double* a, const int64_t* rows_a, int64_t q
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(a && b && cand && nn && width > 0 && k >= 1, SF_ERR_ARG, "sf_match_rerank: bad arguments");
   if (qa == 0) return SF_OK;
-  rerank_kernel<<<unsigned((qa + 127) / 128), 128, 0, stream>>>(a, rows_a, qa, b, rows_b, width, cand, k, nn, d1, d2);
+  SF_REQUIRE(k <= kRerankMaxK, SF_ERR_CAPACITY, "sf_match_rerank: k must be <= %d", kRerankMaxK);
+  rerank_kernel<<<unsigned((qa + kRerankWarps - 1) / kRerankWarps), kRerankWarps * 32, 0, stream>>>(
+      a, rows_a, qa, b, rows_b, width, cand, k, nn, d1, d2);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

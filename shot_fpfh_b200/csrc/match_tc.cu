@@ -11,11 +11,16 @@
 // tile t. The epilogue reads the accumulators with tcgen05.ld (one TMEM lane = one query row per thread), and
 // keeps a per-row running top-k in registers; only (Qa, k) scores/indices ever reach HBM.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warps 4..11 = epilogue: warp w touches TMEM lanes 32*(w%4) .. +31 (a hardware restriction) and the
+// column half (w-4)/4 of each tile. Its fast path is branch-free (score = fma, group minimum, one flag bit per group
+// of 8 columns); the rare insertions run through ONE out-of-line loop that re-reads the flagged groups from TMEM.
 // Grid: (number of 128-row query tiles, number of target splits); each split scans a contiguous range of target
-// tiles and the per-split shortlists are merged by topk_merge_kernel (match.cu) — this keeps all 148 SMs busy when
-// there are few query tiles.
+// tiles; the per-split, per-half shortlists are merged by topk_merge_kernel (match.cu). Splitting keeps all 148 SMs
+// busy when there are few query tiles.
+//
+// Round-1 measurements on B200 (200k x 200k x 352, profiles/r01_summary.md): TMA + MMA alone sustain 1.43 PFLOP/s
+// (89 % of the measured cuBLAS bf16 peak), the full kernel 1.29 PFLOP/s (81 %).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

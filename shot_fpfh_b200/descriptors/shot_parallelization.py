@@ -22,7 +22,6 @@ import torch
 
 from .. import ops
 from ..device import Grid, download, require_cuda, upload
-from ..subsampling import grid_subsampling
 
 
 def _neighborhoods_to_csr(neighborhoods, inv_perm: torch.Tensor):
@@ -74,15 +73,19 @@ class ShotMultiprocessor:
         return self._grid
 
     def _support(self, point_cloud, normals, subsampling_voxel_size, radius):
-        """Uploads the (optionally voxel-subsampled) support and builds the grid for `radius`."""
-        support = grid_subsampling(point_cloud, subsampling_voxel_size) if subsampling_voxel_size is not None else None
-        if self.verbose and support is not None:
-            logging.info(
-                f"Keeping a support of {support.shape[0]} points out of {point_cloud.shape[0]} "
-                f"(voxel size: {subsampling_voxel_size:.2f})"
-            )
-        pts = upload(point_cloud if support is None else np.asarray(point_cloud)[support])
-        nrm = upload(normals if support is None else np.asarray(normals)[support])
+        """
+        Uploads the cloud, reduces it to the voxel-subsampled support when asked (on the device: csrc/subsample.cu,
+        `grid_subsampling` semantics) and builds the grid for `radius`.
+        """
+        pts, nrm = upload(point_cloud), upload(normals)
+        if subsampling_voxel_size is not None:
+            support = ops.voxel_subsample(pts, subsampling_voxel_size)
+            if self.verbose:
+                logging.info(
+                    f"Keeping a support of {support.shape[0]} points out of {pts.shape[0]} "
+                    f"(voxel size: {subsampling_voxel_size:.2f})"
+                )
+            pts, nrm = pts[support].contiguous(), nrm[support].contiguous()
         grid = self._ensure_grid().build(pts, nrm, radius)
         return grid, pts, nrm
 

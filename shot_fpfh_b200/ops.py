@@ -71,6 +71,15 @@ def grid_permutation(grid: Grid) -> tuple[torch.Tensor, torch.Tensor]:
     return perm, inv
 
 
+def voxel_subsample(xyz: torch.Tensor, voxel_size: float) -> torch.Tensor:
+    """Indices (int64, device) of one point per occupied voxel — `grid_subsampling` semantics, see csrc/subsample.cu."""
+    n = int(xyz.shape[0])
+    picked = torch.empty(max(n, 1), dtype=torch.int32, device=xyz.device)
+    count = ctypes.c_int64(0)
+    check(lib.sf_voxel_subsample(ptr(xyz), n, float(voxel_size), ptr(picked), ctypes.byref(count), stream_ptr()))
+    return picked[: int(count.value)].long()
+
+
 def shot_lrf(grid: Grid, queries: torch.Tensor, radius: float, offsets: torch.Tensor, nbr_sorted: torch.Tensor):
     nq = int(queries.shape[0])
     lrf = torch.empty((nq, 3, 3), dtype=torch.float64, device=queries.device)

@@ -14,6 +14,14 @@ import numpy as np
 import numpy.typing as npt
 
 
+def grid_subsampling_gpu(points: npt.NDArray[np.float64], voxel_size: float) -> npt.NDArray[np.int64]:
+    """The same selection on the device (csrc/subsample.cu); what `ShotMultiprocessor` uses for its support."""
+    from . import ops
+    from .device import upload
+
+    return ops.voxel_subsample(upload(points), voxel_size).cpu().numpy()
+
+
 def grid_subsampling(points: npt.NDArray[np.float64], voxel_size: float) -> npt.NDArray[np.int64]:
     points = np.asarray(points, dtype=np.float64)
     if points.shape[0] == 0:

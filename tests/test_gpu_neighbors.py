@@ -112,6 +112,34 @@ def test_smaller_radius_on_same_grid_and_random_box_cloud():
     s.close()
 
 
+def test_voxel_subsampling_equals_host_semantics():
+    """G3: the device support reducer against the host restatement of grid_subsampling (core/subsampling.py:5-39)."""
+    from shot_fpfh_b200.subsampling import grid_subsampling, grid_subsampling_gpu
+
+    rng = np.random.default_rng(3)
+    clouds = [
+        synthetic.bumpy_sphere(200_000, seed=2)[0],
+        rng.uniform(-3, 5, size=(50_000, 3)),
+        np.round(rng.uniform(0, 1, size=(20_000, 3)), 2),  # many points exactly on voxel boundaries / duplicates
+    ]
+    for pts, voxels in zip(clouds, ((0.01, 0.05, 0.4), (0.3, 2.5), (0.05, 0.1, 0.25))):
+        for voxel in voxels:
+            want = grid_subsampling(pts, voxel)
+            got = grid_subsampling_gpu(pts, voxel)
+            assert got.shape == want.shape, (voxel, got.shape, want.shape)
+            keys = ((pts - pts.min(axis=0)) // voxel).astype(int)
+            assert np.array_equal(keys[got], keys[want])  # same voxels, same (lexicographic) order
+            differ = np.nonzero(got != want)[0]
+            # picks may only differ on exact distance ties (host and device sum the barycentre in the same order,
+            # so in practice they do not differ at all)
+            for i in differ[:50]:
+                members = np.nonzero((keys == keys[got[i]]).all(axis=1))[0]
+                centre = pts[members].mean(axis=0)
+                assert abs(np.linalg.norm(pts[got[i]] - centre) - np.linalg.norm(pts[want[i]] - centre)) < 1e-12
+            assert differ.shape[0] <= 0.01 * got.shape[0]
+    assert grid_subsampling_gpu(np.zeros((0, 3)), 0.1).shape == (0,)
+
+
 def test_degenerate_clouds():
     from shot_fpfh_b200.neighbors import RadiusSearch
 
