@@ -291,9 +291,14 @@ def bench_shot(args, dist, rank, world, pk):
     }
     dominant = max(stages, key=stages.get)
     achieved = alg[dominant] / (stages[dominant] * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this workload
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_c2.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            traffic = json.load(f).get(dominant)
     roofline = {
         "kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+        "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
         "algorithmic_bytes": alg[dominant], "kernel_ms": stages[dominant],
         "per_stage": {k: {"ms": stages[k], "algorithmic_GBps": alg[k] / (stages[k] * 1e-3) / 1e9} for k in stages},
     }
