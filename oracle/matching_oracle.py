@@ -58,6 +58,30 @@ def match_descriptors(scan, ref, filter_callback=None, filter_nonreciprocal=Fals
     return scan_ids[mask], ref_ids[nn[mask]]
 
 
+def match_multiscale(scan, ref, filter_callback=None, n_min_matches=100, filter_nonreciprocal=False, **kwargs):
+    """
+    matching.py:76-136, the 3-D branch: (n_scales, n_points, width) descriptors, distance = minimum over the scales
+    of the per-scale Euclidean distances, 1000 for empty rows; dense matrices as in the reference. The reference's
+    reciprocity filter assigns into a temporary (a no-op) and is therefore absent here; its
+    "too few matches" fallback re-runs without it, which gives the same selection.
+    """
+    max_val = 1000
+    n_scales, n_points, _ = scan.shape
+    n_points_ref = ref.shape[1]
+    inf = np.ones((n_points, n_points_ref)) * max_val
+    for s in range(n_scales):
+        ne_a, ne_b = np.any(scan[s], axis=1), np.any(ref[s], axis=1)
+        d = np.ones((n_points, n_points_ref)) * max_val
+        d[np.ix_(ne_a, ne_b)] = cdist(scan[s][ne_a], ref[s][ne_b])
+        inf = np.minimum(d, inf)
+    idx = inf.argmin(axis=1)
+    dist = inf[np.arange(n_points), idx]
+    mask = (filter_callback(dist, **kwargs) if filter_callback is not None else np.ones(n_points, dtype=bool)) & (
+        dist < max_val
+    )
+    return np.arange(n_points)[mask], np.arange(n_points_ref)[idx[mask]]
+
+
 def ratio_matching(scan, ref, threshold: float, lowe: bool = False):
     """
     The ratio test matching.py:172-221 INTENDS (the reference raises on every input): nearest

@@ -90,12 +90,12 @@ def match_descriptors(
     """
     Nearest-neighbour matching with an optional filter on the nearest-neighbour distances and an optional
     reciprocity filter (matching.py:9-74, :138-146). The reciprocity check `D.argmin(0)[idx] == arange` is a second
-    nearest-neighbour search with the roles swapped. Only the 2-D (Euclidean) branch is on the GPU; the 3-D
-    multi-scale branch (matching.py:76-136), which the pipeline never reaches, is not implemented.
+    nearest-neighbour search with the roles swapped. (n_scales, n_points, width) inputs take the multi-scale
+    "infinite-norm" branch (matching.py:76-136), see `_match_multiscale`.
     """
     if np.ndim(scan_descriptors) != 2:
-        raise NotImplementedError(
-            "multi-scale (3-D) infinite-norm matching is outside this round's hot path (SURVEY.md §8f row 3)"
+        return _match_multiscale(
+            scan_descriptors, ref_descriptors, filter_callback, filter_nonreciprocal, verbose, n_min_matches, **kwargs
         )
     logging.info("")
     logging.info("-- Matching descriptors based on Euclidian-norm proximity --")
@@ -113,6 +113,45 @@ def match_descriptors(
     if verbose:
         logging.info(f"Kept {filtered.sum()} matches out of {np.shape(scan_descriptors)[-2]} descriptors.")
     return m.rows_a[filtered], m.rows_b[m.nn[filtered]]
+
+
+def _match_multiscale(scan, ref, filter_callback, filter_nonreciprocal, verbose, n_min_matches, **kwargs):
+    """
+    The 3-D branch of the reference's `match_descriptors` (matching.py:76-136): descriptors given as
+    (n_scales, n_points, width); the distance between two points is the MINIMUM over the scales of their Euclidean
+    descriptor distances, empty rows counting as `max_val = 1000`. The reference builds n_scales dense matrices; here
+    each scale is one exact nearest-neighbour search on the GPU and the per-scale winners are merged on the host —
+    `argmin_j min_s D_s[i, j]` is attained by the nearest neighbour of some scale (lowest j on ties).
+    Kept literally: the reciprocity filter of this branch assigns into a temporary and is a no-op in the reference
+    (matching.py:106-108); only its "too few matches" fallback has an effect.
+    """
+    logging.info("")
+    logging.info("-- Matching descriptors based on infinite-norm proximity --")
+    max_val = 1000.0
+    scan, ref = np.asarray(scan), np.asarray(ref)
+    n_scales, n_points, _ = scan.shape
+    n_points_ref = ref.shape[1]
+    distances = np.full(n_points, max_val)
+    indices = np.zeros(n_points, dtype=np.int64)
+    for scale in range(n_scales):
+        if not ref[scale].any() or not scan[scale].any():
+            continue
+        m, _ = _match(scan[scale], ref[scale])
+        d = np.minimum(m.d1, max_val)
+        j = m.rows_b[m.nn]
+        cur_d, cur_j = distances[m.rows_a], indices[m.rows_a]
+        better = (d < cur_d) | ((d == cur_d) & (j < cur_j) & (d < max_val))
+        distances[m.rows_a] = np.where(better, d, cur_d)
+        indices[m.rows_a] = np.where(better, j, cur_j)
+    filtered = (
+        filter_callback(distances, **kwargs) if filter_callback is not None else np.ones(n_points, dtype=bool)
+    ) & (distances < max_val)
+    if filtered.sum() < n_min_matches and filter_nonreciprocal:
+        logging.warning("Too few reciprocal matches, keeping non-reciprocal matches.")
+        return match_descriptors(scan, ref, filter_callback, filter_nonreciprocal=False, verbose=verbose, **kwargs)
+    if verbose:
+        logging.info(f"Kept {filtered.sum()} matches out of {n_points} descriptors.")
+    return np.arange(n_points)[filtered], np.arange(n_points_ref)[indices[filtered]]
 
 
 def double_matching_with_rejects(

@@ -74,7 +74,9 @@ def grid_permutation(grid: Grid) -> tuple[torch.Tensor, torch.Tensor]:
 def voxel_subsample(xyz: torch.Tensor, voxel_size: float) -> torch.Tensor:
     """Indices (int64, device) of one point per occupied voxel — `grid_subsampling` semantics, see csrc/subsample.cu."""
     n = int(xyz.shape[0])
-    picked = torch.empty(max(n, 1), dtype=torch.int32, device=xyz.device)
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=xyz.device)
+    picked = torch.empty(n, dtype=torch.int32, device=xyz.device)
     count = ctypes.c_int64(0)
     check(lib.sf_voxel_subsample(ptr(xyz), n, float(voxel_size), ptr(picked), ctypes.byref(count), stream_ptr()))
     return picked[: int(count.value)].long()

@@ -130,6 +130,26 @@ def test_topk_merge_equals_unsharded():
         assert torch.equal(i_m, i_all) and torch.equal(s_m, s_all)
 
 
+def test_multiscale_infinite_norm_branch():
+    """(n_scales, n_points, width) descriptors: the 3-D branch of match_descriptors (matching.py:76-136)."""
+    from test_oracle_golden import _multiscale_inputs
+
+    from shot_fpfh_b200.matching import match_descriptors, threshold_filter
+
+    g = load_golden("small_pair_4k")
+    a3, b3 = _multiscale_inputs(g["scan_shot_dense"])
+    for recip in (False, True):
+        for mult in (1.5, 4.0):
+            got = match_descriptors(a3, b3, threshold_filter, filter_nonreciprocal=recip, verbose=False,
+                                    n_min_matches=5, threshold_multiplier=mult)
+            want = matching_oracle.match_multiscale(a3, b3, matching_oracle.threshold_filter, threshold_multiplier=mult)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (recip, mult)
+    got = match_descriptors(a3, b3, verbose=False)
+    want = matching_oracle.match_multiscale(a3, b3)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert 35 not in got[0]  # the row that is empty at every scale is dropped
+
+
 def test_empty_and_degenerate_inputs():
     from shot_fpfh_b200.matching import basic_matching, double_matching_with_rejects
 
