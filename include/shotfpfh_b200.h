@@ -85,6 +85,25 @@ int sf_voxel_subsample(const double* xyz_dev, int64_t n, double voxel_size, int3
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * N — PCA normals ("next" row: upstream of the hot path).  Replaces `compute_normals`
+ * (descriptors/pca_based_descriptors.py:29-59), which get_data runs on every cloud (helpers/io_ply.py:259-301).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* k nearest neighbours, replaces `KDTree(cloud).query(queries, k, return_distance=False)` (:46). For every query
+ * whose status is not 1: if at least k cloud points lie within `reach` (<= the grid's cell edge) the k nearest
+ * (ORIGINAL point indices, nearest first) are written to nbr_index_dev[q*k ..] and status_dev[q] = 1; otherwise
+ * status_dev[q] = 0 (too few: retry with a larger reach) or 2 (more than 512 within reach: retry with a smaller
+ * one). status_dev must be zero-initialised by the caller before the first attempt. */
+int sf_knn(sf_grid* grid, const double* queries_dev, int64_t nq, int32_t k, double reach, int32_t* nbr_index_dev,
+           int32_t* status_dev, void* stream);
+/* normal = eigenvector of the smallest eigenvalue of the neighbourhood's covariance about its barycentre
+ * (`pca(...)[1][:, 0]`, :15-26, :51), LAPACK's sign; flipped when its dot product with pre_normals_dev[q] is
+ * negative (:53-57; pre_normals_dev may be NULL). xyz_dev: the cloud, float64 (n,3); neighbourhoods are ORIGINAL
+ * point indices, CSR (offsets_dev != NULL) or fixed_k entries per query (offsets_dev == NULL).
+ * normals_dev: float64 (nq,3); NaN for an empty neighbourhood, as NumPy gives. */
+int sf_pca_normals(const double* xyz_dev, int64_t nq, const int64_t* offsets_dev, int32_t fixed_k,
+                   const int32_t* nbr_index_dev, const double* pre_normals_dev, double* normals_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * S — SHOT.
  * ---------------------------------------------------------------------------------------------------------- */
 /* Local reference frames. Replaces `get_local_rf` (shot.py:16-48) fanned out by

@@ -82,6 +82,26 @@ def voxel_subsample(xyz: torch.Tensor, voxel_size: float) -> torch.Tensor:
     return picked[: int(count.value)].long()
 
 
+def knn_attempt(grid: Grid, queries: torch.Tensor, k: int, reach: float, nbr_index: torch.Tensor, status: torch.Tensor):
+    """One sf_knn attempt at `reach` (see include/shotfpfh_b200.h); updates nbr_index / status in place."""
+    check(
+        lib.sf_knn(grid.handle, ptr(queries), int(queries.shape[0]), int(k), float(reach), ptr(nbr_index), ptr(status),
+                   stream_ptr())
+    )
+
+
+def pca_normals(xyz: torch.Tensor, nq: int, nbr_index: torch.Tensor, offsets: torch.Tensor | None = None,
+                fixed_k: int = 0, pre_normals: torch.Tensor | None = None) -> torch.Tensor:
+    """PCA normals of neighbourhoods given as ORIGINAL point indices into `xyz` (CSR or fixed_k per query)."""
+    out = torch.empty((nq, 3), dtype=torch.float64, device=xyz.device)
+    if nq:
+        check(
+            lib.sf_pca_normals(ptr(xyz), nq, ptr(offsets), int(fixed_k), ptr(nbr_index), ptr(pre_normals), ptr(out),
+                               stream_ptr())
+        )
+    return out
+
+
 def shot_lrf(grid: Grid, queries: torch.Tensor, radius: float, offsets: torch.Tensor, nbr_sorted: torch.Tensor):
     nq = int(queries.shape[0])
     lrf = torch.empty((nq, 3, 3), dtype=torch.float64, device=queries.device)

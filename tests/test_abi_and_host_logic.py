@@ -97,7 +97,7 @@ def test_signatures_mirror_the_reference():
     def params(fn):
         return [(p.name, p.kind, p.default) for p in inspect.signature(fn).parameters.values()]
 
-    for name in ("compute_fpfh_descriptor",):
+    for name in ("compute_fpfh_descriptor", "compute_normals"):
         assert params(getattr(d, name)) == params(getattr(ref_d, name)), name
     for name in ("basic_matching", "match_descriptors", "double_matching_with_rejects", "threshold_filter",
                  "quantile_filter", "left_median_filter"):
