@@ -89,72 +89,123 @@ SF_HD void octant_centre(int t, double& cx, double& cy) {
   }
 }
 
+// ---- step 1: everything that DECIDES, float64 (bins, interpolation signs, distance key) + the cheap weights --------
 // local = (X, Y, Z) coordinates in the LRF (float64), cosine = clip(n . z_axis) (float64), rho > 0, radius and its
 // reciprocal (computed once per launch: the weights are continuous, so multiplying by 1/radius instead of
 // dividing moves them by an ulp at most, and it removes four float64 divisions per neighbour).
-SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double rho, double radius, double inv_radius) {
-  ShotRecord r;
-  const float kPi = 3.14159265358979323846f;
-  // ---- decisions, float64 -------------------------------------------------------------------------------
+struct ShotDecision {
+  int own, cos_nb, az_nb;  // flat bins: own, statement-1 target, statement-9 target
+  uint32_t key;            // distance order (see ShotRecord::key)
+  int ti, ei, saz;         // azimuth octant, elevation bit, sign of the azimuth offset from the octant centre
+  float a_cos;             // |cosine offset| (statement 1 value; 1 - a_cos goes to the own bin)
+  float own_shell;         // radial weight of the own bin (statement 5)
+  float other_shell;       // radial weight sent to the OTHER shell (statement 3 or 4)
+  float fx, fy, ratio;     // float32 inputs of the two transcendental weights: atan2f(fy, fx), acosf(ratio)
+};
+
+SF_HD ShotDecision shot_decide(double X, double Y, double Z, double cosine, double rho, double radius, double inv_radius) {
+  ShotDecision d;
   const double pos = (cosine + 1.0) * double(kShotCos) / 2.0 - 0.5;  // shot.py:228
   const double ci_f = rint(pos);                                      // round-half-even like np.rint
   const int ci = int(ci_f);
   const double dcos = pos - ci_f;
   const int scos = (dcos > 0.0) - (dcos < 0.0);
-  const int ti = azimuth_octant(X, Y);
-  const int ei = Z > 0.0;
+  d.ti = azimuth_octant(X, Y);
+  d.ei = Z > 0.0;
   const int ri = rho > radius / 2;
-  r.own = shot_flat(ci, ti, ei, ri);
+  d.own = shot_flat(ci, d.ti, d.ei, ri);
   int cnb = ci + scos;
   cnb = cnb < 0 ? cnb + kShotCos : (cnb >= kShotCos ? cnb - kShotCos : cnb);
-  r.cos_nb = shot_flat(cnb, ti, ei, ri);
+  d.cos_nb = shot_flat(cnb, d.ti, d.ei, ri);
   // sign of the azimuth offset from the octant centre: cross(centre, (X, Y)) instead of a float64 atan2
   double cx, cy;
-  octant_centre(ti, cx, cy);
+  octant_centre(d.ti, cx, cy);
   const double cr = cx * Y - cy * X;
   // on the LRF's z axis (X == Y == 0) the reference gets theta = atan2(0, 0) = 0 in octant 0: offset clipped to +0.5
-  const int saz = (X == 0.0 && Y == 0.0) ? 1 : (cr > 0.0) - (cr < 0.0);
-  r.az_nb = shot_flat(ci, (ti + saz + kShotAz) & (kShotAz - 1), ei, ri);
-  // ---- weights ------------------------------------------------------------------------------------------
-  const float a_cos = float(fabs(dcos));
-  r.v_cos = a_cos;
+  d.saz = (X == 0.0 && Y == 0.0) ? 1 : (cr > 0.0) - (cr < 0.0);
+  d.az_nb = shot_flat(ci, (d.ti + d.saz + kShotAz) & (kShotAz - 1), d.ei, ri);
+  d.a_cos = float(fabs(dcos));
   // radial (shot.py:95-118); rho == radius/2 exactly gives 0 everywhere, as in the reference
   const double half = radius / 2, quarter = radius / 4, three_q = radius * 3 / 4, inv_half = 2.0 * inv_radius;
-  float own_shell, other_shell;
   if (ri) {  // rho > r/2: statement 4 carries `inner`, statement 3 writes 0 to `own`
-    own_shell = float(1.0 - fabs(rho - three_q) * inv_half);
-    other_shell = rho < three_q ? float((three_q - rho) * inv_half) : 0.0f;
+    d.own_shell = float(1.0 - fabs(rho - three_q) * inv_half);
+    d.other_shell = rho < three_q ? float((three_q - rho) * inv_half) : 0.0f;
   } else {
-    own_shell = rho < half ? float(1.0 - fabs(rho - quarter) * inv_half) : 0.0f;
-    other_shell = (rho < half && rho > quarter) ? float((rho - quarter) * inv_half) : 0.0f;
+    d.own_shell = rho < half ? float(1.0 - fabs(rho - quarter) * inv_half) : 0.0f;
+    d.other_shell = (rho < half && rho > quarter) ? float((rho - quarter) * inv_half) : 0.0f;
   }
-  r.v_rad = other_shell;
-  // elevation (shot.py:142-171): phi < pi/2 <=> Z > 0; weights are continuous -> float32
-  float ratio = float(Z) / float(rho);
-  ratio = fminf(1.0f, fmaxf(-1.0f, ratio));
-  const float phi = acosf(ratio);
-  const float inv_h = 0.63661977236758134308f;  // 1 / (pi / 2)
-  float own_vol, other_vol;
-  if (ei) {  // upper half-space, elevation bin 1, centre pi/4; statement 7 carries `lower`
+  d.fx = float(X);
+  d.fy = float(Y);
+  d.ratio = fminf(1.0f, fmaxf(-1.0f, float(Z) / float(rho)));
+  // order key: rho / radius in 32-bit fixed point (monotone in rho; resolution radius * 2^-32)
+  const double scaled = rho * inv_radius * 4294967296.0;
+  d.key = scaled >= 4294967295.0 ? 0xFFFFFFFFu : (scaled < 1.0 ? 1u : uint32_t(scaled));
+  return d;
+}
+
+// ---- step 2: the two transcendental weights, float32 (continuous in their inputs) ---------------------------------
+// elevation (shot.py:142-171): phi < pi/2 <=> Z > 0
+SF_HD void shot_elevation(const ShotDecision& d, float& own_vol, float& other_vol) {
+  const float kPi = 3.14159265358979323846f, inv_h = 0.63661977236758134308f;  // 1 / (pi / 2)
+  const float phi = acosf(d.ratio);
+  if (d.ei) {  // upper half-space, elevation bin 1, centre pi/4; statement 7 carries `lower`
     own_vol = 1.0f - fabsf(phi - 0.25f * kPi) * inv_h;
     other_vol = phi >= 0.25f * kPi ? (phi - 0.25f * kPi) * inv_h : 0.0f;
-  } else {   // Z <= 0, elevation bin 0, centre 3pi/4; statement 6 carries `upper`
+  } else {     // Z <= 0, elevation bin 0, centre 3pi/4; statement 6 carries `upper`
     own_vol = 1.0f - fabsf(phi - 0.75f * kPi) * inv_h;
     other_vol = phi <= 0.75f * kPi ? (0.75f * kPi - phi) * inv_h : 0.0f;
   }
-  r.v_el = fmaxf(other_vol, 0.0f);
-  // azimuth (shot.py:282-298)
-  const float theta = atan2f(float(Y), float(X));
-  const float q = 0.25f * kPi, inv_q = 1.27323954473516268615f;  // 1 / (pi / 4)
-  float daz = (theta - (-kPi + float(ti) * q)) * inv_q - 0.5f;
+  other_vol = fmaxf(other_vol, 0.0f);
+}
+// azimuth (shot.py:282-298): |offset from the octant centre| in octant widths, clipped to 0.5
+SF_HD float shot_azimuth(const ShotDecision& d) {
+  const float kPi = 3.14159265358979323846f, q = 0.25f * kPi, inv_q = 1.27323954473516268615f;  // 1 / (pi / 4)
+  const float theta = atan2f(d.fy, d.fx);
+  float daz = (theta - (-kPi + float(d.ti) * q)) * inv_q - 0.5f;
   daz = fminf(0.5f, fmaxf(-0.5f, daz));
-  const float a_az = saz == 0 ? 0.0f : fabsf(daz);
+  return d.saz == 0 ? 0.0f : fabsf(daz);
+}
+
+SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double rho, double radius, double inv_radius) {
+  const ShotDecision d = shot_decide(X, Y, Z, cosine, rho, radius, inv_radius);
+  float own_vol, other_vol;
+  shot_elevation(d, own_vol, other_vol);
+  const float a_az = shot_azimuth(d);
+  ShotRecord r;
+  r.own = d.own; r.cos_nb = d.cos_nb; r.az_nb = d.az_nb; r.key = d.key;
+  r.v_cos = d.a_cos;
+  r.v_rad = d.other_shell;
+  r.v_el = other_vol;
   r.v_az = a_az;
-  r.v_own = (1.0f - a_cos) + own_shell + own_vol + (1.0f - a_az);
-  // ---- order key: rho / radius in 32-bit fixed point (monotone in rho; resolution radius * 2^-32) ---------
-  double scaled = rho * inv_radius * 4294967296.0;
-  r.key = scaled >= 4294967295.0 ? 0xFFFFFFFFu : (scaled < 1.0 ? 1u : uint32_t(scaled));
+  r.v_own = (1.0f - d.a_cos) + d.own_shell + own_vol + (1.0f - a_az);
   return r;
+}
+
+// ---- winner tables, compact form (what the kernel uses) -----------------------------------------------------------
+// The seven statement groups need only THREE winner decisions per neighbour: the four statements that address the
+// neighbour's own bin share one winner, and so do the radial / elevation "other bin" statements, because every
+// neighbour of own bin b addresses the same radial partner b^1 (and elevation partner b^2): the winner of the slot
+// "radial statement, bins {b, b^1}" is whichever of the two own-bin winners is farther, and it contributes its
+// `other_shell` weight to the bin it is NOT in (0 to its own). So per query:
+//   keys  uint32 [3][352] : distance key of the winner of {own-bin group, statement 1, statement 9}, 0 = nobody
+//   vals  float  [5][352] : v_own, v_rad (other_shell), v_el (other_vol) of the own-bin winner; v_cos; v_az
+// Keys are raised with a native 32-bit atomicMax; after a warp barrier the lanes whose key is (still) the slot's key
+// store their values. Two DIFFERENT neighbours with the same 32-bit key on one slot (distances within
+// radius * 2^-32) are an exact-distance tie: one of them wins, as in the reference's unstable argsort.
+constexpr int kKeyOwn = 0, kKeyCos = kShotLen, kKeyAz = 2 * kShotLen, kKeyCount = 3 * kShotLen;
+constexpr int kValOwn = 0, kValRad = kShotLen, kValEl = 2 * kShotLen, kValCos = 3 * kShotLen, kValAz = 4 * kShotLen,
+              kValCount = 5 * kShotLen;
+
+SF_HD float shot_bin_value_compact(const uint32_t* keys, const float* vals, int flat) {
+  const uint32_t k_own = keys[kKeyOwn + flat];
+  float v = k_own ? vals[kValOwn + flat] : 0.0f;
+  if (keys[kKeyCos + flat]) v += vals[kValCos + flat];
+  if (keys[kKeyAz + flat]) v += vals[kValAz + flat];
+  const int radial_partner = flat ^ 1, elevation_partner = flat ^ 2;
+  // the partner bin's winner is farther than this bin's (or this bin is empty): it wrote its "other" weight here
+  if (keys[kKeyOwn + radial_partner] > k_own) v += vals[kValRad + radial_partner];
+  if (keys[kKeyOwn + elevation_partner] > k_own) v += vals[kValEl + elevation_partner];
+  return v;
 }
 
 // Slot layout of the winner tables (per query, 64-bit words (key << 32) | float bits):

@@ -96,22 +96,28 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- S2 ----------------------------------------------------------------------------------------------------
+// Per warp: uint32 keys[3][352] + float vals[5][352] = 11 264 B of shared memory (sf_math.cuh, "winner tables,
+// compact form"). Per 32 neighbours: (a) float64 decisions, (b) three native 32-bit atomicMax on the key tables,
+// (c) warp barrier, (d) the lanes that hold a slot's key compute the transcendental weights they need (only winners
+// pay for acosf / atan2f) and store their values. After the last neighbour each lane assembles 11 bins.
 constexpr int kShotWarpsPerBlock = 4;
+constexpr int kShotSmemPerWarp = (kKeyCount + kValCount) * 4;
 
 template <typename OutT>
-__global__ void __launch_bounds__(kShotWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     shot_descriptor_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
                            const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr,
                            const double* __restrict__ lrf, int min_nb, int normalize, OutT* __restrict__ out) {
-  extern __shared__ unsigned long long slot_mem[];
+  extern __shared__ uint32_t table_mem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  unsigned long long* slots = slot_mem + warp * kSlotCount;
-  for (int i = lane; i < kSlotCount; i += 32) slots[i] = 0ull;
-  __syncwarp();
+  uint32_t* keys = table_mem + warp * (kKeyCount + kValCount);
+  float* vals = reinterpret_cast<float*>(keys + kKeyCount);
   const int64_t warps_total = int64_t(gridDim.x) * kShotWarpsPerBlock;
   const double inv_radius = 1.0 / radius;
   for (int64_t q = blockIdx.x * int64_t(kShotWarpsPerBlock) + warp; q < nq; q += warps_total) {
+#pragma unroll
+    for (int j = 0; j < kKeyCount / 32; ++j) keys[lane + 32 * j] = 0u;  // values are gated by their keys: no clearing
     const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
     const int64_t begin = offsets[q], end = offsets[q + 1];
     double f[9];
@@ -119,7 +125,6 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32)
     for (int k = 0; k < 9; ++k) f[k] = __ldg(lrf + 9 * q + k);
     int positive = 0;
     // software pipeline: the gathers of the lane's NEXT neighbour are issued before the current one is processed
-    // (ncu round 1: a quarter of the stall samples sat on the first use of the gathered point / normal)
     int64_t i = begin + lane;
     double4 p_next = make_double4(0, 0, 0, 0), n_next = p_next;
     if (i < end) {
@@ -127,52 +132,60 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32)
       p_next = load_pt(g.pts + s);
       n_next = load_pt(g.nrm + s);
     }
-    for (; i < end; i += 32) {
+    __syncwarp();
+    for (int64_t base = begin; base < end; base += 32, i += 32) {  // warp-uniform trip count (barriers inside)
       const double4 p = p_next, n = n_next;
       if (i + 32 < end) {
         const int s = __ldg(nbr + i + 32);
         p_next = load_pt(g.pts + s);
         n_next = load_pt(g.nrm + s);
       }
-      const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
-      const double d2 = rdist3(cx, cy, cz);
-      if (d2 > 0.0) {  // shot.py:213: neighbours at distance 0 (the query itself, duplicates) are dropped
-        ++positive;
-        const double rho = sqrt(d2);
-        const double X = cx * f[0] + cy * f[3] + cz * f[6];
-        const double Y = cx * f[1] + cy * f[4] + cz * f[7];
-        const double Z = cx * f[2] + cy * f[5] + cz * f[8];
-        double cosine = n.x * f[2] + n.y * f[5] + n.z * f[8];
-        cosine = fmin(1.0, fmax(-1.0, cosine));
-        const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius, inv_radius);
-        int slot[7];
-        float val[7];
-        shot_slots(rec, slot, val);
-#pragma unroll
-        for (int k = 0; k < 7; ++k) atomicMax(slots + slot[k], pack_slot(rec.key, val[k]));
+      ShotDecision d;
+      bool active = false;
+      if (i < end) {
+        const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+        const double d2 = rdist3(cx, cy, cz);
+        if (d2 > 0.0) {  // shot.py:213: neighbours at distance 0 (the query itself, duplicates) are dropped
+          active = true;
+          ++positive;
+          const double rho = sqrt(d2);
+          const double X = cx * f[0] + cy * f[3] + cz * f[6];
+          const double Y = cx * f[1] + cy * f[4] + cz * f[7];
+          const double Z = cx * f[2] + cy * f[5] + cz * f[8];
+          double cosine = n.x * f[2] + n.y * f[5] + n.z * f[8];
+          cosine = fmin(1.0, fmax(-1.0, cosine));
+          d = shot_decide(X, Y, Z, cosine, rho, radius, inv_radius);
+          atomicMax(keys + kKeyOwn + d.own, d.key);
+          atomicMax(keys + kKeyCos + d.cos_nb, d.key);
+          atomicMax(keys + kKeyAz + d.az_nb, d.key);
+        }
       }
+      __syncwarp();
+      if (active) {
+        const bool win_own = keys[kKeyOwn + d.own] == d.key;
+        const bool win_cos = keys[kKeyCos + d.cos_nb] == d.key;
+        const bool win_az = keys[kKeyAz + d.az_nb] == d.key;
+        float a_az = 0.0f;
+        if (win_own || win_az) a_az = shot_azimuth(d);
+        if (win_own) {
+          float own_vol, other_vol;
+          shot_elevation(d, own_vol, other_vol);
+          vals[kValOwn + d.own] = (1.0f - d.a_cos) + d.own_shell + own_vol + (1.0f - a_az);
+          vals[kValRad + d.own] = d.other_shell;
+          vals[kValEl + d.own] = other_vol;
+        }
+        if (win_cos) vals[kValCos + d.cos_nb] = d.a_cos;
+        if (win_az) vals[kValAz + d.az_nb] = a_az;
+      }
+      __syncwarp();  // the stores above are ordered before the next round's key updates
     }
     positive = warp_sum(positive);
-    __syncwarp();
-    // bins lane, lane + 32, ...; every slot is read by exactly one bin, which also clears it for the next query
     float v[kShotLen / 32];
     double sq = 0.0;
 #pragma unroll
     for (int j = 0; j < kShotLen / 32; ++j) {
-      const int flat = lane + 32 * j;
-      v[j] = shot_bin_value(slots, flat);
+      v[j] = shot_bin_value_compact(keys, vals, lane + 32 * j);
       sq += double(v[j]) * double(v[j]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < kShotLen / 32; ++j) {
-      const int flat = lane + 32 * j;
-      const int ri = flat & 1, ei = (flat >> 1) & 1;
-      slots[kSlotOwn + flat] = 0ull;
-      slots[kSlotCos + flat] = 0ull;
-      slots[kSlotAz + flat] = 0ull;
-      slots[(ri ? kSlotRad1 : kSlotRad0) + drop_rad(flat)] = 0ull;
-      slots[(ei ? kSlotEl1 : kSlotEl0) + drop_el(flat)] = 0ull;
     }
     sq = warp_sum(sq);
     const double norm = sqrt(sq);
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32)
     OutT* row = out + q * kShotLen;
 #pragma unroll
     for (int j = 0; j < kShotLen / 32; ++j) row[lane + 32 * j] = OutT(v[j] * inv);
-    __syncwarp();
+    __syncwarp();  // all lanes have read the tables before the next query clears the keys
   }
 }
 
@@ -209,16 +222,16 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_descriptor: grid built without normals");
   SF_REQUIRE(queries && offsets && lrf && out && nq >= 0, SF_ERR_ARG, "sf_shot_descriptor: bad arguments");
   if (nq == 0) return SF_OK;
-  const size_t smem = size_t(kShotWarpsPerBlock) * kSlotCount * sizeof(unsigned long long);
+  const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
   static bool configured = false;
   if (!configured) {
     SF_CUDA(cudaFuncSetAttribute(shot_descriptor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     SF_CUDA(cudaFuncSetAttribute(shot_descriptor_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured = true;
   }
-  // persistent-style launch: 148 SMs x 4 resident blocks (56 KB shared memory each), capped by the work
+  // persistent-style launch: 148 SMs x 5 resident blocks (44 KB shared memory each), capped by the work
   const int64_t blocks_needed = (nq + kShotWarpsPerBlock - 1) / kShotWarpsPerBlock;
-  const unsigned blocks = unsigned(blocks_needed < 148 * 4 ? blocks_needed : 148 * 4);
+  const unsigned blocks = unsigned(blocks_needed < 148 * 5 ? blocks_needed : 148 * 5);
   if (out_is_f64)
     shot_descriptor_kernel<double><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
         g->view(), queries, nq, radius, offsets, nbr, lrf, min_nb, normalize, static_cast<double*>(out));

@@ -59,35 +59,59 @@ void hm_lrf(const double* point, const double* nbrs, int k, double radius, doubl
   }
 }
 
-// Mirrors shot_descriptor_kernel for one query (atomicMax replaced by a sequential max).
+// Mirrors shot_descriptor_kernel for one query: compact winner tables, neighbours taken 32 at a time (key pass,
+// then value pass), atomicMax replaced by a sequential max.
 void hm_shot_descriptor(const double* point, const double* nbrs, const double* normals, int k, double radius,
                         const double* f, int normalize, int min_nb, float* out352) {
-  std::vector<unsigned long long> slots(kSlotCount, 0ull);
+  std::vector<uint32_t> keys(kKeyCount, 0u);
+  std::vector<float> vals(kValCount, 0.0f);
   int positive = 0;
-  for (int i = 0; i < k; ++i) {
-    const double cx = nbrs[3 * i] - point[0], cy = nbrs[3 * i + 1] - point[1], cz = nbrs[3 * i + 2] - point[2];
-    const double d2 = rdist3(cx, cy, cz);
-    if (!(d2 > 0.0)) continue;
-    ++positive;
-    const double rho = sqrt(d2);
-    const double X = cx * f[0] + cy * f[3] + cz * f[6];
-    const double Y = cx * f[1] + cy * f[4] + cz * f[7];
-    const double Z = cx * f[2] + cy * f[5] + cz * f[8];
-    double cosine = normals[3 * i] * f[2] + normals[3 * i + 1] * f[5] + normals[3 * i + 2] * f[8];
-    cosine = fmin(1.0, fmax(-1.0, cosine));
-    const ShotRecord rec = shot_record(X, Y, Z, cosine, rho, radius, 1.0 / radius);
-    int slot[7];
-    float val[7];
-    shot_slots(rec, slot, val);
-    for (int s = 0; s < 7; ++s) {
-      const unsigned long long w = pack_slot(rec.key, val[s]);
-      if (w > slots[slot[s]]) slots[slot[s]] = w;
+  const double inv_radius = 1.0 / radius;
+  for (int base = 0; base < k; base += 32) {
+    ShotDecision d[32];
+    bool active[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      active[lane] = false;
+      const int i = base + lane;
+      if (i >= k) continue;
+      const double cx = nbrs[3 * i] - point[0], cy = nbrs[3 * i + 1] - point[1], cz = nbrs[3 * i + 2] - point[2];
+      const double d2 = rdist3(cx, cy, cz);
+      if (!(d2 > 0.0)) continue;
+      active[lane] = true;
+      ++positive;
+      const double rho = sqrt(d2);
+      const double X = cx * f[0] + cy * f[3] + cz * f[6];
+      const double Y = cx * f[1] + cy * f[4] + cz * f[7];
+      const double Z = cx * f[2] + cy * f[5] + cz * f[8];
+      double cosine = normals[3 * i] * f[2] + normals[3 * i + 1] * f[5] + normals[3 * i + 2] * f[8];
+      cosine = fmin(1.0, fmax(-1.0, cosine));
+      d[lane] = shot_decide(X, Y, Z, cosine, rho, radius, inv_radius);
+      if (d[lane].key > keys[kKeyOwn + d[lane].own]) keys[kKeyOwn + d[lane].own] = d[lane].key;
+      if (d[lane].key > keys[kKeyCos + d[lane].cos_nb]) keys[kKeyCos + d[lane].cos_nb] = d[lane].key;
+      if (d[lane].key > keys[kKeyAz + d[lane].az_nb]) keys[kKeyAz + d[lane].az_nb] = d[lane].key;
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      if (!active[lane]) continue;
+      const ShotDecision& e = d[lane];
+      const bool win_own = keys[kKeyOwn + e.own] == e.key, win_cos = keys[kKeyCos + e.cos_nb] == e.key,
+                 win_az = keys[kKeyAz + e.az_nb] == e.key;
+      float a_az = 0.0f;
+      if (win_own || win_az) a_az = shot_azimuth(e);
+      if (win_own) {
+        float own_vol, other_vol;
+        shot_elevation(e, own_vol, other_vol);
+        vals[kValOwn + e.own] = (1.0f - e.a_cos) + e.own_shell + own_vol + (1.0f - a_az);
+        vals[kValRad + e.own] = e.other_shell;
+        vals[kValEl + e.own] = other_vol;
+      }
+      if (win_cos) vals[kValCos + e.cos_nb] = e.a_cos;
+      if (win_az) vals[kValAz + e.az_nb] = a_az;
     }
   }
   double sq = 0.0;
   float v[kShotLen];
   for (int b = 0; b < kShotLen; ++b) {
-    v[b] = shot_bin_value(slots.data(), b);
+    v[b] = shot_bin_value_compact(keys.data(), vals.data(), b);
     sq += double(v[b]) * double(v[b]);
   }
   const double norm = sqrt(sq);

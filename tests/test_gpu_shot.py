@@ -128,6 +128,26 @@ def test_oracle_parity_dense_queries_100k_cloud():
     _check_rows(got, want, "oracle/100k")
 
 
+def test_large_neighbourhoods_and_offset_coordinates():
+    """K ~ 650 neighbours per query (radius 15 x spacing), and a cloud far from the origin (large float64 offsets)."""
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor
+
+    n = 50000
+    pts, normals = synthetic.bumpy_sphere(n, seed=13)
+    radius = 15.0 * synthetic.mean_spacing(n)
+    kp = pts[::250]
+    want = shot_oracle.shot_single_scale(pts, normals, kp, radius, True, 100)
+    with ShotMultiprocessor(verbose=False) as shot:  # the reference default min_neighborhood_size = 100 is fine here
+        got = shot.compute_descriptor_single_scale(pts, normals, kp, radius)
+        _check_rows(got, want, "K~650")
+        shift = np.array([4.0e5, -2.5e6, 1.0e4])  # UTM-like coordinates: differences are still exact in float64
+        radius2 = 5.0 * synthetic.mean_spacing(n)
+        want2 = shot_oracle.shot_single_scale(pts + shift, normals, kp + shift, radius2, True, 10)
+    with ShotMultiprocessor(min_neighborhood_size=10, verbose=False) as shot:
+        got2 = shot.compute_descriptor_single_scale(pts + shift, normals, kp + shift, radius2)
+    _check_rows(got2, want2, "shifted cloud")
+
+
 def test_bi_scale_and_multiscale_against_oracle():
     from shot_fpfh_b200.descriptors import ShotMultiprocessor
     from sklearn.neighbors import KDTree
