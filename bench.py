@@ -38,7 +38,7 @@ N_POINTS = 1_000_000
 QUERY_VOXEL_IN_SPACINGS = 3.75
 RADIUS_IN_SPACINGS = 5.0
 MIN_NB = 10
-OWN_KERNELS_PER_SHOT_STEP = 9  # bbox_init, bbox, key, reorder, radius<count>, widen_total, radius<fill>, shot_lrf, shot_descriptor
+OWN_KERNELS_PER_SHOT_STEP = 8  # bbox_init, bbox, key, reorder, candidate_count, search_moments, lrf_eigen, shot_descriptor
 
 
 def parse_args():
@@ -189,8 +189,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def timed_steps(step_fn, steps: int, warmup: int, flush, dist=None):
+def timed_steps(step_fn, steps: int, warmup: int, flush, dist=None, after_step=None):
     """W untimed steps, then K steps each bracketed by CUDA events (L2 flushed, untimed, in between).
+    `after_step` runs after the closing event of a step has been recorded (it may synchronise).
     Returns (ms per step = max over ranks of the mean, list of per-stage event dicts)."""
     import torch
 
@@ -209,6 +210,8 @@ def timed_steps(step_fn, steps: int, warmup: int, flush, dist=None):
         a.record()
         step_fn(stage)
         b.record()
+        if after_step is not None:
+            after_step()
         pairs.append((a, b))
         marks.append(stage)
     torch.cuda.synchronize()
@@ -265,29 +268,38 @@ def bench_shot(args, dist, rank, world, pk):
     def flush():
         flush_buf.fill_(1)
 
+    ops.profile_enable(True)
+    kernel_ms = []
+
     def step(stage):
         with mark(stage, "grid_build"):
             grid.build(p_dev, n_dev, radius)
-        with mark(stage, "radius_search"):
-            offsets, nbr, _, _ = ops.radius_csr(grid, k_dev, radius)
-        with mark(stage, "shot_lrf"):
-            lrf = ops.shot_lrf(grid, k_dev, radius, offsets, nbr)
-        with mark(stage, "shot_descriptor"):
-            ops.shot_descriptor(grid, k_dev, radius, offsets, nbr, lrf, MIN_NB, True, out=out)
-        counts["pairs"] = int(nbr.shape[0])
+        # the fused single-scale driver: what ShotMultiprocessor.compute_descriptor_single_scale runs
+        _, _, pairs = ops.shot_single_scale(grid, k_dev, radius, MIN_NB, True, out=out, want_pairs="pairs" not in counts)
+        if pairs is not None:
+            counts["pairs"] = pairs
+
+    def read_kernel_events():  # CUDA events recorded by the driver around its three kernels; outside the bracket
+        kernel_ms.append(ops.profile_read())
 
     sampler = ClockSampler(torch.cuda.current_device())
-    ms, stages = timed_steps(step, args.steps, args.warmup, flush, dist)
+    ms, stages = timed_steps(step, args.steps, args.warmup, flush, dist, after_step=read_kernel_events)
+    ops.profile_enable(False)
+    k_ms = np.mean(np.array(kernel_ms), axis=0)
+    stages.update({"search_moments": float(k_ms[0]), "lrf_eigen": float(k_ms[1]), "votes_descriptor": float(k_ms[2])})
     pairs = counts["pairs"]
     nonzero_rows = int((out.abs().sum(dim=1) > 0).sum().item())
     value = world * q / (ms * 1e-3)
 
     # algorithmic bytes per launch (float32 payloads, int32 indices)
+    # B_search = 12N + 12Q + 4P + 4(Q+1), B_lrf = 16P + 48Q, B_shot = 28P + 48Q + 1408Q. The fused
+    # driver finds the neighbours and accumulates the frame's moments in one kernel (B_search + the 48Q frame
+    # scratch) and runs the frame's sign votes inside the descriptor kernel (B_shot + the 16P gather of B_lrf).
     alg = {
         "grid_build": 52 * n,
-        "radius_search": 12 * n + 12 * q + 4 * pairs + 4 * (q + 1),
-        "shot_lrf": 16 * pairs + 12 * q + 36 * q,
-        "shot_descriptor": 28 * pairs + 48 * q + 4 * 352 * q,
+        "search_moments": 12 * n + 12 * q + 4 * pairs + 4 * (q + 1) + 48 * q,
+        "lrf_eigen": 2 * 48 * q,
+        "votes_descriptor": 28 * pairs + 48 * q + 4 * 352 * q + 16 * pairs,
     }
     dominant = max(stages, key=stages.get)
     achieved = alg[dominant] / (stages[dominant] * 1e-3) / 1e9

@@ -119,6 +119,22 @@ int sf_shot_descriptor(sf_grid* grid, const double* queries_dev, int64_t nq, dou
                        int32_t min_neighborhood_size, int32_t normalize, void* out_dev, int32_t out_is_f64,
                        void* stream);
 
+/* The whole single-scale driver in one call: replaces `compute_descriptor_single_scale` (shot_parallelization.py:
+ * 135-183) after the grid is built — query_radius, compute_local_rf and compute_descriptor on the same neighbourhoods.
+ * Same results as sf_radius_* + sf_shot_lrf + sf_shot_descriptor, but the neighbour list stays an internal (padded)
+ * temporary: ONE pass over the candidate cells finds the neighbours and accumulates the frame's moments, and the sign
+ * votes run inside the descriptor kernel. lrf_out_dev (nq,3,3) and pairs_host (number of neighbour pairs found) are
+ * optional. Synchronises `stream` once (to size the temporary). */
+int sf_shot_single_scale(sf_grid* grid, const double* queries_dev, int64_t nq, double radius,
+                         int32_t min_neighborhood_size, int32_t normalize, void* out_dev, int32_t out_is_f64,
+                         double* lrf_out_dev, int64_t* pairs_host, void* stream);
+
+/* Measurement hook: with profiling enabled, sf_shot_single_scale records CUDA events on its stream around its three
+ * kernels; sf_profile_read waits for the last call and returns their durations in milliseconds:
+ * ms_out[0] = search + moments, ms_out[1] = eigen-decomposition, ms_out[2] = sign votes + descriptor. */
+int sf_profile_enable(int32_t enable);
+int sf_profile_read(float* ms_out3);
+
 /* ------------------------------------------------------------------------------------------------------------
  * P — FPFH.  Replaces `compute_fpfh_descriptor` (fpfh.py:16-117).
  * ---------------------------------------------------------------------------------------------------------- */

@@ -53,6 +53,11 @@ def _load() -> ctypes.CDLL:
             c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
             c_void_p,
         ],
+        "sf_shot_single_scale": [
+            c_void_p, c_void_p, c_int64, c_double, c_int32, c_int32, c_void_p, c_int32, c_void_p, p_i64, c_void_p,
+        ],
+        "sf_profile_enable": [c_int32],
+        "sf_profile_read": [POINTER(c_float)],
         "sf_spfh": [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, p_f64, c_void_p, c_void_p],
         "sf_fpfh": [
             c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32,
@@ -80,7 +85,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTS = (
     "sf_last_error sf_abi_version sf_grid_create sf_grid_destroy sf_grid_build sf_grid_info sf_grid_permutation "
-    "sf_radius_count sf_radius_fill sf_voxel_subsample sf_knn sf_pca_normals sf_shot_lrf sf_shot_descriptor sf_spfh sf_fpfh sf_nonempty_rows sf_match_pack "
+    "sf_radius_count sf_radius_fill sf_voxel_subsample sf_knn sf_pca_normals sf_shot_lrf sf_shot_descriptor sf_shot_single_scale sf_profile_enable sf_profile_read sf_spfh sf_fpfh sf_nonempty_rows sf_match_pack "
     "sf_match_topk sf_topk_merge sf_match_rerank"
 ).split()
 

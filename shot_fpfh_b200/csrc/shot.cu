@@ -7,91 +7,176 @@
 // largest distance that addresses the bin contributes (even with value 0). Each warp owns a table of 1760
 // 64-bit words in shared memory, one word per (statement group, bin): (distance key << 32) | float value, updated
 // with atomicMax. The largest key wins and carries its value along; bins then sum their five tables.
+#include <cub/cub.cuh>
+
 #include "sf_common.cuh"
 
 namespace sf {
 
 // ---- S1 ----------------------------------------------------------------------------------------------------
-// One warp owns a batch of 32 consecutive queries. Phase A: the 32 lanes stride over the neighbours of query j and
-// reduce its 7 weighted moments, which lane j keeps. Phase B: every lane solves ITS OWN query's 3x3 eigenproblem
-// (the LAPACK-path solver is a long serial chain: one per lane = 32 in flight, instead of 32 lanes redundantly
-// solving one). Phase C: the axes of lane j are broadcast and the warp counts the sign votes of query j.
-__global__ void __launch_bounds__(128)
-    shot_lrf_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
-                    const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr, double* __restrict__ lrf) {
+// Three launches; the (nq, 3, 3) output buffer doubles as scratch between them (9 float64 per query):
+//   lrf_moments_kernel  warp per query   : 6 weighted second moments by warp reduction          -> out[0..5], K -> out[6]
+//   lrf_eigen_kernel    THREAD per query : LAPACK-path 3x3 eigensolver (a long serial chain: run 32 independent
+//                                          ones per warp instead of one per warp)               -> x, z axes in out[0..5]
+//   lrf_votes_kernel    warp per query   : sign votes, y = z cross x, final row-major frame      -> out[0..8]
+// (Round 1 history: one warp doing all three for one query took 690 us at C2, a warp per batch of 32 queries 240 us
+// but with only 3 200 warps in flight for the two gather passes; this split keeps 100k warps available for them.)
+__global__ void __launch_bounds__(256)
+    lrf_moments_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
+                       const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr, double* __restrict__ lrf) {
   const int lane = threadIdx.x & 31;
-  const int64_t q0 = ((blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5) * 32;
-  if (q0 >= nq) return;
-  const int batch = int(nq - q0 < 32 ? nq - q0 : 32);
-  // this lane's query
-  const int64_t mine = q0 + (lane < batch ? lane : 0);
-  const int64_t my_begin = __ldg(offsets + mine), my_end = __ldg(offsets + mine + 1);
-  const double my_qx = __ldg(queries + 3 * mine), my_qy = __ldg(queries + 3 * mine + 1), my_qz = __ldg(queries + 3 * mine + 2);
-  // ---- phase A: weighted covariance, weights (radius - distance), over ALL neighbours incl. the query itself (F5)
-  double mom[6] = {0, 0, 0, 0, 0, 0};
-  for (int j = 0; j < batch; ++j) {
-    const int64_t begin = __shfl_sync(kFull, my_begin, j), end = __shfl_sync(kFull, my_end, j);
-    const double qx = __shfl_sync(kFull, my_qx, j), qy = __shfl_sync(kFull, my_qy, j), qz = __shfl_sync(kFull, my_qz, j);
-    double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t i = begin + lane; i < end; i += 32) {
-      const double4 p = load_pt(g.pts + __ldg(nbr + i));
-      const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
-      const double w = radius - sqrt(rdist3(cx, cy, cz));
-      sw += w;
-      m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
-      m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
-    }
-    sw = warp_sum(sw);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const double v = warp_sum(m[k]) / sw;
-      if (lane == j) mom[k] = v;
-    }
+  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
+  const int64_t begin = offsets[q], end = offsets[q + 1];
+  // weighted covariance, weights (radius - distance), over ALL neighbours incl. the query itself (F5)
+  double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t i = begin + lane; i < end; i += 32) {
+    const double4 p = load_pt(g.pts + __ldg(nbr + i));
+    const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+    const double w = radius - sqrt(rdist3(cx, cy, cz));
+    sw += w;
+    m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
+    m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
   }
-  // ---- phase B: one eigen-decomposition per lane
-  double x[3] = {1, 0, 0}, z[3] = {0, 0, 1};
-  const bool has_neighbours = lane < batch && my_end > my_begin;
-  if (has_neighbours) {
-    double eval[3], evec[3][3];
-    eigh3(mom, eval, evec);
-    x[0] = evec[2][0]; x[1] = evec[2][1]; x[2] = evec[2][2];  // largest eigenvalue
-    z[0] = evec[0][0]; z[1] = evec[0][1]; z[2] = evec[0][2];  // smallest eigenvalue
-  }
-  // ---- phase C: sign votes (shot.py:40-45): flip when strictly more neighbours project negatively than not
-  int my_neg_x = 0, my_neg_z = 0;
-  for (int j = 0; j < batch; ++j) {
-    const int64_t begin = __shfl_sync(kFull, my_begin, j), end = __shfl_sync(kFull, my_end, j);
-    const double qx = __shfl_sync(kFull, my_qx, j), qy = __shfl_sync(kFull, my_qy, j), qz = __shfl_sync(kFull, my_qz, j);
-    const double x0 = __shfl_sync(kFull, x[0], j), x1 = __shfl_sync(kFull, x[1], j), x2 = __shfl_sync(kFull, x[2], j);
-    const double z0 = __shfl_sync(kFull, z[0], j), z1 = __shfl_sync(kFull, z[1], j), z2 = __shfl_sync(kFull, z[2], j);
-    int neg_x = 0, neg_z = 0;
-    for (int64_t i = begin + lane; i < end; i += 32) {
-      const double4 p = load_pt(g.pts + __ldg(nbr + i));
-      const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
-      neg_x += (cx * x0 + cy * x1 + cz * x2) < 0.0;
-      neg_z += (cx * z0 + cy * z1 + cz * z2) < 0.0;
-    }
-    neg_x = warp_sum(neg_x);
-    neg_z = warp_sum(neg_z);
-    if (lane == j) { my_neg_x = neg_x; my_neg_z = neg_z; }
-  }
-  if (lane < batch) {
-    double* out = lrf + 9 * mine;
-    if (!has_neighbours) {  // shot.py:24-25
+  sw = warp_sum(sw);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) out[k] = (k % 4 == 0) ? 1.0 : 0.0;
-    } else {
-      const int k_all = int(my_end - my_begin);
-      if (my_neg_x > k_all - my_neg_x) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
-      if (my_neg_z > k_all - my_neg_z) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
-      const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+  for (int k = 0; k < 6; ++k) m[k] = warp_sum(m[k]);
+  if (lane < 6) {
+    double v = m[0];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {  // row a of the matrix whose columns are [x y z]
-        out[3 * a + 0] = x[a];
-        out[3 * a + 1] = y[a];
-        out[3 * a + 2] = z[a];
+    for (int k = 1; k < 6; ++k) v = lane == k ? m[k] : v;
+    lrf[9 * q + lane] = end > begin ? v / sw : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    lrf_eigen_kernel(int64_t nq, const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
+                     double* __restrict__ lrf) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= nq) return;
+  if (counts ? counts[q] == 0 : offsets[q + 1] == offsets[q]) return;  // empty: the votes step writes the identity
+  double m[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m[k] = lrf[9 * q + k];
+  double eval[3], evec[3][3];
+  eigh3(m, eval, evec);
+  lrf[9 * q + 0] = evec[2][0]; lrf[9 * q + 1] = evec[2][1]; lrf[9 * q + 2] = evec[2][2];  // x: largest eigenvalue
+  lrf[9 * q + 3] = evec[0][0]; lrf[9 * q + 4] = evec[0][1]; lrf[9 * q + 5] = evec[0][2];  // z: smallest eigenvalue
+}
+
+__global__ void __launch_bounds__(256)
+    lrf_votes_kernel(GridView g, const double* __restrict__ queries, int64_t nq, const int64_t* __restrict__ offsets,
+                     const int32_t* __restrict__ nbr, double* __restrict__ lrf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const int64_t begin = offsets[q], end = offsets[q + 1];
+  double* out = lrf + 9 * q;
+  if (end == begin) {  // shot.py:24-25
+    if (lane < 9) out[lane] = (lane % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
+  double x[3] = {out[0], out[1], out[2]}, z[3] = {out[3], out[4], out[5]};
+  // sign votes (shot.py:40-45): flip when strictly more neighbours project negatively than non-negatively
+  int neg_x = 0, neg_z = 0;
+  for (int64_t i = begin + lane; i < end; i += 32) {
+    const double4 p = load_pt(g.pts + __ldg(nbr + i));
+    const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+    neg_x += (cx * x[0] + cy * x[1] + cz * x[2]) < 0.0;
+    neg_z += (cx * z[0] + cy * z[1] + cz * z[2]) < 0.0;
+  }
+  neg_x = warp_sum(neg_x);
+  neg_z = warp_sum(neg_z);
+  const int k_all = int(end - begin);
+  if (neg_x > k_all - neg_x) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
+  if (neg_z > k_all - neg_z) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
+  const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+  __syncwarp();  // every lane has read the axes before the frame overwrites them
+  if (lane < 3) {  // row `lane` of the matrix whose columns are [x y z] (selects, not indexing: stays in registers)
+    out[3 * lane + 0] = lane == 0 ? x[0] : (lane == 1 ? x[1] : x[2]);
+    out[3 * lane + 1] = lane == 0 ? y[0] : (lane == 1 ? y[1] : y[2]);
+    out[3 * lane + 2] = lane == 0 ? z[0] : (lane == 1 ? z[1] : z[2]);
+  }
+}
+
+// ---- fused single-scale driver: search + moments in ONE pass over the candidates ----------------------------------
+// The generic path scans the 27 cells twice (count, fill) and gathers the neighbours twice more for the frame
+// (moments, votes). For the single-scale driver (shot_parallelization.py:135-183, the pipeline's default and the
+// benchmark's headline) the neighbour list is an internal temporary, so it can be PADDED: query q owns the slots
+// [cand_offsets[q], cand_offsets[q+1]) sized by its candidate count (a cell_start lookup, no distance test), the
+// one scan writes the hits there, counts them and accumulates the frame's weighted moments while the points are
+// in registers. The votes then run inside the descriptor kernel.
+__global__ void __launch_bounds__(256)
+    candidate_count_kernel(GridView g, const double* __restrict__ queries, int64_t nq, int64_t* __restrict__ cand) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= nq) return;
+  const int cx = cell_coord(queries[3 * q], g.origin[0], g.inv_cell, g.dims[0]);
+  const int cy = cell_coord(queries[3 * q + 1], g.origin[1], g.inv_cell, g.dims[1]);
+  const int cz = cell_coord(queries[3 * q + 2], g.origin[2], g.inv_cell, g.dims[2]);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+  int total = 0;
+  if (x0 <= x1) {
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = cy + dy, zz = cz + dz;
+        if (yy < 0 || yy >= g.dims[1] || zz < 0 || zz >= g.dims[2]) continue;
+        const int64_t base = (int64_t(zz) * g.dims[1] + yy) * g.dims[0];
+        total += __ldg(g.cell_start + base + x1 + 1) - __ldg(g.cell_start + base + x0);
+      }
+  }
+  cand[q] = total;
+}
+
+__global__ void __launch_bounds__(256)
+    search_moments_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius, double r2,
+                          const int64_t* __restrict__ cand_offsets, int32_t* __restrict__ nbr,
+                          int32_t* __restrict__ counts, double* __restrict__ lrf,
+                          unsigned long long* __restrict__ pair_counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
+  const Runs runs = build_runs(g, qx, qy, qz, lane);
+  const int total = runs.pref[9];
+  int64_t out = cand_offsets[q];
+  int count = 0;
+  double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
+  for (int base = 0; base < total; base += 32) {
+    const int v = base + lane;
+    bool hit = false;
+    int pos = 0;
+    if (v < total) {
+      pos = run_position(runs, v);
+      const double4 p = load_pt(g.pts + pos);
+      const double cx = qx - p.x, cy = qy - p.y, cz = qz - p.z;  // second moments do not see the sign
+      const double d2 = rdist3(cx, cy, cz);
+      hit = d2 <= r2;
+      if (hit) {
+        const double w = radius - sqrt(d2);
+        sw += w;
+        m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
+        m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
       }
     }
+    const unsigned mask = __ballot_sync(kFull, hit);
+    if (hit) nbr[out + __popc(mask & lanemask_lt())] = pos;
+    out += __popc(mask);
+    count += __popc(mask);
+  }
+  sw = warp_sum(sw);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m[k] = warp_sum(m[k]);
+  if (lane < 6) {
+    double v = m[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) v = lane == k ? m[k] : v;
+    lrf[9 * q + lane] = count > 0 ? v / sw : 0.0;
+  }
+  if (lane == 0) {
+    counts[q] = count;
+    atomicAdd(pair_counter, static_cast<unsigned long long>(count));
   }
 }
 
@@ -106,8 +191,14 @@ constexpr int kShotSmemPerWarp = (kKeyCount + kValCount) * 4;
 template <typename OutT>
 __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     shot_descriptor_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
-                           const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr,
-                           const double* __restrict__ lrf, int min_nb, int normalize, OutT* __restrict__ out) {
+                           const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
+                           const int32_t* __restrict__ nbr, double* __restrict__ lrf, int fuse_votes, int min_nb,
+                           int normalize, OutT* __restrict__ out) {
+  // counts == nullptr: classic CSR, neighbours of q are nbr[offsets[q] .. offsets[q+1]). Otherwise a padded list:
+  // nbr[offsets[q] .. offsets[q] + counts[q]) (the fused single-scale driver).
+  // fuse_votes: lrf[9q + 0..5] holds the RAW eigenvectors (x, z) from lrf_eigen_kernel; the sign votes of
+  // shot.py:40-45 run here (the second pass over the same neighbours then hits L1) and the final frame is written
+  // back to lrf[9q + 0..8].
   extern __shared__ uint32_t table_mem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -119,10 +210,39 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
 #pragma unroll
     for (int j = 0; j < kKeyCount / 32; ++j) keys[lane + 32 * j] = 0u;  // values are gated by their keys: no clearing
     const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
-    const int64_t begin = offsets[q], end = offsets[q + 1];
+    const int64_t begin = offsets[q], end = counts ? begin + counts[q] : offsets[q + 1];
     double f[9];
+    if (!fuse_votes) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) f[k] = __ldg(lrf + 9 * q + k);
+      for (int k = 0; k < 9; ++k) f[k] = lrf[9 * q + k];
+    } else if (end == begin) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = (k % 4 == 0) ? 1.0 : 0.0;  // shot.py:24-25
+      __syncwarp();
+      if (lane < 9) lrf[9 * q + lane] = (lane % 4 == 0) ? 1.0 : 0.0;
+    } else {
+      double x[3] = {lrf[9 * q], lrf[9 * q + 1], lrf[9 * q + 2]}, z[3] = {lrf[9 * q + 3], lrf[9 * q + 4], lrf[9 * q + 5]};
+      int neg_x = 0, neg_z = 0;
+      for (int64_t i = begin + lane; i < end; i += 32) {
+        const double4 p = load_pt(g.pts + __ldg(nbr + i));
+        const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+        neg_x += (cx * x[0] + cy * x[1] + cz * x[2]) < 0.0;
+        neg_z += (cx * z[0] + cy * z[1] + cz * z[2]) < 0.0;
+      }
+      neg_x = warp_sum(neg_x);
+      neg_z = warp_sum(neg_z);
+      const int k_all = int(end - begin);
+      if (neg_x > k_all - neg_x) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
+      if (neg_z > k_all - neg_z) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
+      const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { f[3 * a] = x[a]; f[3 * a + 1] = y[a]; f[3 * a + 2] = z[a]; }
+      __syncwarp();  // every lane has read the raw axes before the frame overwrites them
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) lrf[9 * q + k] = f[k];
+      }
+    }
     int positive = 0;
     // software pipeline: the gathers of the lane's NEXT neighbour are issued before the current one is processed
     int64_t i = begin + lane;
@@ -209,19 +329,37 @@ extern "C" int sf_shot_lrf(sf_grid* g, const double* queries, int64_t nq, double
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_shot_lrf: grid not built");
   SF_REQUIRE(queries && offsets && lrf && nq >= 0, SF_ERR_ARG, "sf_shot_lrf: bad arguments");
   if (nq == 0) return SF_OK;
-  const int64_t warps = (nq + 31) / 32;  // one warp per batch of 32 queries
-  shot_lrf_kernel<<<unsigned((warps + 3) / 4), 128, 0, stream>>>(g->view(), queries, nq, radius, offsets, nbr, lrf);
+  const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
+  lrf_moments_kernel<<<warp_blocks, 256, 0, stream>>>(g->view(), queries, nq, radius, offsets, nbr, lrf);
+  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, offsets, nullptr, lrf);
+  lrf_votes_kernel<<<warp_blocks, 256, 0, stream>>>(g->view(), queries, nq, offsets, nbr, lrf);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
 
-extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq, double radius,
-                                  const int64_t* offsets, const int32_t* nbr, const double* lrf, int32_t min_nb,
-                                  int32_t normalize, void* out, int32_t out_is_f64, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_descriptor: grid built without normals");
-  SF_REQUIRE(queries && offsets && lrf && out && nq >= 0, SF_ERR_ARG, "sf_shot_descriptor: bad arguments");
-  if (nq == 0) return SF_OK;
+// Optional per-kernel timing of the fused driver (bench.py's roofline needs the dominant kernel's own duration and
+// the driver is a single C call): CUDA events recorded on the launching stream around its three kernels.
+static bool g_profile = false;
+static cudaEvent_t g_events[4] = {nullptr, nullptr, nullptr, nullptr};
+
+extern "C" int sf_profile_enable(int32_t enable) {
+  if (enable && g_events[0] == nullptr)
+    for (auto& e : g_events) SF_CUDA(cudaEventCreate(&e));
+  g_profile = enable != 0;
+  return SF_OK;
+}
+
+// ms_out[0..2] = search+moments, eigen, votes+descriptor of the LAST sf_shot_single_scale call (synchronises).
+extern "C" int sf_profile_read(float* ms_out) {
+  SF_REQUIRE(g_profile && g_events[0] != nullptr && ms_out != nullptr, SF_ERR_ARG, "sf_profile_read: profiling is off");
+  SF_CUDA(cudaEventSynchronize(g_events[3]));
+  for (int i = 0; i < 3; ++i) SF_CUDA(cudaEventElapsedTime(ms_out + i, g_events[i], g_events[i + 1]));
+  return SF_OK;
+}
+
+static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, double radius, const int64_t* offsets,
+                             const int32_t* counts, const int32_t* nbr, double* lrf, int fuse_votes, int min_nb,
+                             int normalize, void* out, int out_is_f64, cudaStream_t stream) {
   const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
   static bool configured = false;
   if (!configured) {
@@ -234,10 +372,75 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
   const unsigned blocks = unsigned(blocks_needed < 148 * 5 ? blocks_needed : 148 * 5);
   if (out_is_f64)
     shot_descriptor_kernel<double><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
-        g->view(), queries, nq, radius, offsets, nbr, lrf, min_nb, normalize, static_cast<double*>(out));
+        g->view(), queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<double*>(out));
   else
     shot_descriptor_kernel<float><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
-        g->view(), queries, nq, radius, offsets, nbr, lrf, min_nb, normalize, static_cast<float*>(out));
+        g->view(), queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<float*>(out));
   SF_CUDA(cudaGetLastError());
   return SF_OK;
+}
+
+extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq, double radius,
+                                  const int64_t* offsets, const int32_t* nbr, const double* lrf, int32_t min_nb,
+                                  int32_t normalize, void* out, int32_t out_is_f64, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_descriptor: grid built without normals");
+  SF_REQUIRE(queries && offsets && lrf && out && nq >= 0, SF_ERR_ARG, "sf_shot_descriptor: bad arguments");
+  if (nq == 0) return SF_OK;
+  return launch_descriptor(g, queries, nq, radius, offsets, nullptr, nbr, const_cast<double*>(lrf), 0, min_nb, normalize,
+                           out, out_is_f64, stream);
+}
+
+extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t nq, double radius, int32_t min_nb,
+                                    int32_t normalize, void* out, int32_t out_is_f64, double* lrf_out,
+                                    int64_t* pairs_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_single_scale: grid built without normals");
+  SF_REQUIRE(queries && out && nq >= 0, SF_ERR_ARG, "sf_shot_single_scale: bad arguments");
+  SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
+             "sf_shot_single_scale: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
+  if (pairs_host) *pairs_host = 0;
+  if (nq == 0) return SF_OK;
+  int64_t *cand = nullptr, *cand_offsets = nullptr;
+  int32_t *counts = nullptr, *nbr = nullptr;
+  double* lrf = lrf_out;
+  void* scan_temp = nullptr;
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cand, cand_offsets, int(nq + 1), stream);
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand), size_t(nq + 1) * 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand_offsets), size_t(nq + 1) * 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&counts), size_t(nq) * 4, stream));
+  SF_CUDA(scratch_alloc(&scan_temp, scan_bytes + 16, stream));
+  if (lrf == nullptr) SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&lrf), size_t(nq) * 9 * 8, stream));
+  const GridView view = g->view();
+  SF_CUDA(cudaMemsetAsync(cand + nq, 0, 8, stream));
+  unsigned long long* pair_counter = nullptr;
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pair_counter), 8, stream));
+  SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
+  candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(view, queries, nq, cand);
+  SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, cand, cand_offsets, int(nq + 1), stream));
+  int64_t total = 0;
+  SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + nq, 8, cudaMemcpyDeviceToHost, stream));
+  SF_CUDA(cudaStreamSynchronize(stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * 4, stream));
+  const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
+  if (g_profile) cudaEventRecord(g_events[0], stream);
+  search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets, nbr,
+                                                        counts, lrf, pair_counter);
+  if (g_profile) cudaEventRecord(g_events[1], stream);
+  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf);
+  if (g_profile) cudaEventRecord(g_events[2], stream);
+  int rc = launch_descriptor(g, queries, nq, radius, cand_offsets, counts, nbr, lrf, 1, min_nb, normalize, out, out_is_f64,
+                             stream);
+  if (g_profile) cudaEventRecord(g_events[3], stream);
+  if (rc == SF_OK && pairs_host != nullptr) {  // neighbour pairs found (logging / algorithmic-byte accounting)
+    unsigned long long pairs = 0;
+    SF_CUDA(cudaMemcpyAsync(&pairs, pair_counter, 8, cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaStreamSynchronize(stream));
+    *pairs_host = int64_t(pairs);
+  }
+  void* to_free[] = {cand, cand_offsets, counts, nbr, scan_temp, pair_counter, lrf_out == nullptr ? lrf : nullptr};
+  for (void* p : to_free)
+    if (p) cudaFreeAsync(p, stream);
+  return rc;
 }

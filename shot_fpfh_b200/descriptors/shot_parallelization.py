@@ -134,8 +134,16 @@ class ShotMultiprocessor:
         return self._to_host(desc)
 
     # ------------------------------------------------------------------------------------------------------
-    def _single_scale_device(self, grid, keypoints_dev, lrf_radius, shot_radius, lrf=None, out_dtype=torch.float64):
+    def _single_scale_device(self, grid, keypoints_dev, lrf_radius, shot_radius, lrf=None, out_dtype=torch.float64,
+                             need_lrf=False):
         """search -> LRF -> descriptor, all on the device. Returns (descriptors, lrf)."""
+        if lrf is None and shot_radius == lrf_radius:
+            # frames and descriptors on the same neighbourhoods: the fused driver (one pass over the candidate cells)
+            desc, lrf, _ = ops.shot_single_scale(
+                grid, keypoints_dev, shot_radius, self.min_neighborhood_size, self.normalize, out_dtype=out_dtype,
+                want_lrf=need_lrf,
+            )
+            return desc, lrf
         offsets, nbr, _, _ = ops.radius_csr(grid, keypoints_dev, lrf_radius)
         if lrf is None:
             lrf = ops.shot_lrf(grid, keypoints_dev, lrf_radius, offsets, nbr)
@@ -206,7 +214,7 @@ class ShotMultiprocessor:
             voxel = None if voxel_sizes is None else float(voxel_sizes[scale])
             grid, _, _ = self._support(point_cloud, normals, voxel, radius)
             desc, new_lrf = self._single_scale_device(
-                grid, kp, radius, radius, lrf=lrf if self.share_local_rfs else None
+                grid, kp, radius, radius, lrf=lrf if self.share_local_rfs else None, need_lrf=self.share_local_rfs
             )
             if lrf is None or not self.share_local_rfs:
                 lrf = new_lrf

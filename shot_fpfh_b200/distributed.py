@@ -134,9 +134,7 @@ def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, m
 
     def block(lo, hi):
         q = kp[lo:hi].contiguous()
-        offsets, nbr, _, _ = ops.radius_csr(grid, q, radius)
-        lrf = ops.shot_lrf(grid, q, radius, offsets, nbr)
-        return ops.shot_descriptor(grid, q, radius, offsets, nbr, lrf, min_neighborhood_size, normalize, out_dtype=out_dtype)
+        return ops.shot_single_scale(grid, q, radius, min_neighborhood_size, normalize, out_dtype=out_dtype)[0]
 
     out = sharded_rows(int(kp.shape[0]), block, gather, group)
     torch.cuda.synchronize()

@@ -134,6 +134,47 @@ def shot_descriptor(
     return out
 
 
+def shot_single_scale(
+    grid: Grid,
+    queries: torch.Tensor,
+    radius: float,
+    min_neighborhood_size: int,
+    normalize: bool,
+    out_dtype: torch.dtype = torch.float64,
+    out: torch.Tensor | None = None,
+    want_lrf: bool = False,
+    want_pairs: bool = False,
+):
+    """
+    The fused single-scale driver (sf_shot_single_scale): search + frames + descriptors on the same neighbourhoods.
+    Returns (descriptors, lrf | None, number of neighbour pairs | None).
+    """
+    nq = int(queries.shape[0])
+    if out is None:
+        out = torch.empty((nq, SHOT_LEN), dtype=out_dtype, device=queries.device)
+    assert out.shape == (nq, SHOT_LEN) and out.dtype in (torch.float32, torch.float64)
+    lrf = torch.empty((nq, 3, 3), dtype=torch.float64, device=queries.device) if want_lrf else None
+    pairs = ctypes.c_int64(0)
+    check(
+        lib.sf_shot_single_scale(
+            grid.handle, ptr(queries), nq, float(radius), int(min_neighborhood_size), int(bool(normalize)), ptr(out),
+            int(out.dtype == torch.float64), ptr(lrf), ctypes.byref(pairs) if want_pairs else None, stream_ptr(),
+        )
+    )
+    return out, lrf, (int(pairs.value) if want_pairs else None)
+
+
+def profile_enable(enable: bool) -> None:
+    check(lib.sf_profile_enable(int(bool(enable))))
+
+
+def profile_read() -> tuple[float, float, float]:
+    """(search + moments, eigen, votes + descriptor) milliseconds of the last fused single-scale call."""
+    ms = (ctypes.c_float * 3)()
+    check(lib.sf_profile_read(ms))
+    return float(ms[0]), float(ms[1]), float(ms[2])
+
+
 def fpfh_edges(n_bins: int) -> np.ndarray:
     """(3, n_bins + 1) float64 histogram edges, built on the host exactly as NumPy builds them."""
     return np.ascontiguousarray(np.stack([np.linspace(lo, hi, n_bins + 1) for lo, hi in FPFH_RANGES]))
