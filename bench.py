@@ -254,7 +254,7 @@ def bench_shot(args, dist, rank, world, pk):
 
     from shot_fpfh_b200 import ops
     from shot_fpfh_b200.descriptors import ShotMultiprocessor
-    from shot_fpfh_b200.device import Grid, upload
+    from shot_fpfh_b200.device import Grid, host_threads, upload
 
     pts, normals, kp, radius = make_shot_workload(rank)
     n, q = pts.shape[0], kp.shape[0]
@@ -323,6 +323,7 @@ def bench_shot(args, dist, rank, world, pk):
 
     h_pts, h_nrm, h_kp = pinned(pts), pinned(normals), pinned(kp)
     e2e_times = []
+    n_threads = host_threads(ShotMultiprocessor.n_procs)  # the reference's default worker count (8)
     with ShotMultiprocessor(min_neighborhood_size=MIN_NB, verbose=False) as shot:
         for i in range(args.warmup + args.steps):
             flush()
@@ -343,7 +344,9 @@ def bench_shot(args, dist, rank, world, pk):
         e2e_ms = float(t.item())
     e2e = {
         "value": world * q / (e2e_ms * 1e-3), "unit": "descriptors/s", "ms_per_step": e2e_ms,
-        "h2d_bytes_per_step": int(h_pts.nbytes + h_nrm.nbytes + h_kp.nbytes), "d2h_bytes_per_step": int(d.nbytes),
+        "h2d_bytes_per_step": int(h_pts.nbytes + h_nrm.nbytes + h_kp.nbytes), "d2h_bytes_per_step": int(shot.last_d2h_bytes),
+        "host_threads": n_threads,
+        "transport": "in blocks of queries: the rows (~86% zeros) are compacted on the device (offsets + uint16 column + float32 value per non-zero), copied, and expanded into the float64 result by the host threads while the next block is computed",
         "api": "ShotMultiprocessor.compute_descriptor_single_scale(point_cloud, normals, keypoints, radius) -> float64 (Q,352)",
     }
     config = {

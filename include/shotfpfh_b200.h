@@ -182,6 +182,27 @@ int sf_match_rerank(const double* a_desc_dev, const int64_t* rows_a_dev, int64_t
                     const int64_t* rows_b_dev, int32_t width, const int32_t* cand_idx_dev, int32_t k,
                     int32_t* nn_dev, double* d1_dev, double* d2_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Result transport. The reference returns dense float64 rows on the host (shot_parallelization.py:183); a SHOT row
+ * is ~86 % zeros and the kernels' values are float32, so the rows cross PCIe compacted and the dense float64
+ * array is rebuilt by host threads (float64(float32 x) is exact: the array equals a dense float64 copy).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Device: non-zero entries of dense float32 rows (n_rows, width <= 65536), row by row, ascending columns.
+ * _count writes offsets_dev[0..n_rows] (exclusive prefix of the per-row counts) and the total to *total_host
+ * (synchronises `stream`); _fill writes cols_dev / vals_dev [0, total). */
+int sf_rows_compact_count(const float* dense_dev, int64_t n_rows, int32_t width, int64_t* offsets_dev,
+                          int64_t* total_host, void* stream);
+int sf_rows_compact_fill(const float* dense_dev, int64_t n_rows, int32_t width, const int64_t* offsets_dev,
+                         uint16_t* cols_dev, float* vals_dev, void* stream);
+/* Host (all pointers are HOST memory; a persistent pool of up to `threads` threads). sf_host_expand_rows_begin
+ * starts writing the dense rows dst[r * width + c] (zeros, and vals[i] at c = cols[i] for the entries
+ * i in [offsets[r], offsets[r+1]) of row r; width <= 4096) and returns at once, so that one block of rows is
+ * rebuilt while the next is computed and copied; a second call first waits for the previous one. sf_host_wait blocks until
+ * everything started has finished and reports a malformed input. The buffers must stay valid until then. */
+int sf_host_expand_rows_begin(const int64_t* offsets_host, const uint16_t* cols_host, const float* vals_host,
+                              int64_t n_rows, int32_t width, double* dst_host, int32_t threads);
+int sf_host_wait(void);
+
 #ifdef __cplusplus
 }
 #endif

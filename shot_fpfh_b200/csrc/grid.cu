@@ -65,12 +65,23 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xy
       hi[a] = fmax(hi[a], __shfl_xor_sync(kFull, hi[a], o));
     }
   }
-  if ((threadIdx.x & 31) == 0) {
+  // warp leaders -> shared memory -> six atomics per BLOCK (one per warp serialised ~57k atomics on six words)
+  __shared__ double part[8][6];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      atomicMin(box + a, ordered_bits(lo[a]));
-      atomicMax(box + 3 + a, ordered_bits(hi[a]));
+      part[warp][a] = lo[a];
+      part[warp][3 + a] = hi[a];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = part[0][threadIdx.x];
+    for (int w = 1; w < int(blockDim.x >> 5); ++w)
+      v = threadIdx.x < 3 ? fmin(v, part[w][threadIdx.x]) : fmax(v, part[w][threadIdx.x]);
+    if (threadIdx.x < 3) atomicMin(box + threadIdx.x, ordered_bits(v));
+    else atomicMax(box + threadIdx.x, ordered_bits(v));
   }
 }
 
@@ -230,7 +241,7 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   // 1. bounding box (device) -> host, the only synchronisation of the build
   unsigned long long* box = reinterpret_cast<unsigned long long*>(g->bbox);
   bbox_init_kernel<<<1, 32, 0, stream>>>(box);
-  const int bbox_blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  const int bbox_blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 4));
   bbox_kernel<<<bbox_blocks, 256, 0, stream>>>(xyz, n, box);
   unsigned long long hbox[6];
   SF_CUDA(cudaMemcpyAsync(hbox, box, sizeof(hbox), cudaMemcpyDeviceToHost, stream));

@@ -208,59 +208,22 @@ SF_HD float shot_bin_value_compact(const uint32_t* keys, const float* vals, int 
   return v;
 }
 
-// Slot layout of the winner tables (per query, 64-bit words (key << 32) | float bits):
-//   [0, 352)          own-bin group (statements 2, 5, 8, 10)
-//   [352, 704)        statement 1
-//   [704, 1056)       statement 9
-//   [1056, 1232)      statement 3  (target radial 1)      index = flat >> 1
-//   [1232, 1408)      statement 4  (target radial 0)
-//   [1408, 1584)      statement 6  (target elevation 1)   index = ((flat >> 2) << 1) | (flat & 1)
-//   [1584, 1760)      statement 7  (target elevation 0)
-constexpr int kSlotOwn = 0, kSlotCos = 352, kSlotAz = 704, kSlotRad1 = 1056, kSlotRad0 = 1232, kSlotEl1 = 1408,
-              kSlotEl0 = 1584, kSlotCount = 1760;
-
-SF_HD int drop_rad(int flat) { return flat >> 1; }
-SF_HD int drop_el(int flat) { return ((flat >> 2) << 1) | (flat & 1); }
-
-// The seven slot writes of one neighbour: slot index and value. Every neighbour performs all ten statements
-// of the reference, even with value 0 (that is how a later neighbour erases an earlier contribution).
-SF_HD void shot_slots(const ShotRecord& r, int slot[7], float val[7]) {
-  const int ri = r.own & 1, ei = (r.own >> 1) & 1;
-  slot[0] = kSlotOwn + r.own;                    val[0] = r.v_own;
-  slot[1] = kSlotCos + r.cos_nb;                 val[1] = r.v_cos;
-  slot[2] = kSlotAz + r.az_nb;                   val[2] = r.v_az;
-  // statement 3 targets radial 1: carries `outer` when the neighbour is in shell 0, else writes 0 to its own bin
-  slot[3] = kSlotRad1 + drop_rad(r.own);         val[3] = ri == 0 ? r.v_rad : 0.0f;
-  slot[4] = kSlotRad0 + drop_rad(r.own);         val[4] = ri == 1 ? r.v_rad : 0.0f;
-  slot[5] = kSlotEl1 + drop_el(r.own);           val[5] = ei == 0 ? r.v_el : 0.0f;
-  slot[6] = kSlotEl0 + drop_el(r.own);           val[6] = ei == 1 ? r.v_el : 0.0f;
-}
-
-SF_HD unsigned long long pack_slot(uint32_t key, float v) {
+// The same assembly for the four bins {4g .. 4g+3} of one (cosine, azimuth) cell at once: their radial / elevation
+// partners are inside the group, so a lane needs exactly eight 16-byte table reads (what the kernel does).
+SF_HD void shot_bin_group_compact(const uint32_t ko[4], const uint32_t kc[4], const uint32_t ka[4], const float vo[4],
+                                  const float vr[4], const float ve[4], const float vc[4], const float va[4],
+                                  float out[4]) {
 #if defined(__CUDA_ARCH__)
-  return (static_cast<unsigned long long>(key) << 32) | __float_as_uint(v);
-#else
-  union { float f; uint32_t u; } c; c.f = v;
-  return (static_cast<unsigned long long>(key) << 32) | c.u;
+#pragma unroll
 #endif
-}
-SF_HD float slot_value(unsigned long long w) {
-#if defined(__CUDA_ARCH__)
-  return __uint_as_float(static_cast<uint32_t>(w));
-#else
-  union { float f; uint32_t u; } c; c.u = static_cast<uint32_t>(w);
-  return c.f;
-#endif
-}
-
-// Value of descriptor bin `flat` from the winner tables.
-SF_HD float shot_bin_value(const unsigned long long* slots, int flat) {
-  const int ri = flat & 1, ei = (flat >> 1) & 1;
-  float v = slot_value(slots[kSlotOwn + flat]) + slot_value(slots[kSlotCos + flat]) +
-            slot_value(slots[kSlotAz + flat]);
-  v += slot_value(slots[(ri ? kSlotRad1 : kSlotRad0) + drop_rad(flat)]);
-  v += slot_value(slots[(ei ? kSlotEl1 : kSlotEl0) + drop_el(flat)]);
-  return v;
+  for (int t = 0; t < 4; ++t) {
+    float v = ko[t] ? vo[t] : 0.0f;
+    if (kc[t]) v += vc[t];
+    if (ka[t]) v += va[t];
+    if (ko[t ^ 1] > ko[t]) v += vr[t ^ 1];
+    if (ko[t ^ 2] > ko[t]) v += ve[t ^ 2];
+    out[t] = v;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------

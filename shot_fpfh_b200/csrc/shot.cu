@@ -188,6 +188,15 @@ __global__ void __launch_bounds__(256)
 constexpr int kShotWarpsPerBlock = 4;
 constexpr int kShotSmemPerWarp = (kKeyCount + kValCount) * 4;
 
+// 352 * sizeof(OutT) is a multiple of 16, so every row and every group of four bins is 16-byte aligned
+__device__ __forceinline__ void store_group(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store_group(double* p, float a, float b, float c, float d) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+  reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     shot_descriptor_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
@@ -207,8 +216,8 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
   const int64_t warps_total = int64_t(gridDim.x) * kShotWarpsPerBlock;
   const double inv_radius = 1.0 / radius;
   for (int64_t q = blockIdx.x * int64_t(kShotWarpsPerBlock) + warp; q < nq; q += warps_total) {
-#pragma unroll
-    for (int j = 0; j < kKeyCount / 32; ++j) keys[lane + 32 * j] = 0u;  // values are gated by their keys: no clearing
+    // values are gated by their keys: only the keys are cleared (16 bytes per lane and store)
+    for (int j = lane; j < kKeyCount / 4; j += 32) reinterpret_cast<uint4*>(keys)[j] = make_uint4(0u, 0u, 0u, 0u);
     const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
     const int64_t begin = offsets[q], end = counts ? begin + counts[q] : offsets[q + 1];
     double f[9];
@@ -300,12 +309,33 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
       __syncwarp();  // the stores above are ordered before the next round's key updates
     }
     positive = warp_sum(positive);
-    float v[kShotLen / 32];
+    // assembly: lane handles the groups {lane, lane + 32, lane + 64} of four consecutive bins (one (cosine, azimuth)
+    // cell: the radial / elevation partners are inside the group) -> eight 16-byte table reads and one 16-byte
+    // store per group
+    constexpr int kGroups = kShotLen / 4, kGroupRounds = (kGroups + 31) / 32;
+    float v[kGroupRounds][4];
     double sq = 0.0;
 #pragma unroll
-    for (int j = 0; j < kShotLen / 32; ++j) {
-      v[j] = shot_bin_value_compact(keys, vals, lane + 32 * j);
-      sq += double(v[j]) * double(v[j]);
+    for (int j = 0; j < kGroupRounds; ++j) {
+      const int grp = lane + 32 * j;
+      if (grp < kGroups) {
+        const uint4 ko = *reinterpret_cast<const uint4*>(keys + kKeyOwn + 4 * grp);
+        const uint4 kc = *reinterpret_cast<const uint4*>(keys + kKeyCos + 4 * grp);
+        const uint4 ka = *reinterpret_cast<const uint4*>(keys + kKeyAz + 4 * grp);
+        const float4 vo = *reinterpret_cast<const float4*>(vals + kValOwn + 4 * grp);
+        const float4 vr = *reinterpret_cast<const float4*>(vals + kValRad + 4 * grp);
+        const float4 ve = *reinterpret_cast<const float4*>(vals + kValEl + 4 * grp);
+        const float4 vc = *reinterpret_cast<const float4*>(vals + kValCos + 4 * grp);
+        const float4 va = *reinterpret_cast<const float4*>(vals + kValAz + 4 * grp);
+        const uint32_t ko_[4] = {ko.x, ko.y, ko.z, ko.w}, kc_[4] = {kc.x, kc.y, kc.z, kc.w},
+                       ka_[4] = {ka.x, ka.y, ka.z, ka.w};
+        const float vo_[4] = {vo.x, vo.y, vo.z, vo.w}, vr_[4] = {vr.x, vr.y, vr.z, vr.w},
+                    ve_[4] = {ve.x, ve.y, ve.z, ve.w}, vc_[4] = {vc.x, vc.y, vc.z, vc.w},
+                    va_[4] = {va.x, va.y, va.z, va.w};
+        shot_bin_group_compact(ko_, kc_, ka_, vo_, vr_, ve_, vc_, va_, v[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sq += double(v[j][t]) * double(v[j][t]);
+      }
     }
     sq = warp_sum(sq);
     const double norm = sqrt(sq);
@@ -314,7 +344,10 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     const float inv = keep ? (normalize ? float(1.0 / norm) : 1.0f) : 0.0f;
     OutT* row = out + q * kShotLen;
 #pragma unroll
-    for (int j = 0; j < kShotLen / 32; ++j) row[lane + 32 * j] = OutT(v[j] * inv);
+    for (int j = 0; j < kGroupRounds; ++j) {
+      const int grp = lane + 32 * j;
+      if (grp < kGroups) store_group(row + 4 * grp, v[j][0] * inv, v[j][1] * inv, v[j][2] * inv, v[j][3] * inv);
+    }
     __syncwarp();  // all lanes have read the tables before the next query clears the keys
   }
 }
@@ -361,6 +394,7 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
                              const int32_t* counts, const int32_t* nbr, double* lrf, int fuse_votes, int min_nb,
                              int normalize, void* out, int out_is_f64, cudaStream_t stream) {
   const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
+  SF_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, SF_ERR_ARG, "SHOT output rows must be 16-byte aligned");
   static bool configured = false;
   if (!configured) {
     SF_CUDA(cudaFuncSetAttribute(shot_descriptor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

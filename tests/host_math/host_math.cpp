@@ -110,9 +110,15 @@ void hm_shot_descriptor(const double* point, const double* nbrs, const double* n
   }
   double sq = 0.0;
   float v[kShotLen];
-  for (int b = 0; b < kShotLen; ++b) {
-    v[b] = shot_bin_value_compact(keys.data(), vals.data(), b);
-    sq += double(v[b]) * double(v[b]);
+  for (int g = 0; g < kShotLen / 4; ++g) {  // four bins of one (cosine, azimuth) cell at a time, as the kernel does
+    const uint32_t* k = keys.data() + 4 * g;
+    const float* x = vals.data() + 4 * g;
+    shot_bin_group_compact(k + kKeyOwn, k + kKeyCos, k + kKeyAz, x + kValOwn, x + kValRad, x + kValEl, x + kValCos,
+                           x + kValAz, v + 4 * g);
+    for (int t = 0; t < 4; ++t) {
+      if (v[4 * g + t] != shot_bin_value_compact(keys.data(), vals.data(), 4 * g + t)) v[4 * g + t] = NAN;  // must agree
+      sq += double(v[4 * g + t]) * double(v[4 * g + t]);
+    }
   }
   const double norm = sqrt(sq);
   const bool keep = positive > min_nb && norm > 0.0;

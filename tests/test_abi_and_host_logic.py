@@ -181,3 +181,35 @@ def test_synthetic_generator_is_seeded_and_matches_the_survey_shape():
     assert kp.shape[0] < 5000 and np.all(np.diff(kp) > 0)
     rows = synthetic.sparse_unit_rows(100)
     assert np.allclose(np.linalg.norm(rows, axis=1), 1.0, atol=1e-6) and (rows == 0).mean() > 0.8
+
+
+def test_host_row_expansion_rebuilds_dense_float64_rows():
+    """csrc/host_io.cpp (no GPU involved): compact rows -> dense float64, every thread count, odd shapes, bad input."""
+    from shot_fpfh_b200._lib import SF_ERR_ARG, check, lib
+
+    rng = np.random.default_rng(3)
+    for n_rows, width in ((0, 352), (1, 352), (3, 352), (777, 352), (5000, 33), (300, 125), (64, 4096)):
+        dense = (rng.random((n_rows, width)) * (rng.random((n_rows, width)) < 0.14)).astype(np.float32)
+        if n_rows > 2:
+            dense[1] = 0.0  # an empty row
+            dense[2] = -1.5  # a full row, negative values
+        r, c = np.nonzero(dense)
+        offsets = np.zeros(n_rows + 1, np.int64)
+        np.cumsum(np.bincount(r, minlength=n_rows), out=offsets[1:])
+        cols, vals = c.astype(np.uint16), dense[r, c]
+        for threads in (1, 3, 8):
+            out = np.full((n_rows, width), 7.0)
+            check(lib.sf_host_expand_rows_begin(offsets.ctypes.data, cols.ctypes.data, vals.ctypes.data, n_rows, width,
+                                                out.ctypes.data, threads))
+            check(lib.sf_host_wait())
+            assert np.array_equal(out, dense.astype(np.float64)), (n_rows, width, threads)
+    bad = cols.copy()
+    bad[0] = 5000  # column outside the row
+    out = np.zeros((n_rows, width))
+    check(lib.sf_host_expand_rows_begin(offsets.ctypes.data, bad.ctypes.data, vals.ctypes.data, n_rows, width,
+                                        out.ctypes.data, 2))
+    assert lib.sf_host_wait() == SF_ERR_ARG
+    assert lib.sf_host_expand_rows_begin(None, None, None, 4, 352, None, 2) == SF_ERR_ARG
+    assert lib.sf_host_expand_rows_begin(offsets.ctypes.data, cols.ctypes.data, vals.ctypes.data, 1, 5000,
+                                         out.ctypes.data, 2) == SF_ERR_ARG
+    assert lib.sf_host_wait() == 0

@@ -225,3 +225,28 @@ def test_large_size_properties_1m():
     rows = np.random.default_rng(4).choice(kp.shape[0], 300, replace=False)
     want = shot_oracle.shot_single_scale(pts, normals, kp[rows], radius, True, 10)
     _check_rows(d[rows], want, "1M spot check")
+
+
+def test_result_transport_equals_a_dense_copy():
+    """device.SparseRowsDownload (csrc/transport.cu + csrc/host_io.cpp): compact -> copy -> expand == rows.double()."""
+    import torch
+
+    from shot_fpfh_b200.device import SparseRowsDownload, download_sparse_rows
+
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for n_rows, width in ((1, 352), (1000, 352), (40000, 352), (5000, 33), (257, 125)):
+        rows = torch.rand((n_rows, width), device="cuda", generator=gen)
+        rows = (rows * (torch.rand((n_rows, width), device="cuda", generator=gen) < 0.14)).float().contiguous()
+        if n_rows > 2:
+            rows[1] = 0.0
+            rows[2] = -2.5
+        expect = rows.double().cpu().numpy()
+        assert np.array_equal(download_sparse_rows(rows, 4), expect)
+        if n_rows >= 1000:  # in blocks, as compute_descriptor_single_scale pushes them
+            job = SparseRowsDownload(n_rows, width, 3)
+            for lo in range(0, n_rows, 300):
+                job.push(rows[lo : lo + 300])
+            assert np.array_equal(job.finish(), expect)
+    assert download_sparse_rows(torch.zeros((0, 352), device="cuda"), 2).shape == (0, 352)
+    all_zero = download_sparse_rows(torch.zeros((50, 352), device="cuda"), 2)
+    assert all_zero.shape == (50, 352) and not all_zero.any()
