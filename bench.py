@@ -376,21 +376,27 @@ def bench_fpfh(args, pk):
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     info = {}
 
+    out = torch.empty((N_POINTS, 33), dtype=torch.float32, device="cuda")
+    kernel_ms = []
+    ops.profile_enable(True)
+
     def step(stage):
         with mark(stage, "grid_build"):
             grid.build(p_dev, n_dev, radius)
-        with mark(stage, "radius_search"):
-            offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
-        with mark(stage, "spfh"):
-            rows = ops.spfh(grid, offsets, nbr, 11, True)
-        with mark(stage, "fpfh"):
-            ops.fpfh(grid, offsets, nbr, dist, rows, kp, out_dtype=torch.float32)
-        info["pairs"] = int(nbr.shape[0])
+        # the fused driver: what compute_fpfh_descriptor runs (search + weights, SPFH, FPFH; padded neighbour list)
+        _, pairs = ops.fpfh_cloud(grid, radius, 11, True, kp, out=out, want_pairs="pairs" not in info)
+        if pairs is not None:
+            info["pairs"] = pairs
 
     steps = max(3, args.steps // 2)
-    ms, stages = timed_steps(step, steps, args.warmup, lambda: flush_buf.fill_(1))
+    ms, stages = timed_steps(step, steps, args.warmup, lambda: flush_buf.fill_(1),
+                             after_step=lambda: kernel_ms.append(ops.profile_read()))
+    ops.profile_enable(False)
+    k_ms = np.mean(np.array(kernel_ms), axis=0)
+    stages.update({"radius_search": float(k_ms[0]), "spfh": float(k_ms[1]), "fpfh": float(k_ms[2])})
     p, n, d = info["pairs"], N_POINTS, 33
-    alg = {"grid_build": 52 * n, "radius_search": 12 * n + 12 * n + 12 * p + 4 * (n + 1), "spfh": 28 * p + 24 * n + 4 * d * n,
+    # SURVEY.md §8d; the search writes index + float32 weight per pair (8P) and the padded offsets / counts
+    alg = {"grid_build": 52 * n, "radius_search": 12 * n + 12 * n + 8 * p + 12 * (n + 1), "spfh": 28 * p + 24 * n + 4 * d * n,
            "fpfh": (4 * d + 8) * p + 4 * d * n + 4 * n}
     dominant = max(stages, key=stages.get)
     grid.close()

@@ -79,10 +79,12 @@ int sf_radius_fill(sf_grid* grid, const double* queries_dev, int64_t self_first,
  * drivers call it on the support cloud (shot_parallelization.py:157-161, :210-214, :273-277).
  * picked_dev: int32[n] capacity; the first *count_host entries receive, in lexicographic voxel order, the index of
  * the point closest to each occupied voxel's barycentre (first on ties, members in ascending index order).
+ * members_dev (optional, same capacity): the number of points of each of those voxels — what
+ * `select_keypoints_with_density_threshold` thresholds (keypoint_selection.py:75-80, :109-111).
  * Synchronises `stream` (the count is a host result).
  * ---------------------------------------------------------------------------------------------------------- */
-int sf_voxel_subsample(const double* xyz_dev, int64_t n, double voxel_size, int32_t* picked_dev, int64_t* count_host,
-                       void* stream);
+int sf_voxel_subsample(const double* xyz_dev, int64_t n, double voxel_size, int32_t* picked_dev, int32_t* members_dev,
+                       int64_t* count_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * N — PCA normals ("next" row: upstream of the hot path).  Replaces `compute_normals`
@@ -129,9 +131,10 @@ int sf_shot_single_scale(sf_grid* grid, const double* queries_dev, int64_t nq, d
                          int32_t min_neighborhood_size, int32_t normalize, void* out_dev, int32_t out_is_f64,
                          double* lrf_out_dev, int64_t* pairs_host, void* stream);
 
-/* Measurement hook: with profiling enabled, sf_shot_single_scale records CUDA events on its stream around its three
- * kernels; sf_profile_read waits for the last call and returns their durations in milliseconds:
- * ms_out[0] = search + moments, ms_out[1] = eigen-decomposition, ms_out[2] = sign votes + descriptor. */
+/* Measurement hook: with profiling enabled, the fused drivers (sf_shot_single_scale, sf_fpfh_cloud) record CUDA
+ * events on their stream around their three stages; sf_profile_read waits for the last call and returns the
+ * durations in milliseconds: search + moments, eigen-decomposition, sign votes + descriptor for SHOT;
+ * search + weights, SPFH, FPFH for FPFH. */
 int sf_profile_enable(int32_t enable);
 int sf_profile_read(float* ms_out3);
 
@@ -151,6 +154,15 @@ int sf_spfh(sf_grid* grid, int64_t first, int64_t count, const int64_t* offsets_
 int sf_fpfh(sf_grid* grid, const int64_t* offsets_dev, const int32_t* nbr_sorted_dev, const double* dist_dev,
             int32_t csr_by_keypoint, const float* spfh_dev, int32_t width, const int64_t* keypoint_index_dev,
             int64_t nq, void* out_dev, int32_t out_is_f64, void* stream);
+
+/* The fused driver of one cloud, what `compute_fpfh_descriptor` does between its KDTree and its return
+ * (fpfh.py:26-117): search around EVERY cloud point, SPFH of every point, FPFH of the keypoints (original point
+ * indices). The neighbour list is an internal, padded temporary written by ONE pass over the candidate cells,
+ * together with the float32 weights 1/d of fpfh.py:112-114. edges_host as for sf_spfh. pairs_host (optional):
+ * number of neighbour pairs found (the "mean neighbourhood size" the reference logs). Synchronises `stream` once. */
+int sf_fpfh_cloud(sf_grid* grid, double radius, int32_t n_bins, int32_t decorrelated, const double* edges_host,
+                  const int64_t* keypoint_index_dev, int64_t nq, void* out_dev, int32_t out_is_f64, int64_t* pairs_host,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * M — descriptor matching.  Replaces `cdist(...).argmin(axis=1)` in `basic_matching` (matching.py:162-169),

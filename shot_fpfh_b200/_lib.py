@@ -45,7 +45,7 @@ def _load() -> ctypes.CDLL:
         "sf_radius_fill": [
             c_void_p, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
         ],
-        "sf_voxel_subsample": [c_void_p, c_int64, c_double, c_void_p, p_i64, c_void_p],
+        "sf_voxel_subsample": [c_void_p, c_int64, c_double, c_void_p, c_void_p, p_i64, c_void_p],
         "sf_knn": [c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p, c_void_p, c_void_p],
         "sf_pca_normals": [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p],  # xyz first
         "sf_shot_lrf": [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -63,6 +63,7 @@ def _load() -> ctypes.CDLL:
             c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32,
             c_void_p,
         ],
+        "sf_fpfh_cloud": [c_void_p, c_double, c_int32, c_int32, p_f64, c_void_p, c_int64, c_void_p, c_int32, p_i64, c_void_p],
         "sf_nonempty_rows": [c_void_p, c_int64, c_int32, c_void_p, p_i64, c_void_p],
         "sf_match_pack": [c_void_p, c_int32, c_void_p, c_int64, c_double, c_void_p, c_int32, c_void_p, c_void_p],
         "sf_match_topk": [
@@ -89,7 +90,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTS = (
     "sf_last_error sf_abi_version sf_grid_create sf_grid_destroy sf_grid_build sf_grid_info sf_grid_permutation "
-    "sf_radius_count sf_radius_fill sf_voxel_subsample sf_knn sf_pca_normals sf_shot_lrf sf_shot_descriptor sf_shot_single_scale sf_profile_enable sf_profile_read sf_spfh sf_fpfh sf_nonempty_rows sf_match_pack "
+    "sf_radius_count sf_radius_fill sf_voxel_subsample sf_knn sf_pca_normals sf_shot_lrf sf_shot_descriptor sf_shot_single_scale sf_profile_enable sf_profile_read sf_spfh sf_fpfh sf_fpfh_cloud sf_nonempty_rows sf_match_pack "
     "sf_match_topk sf_topk_merge sf_match_rerank sf_rows_compact_count sf_rows_compact_fill "
     "sf_host_expand_rows_begin sf_host_wait"
 ).split()

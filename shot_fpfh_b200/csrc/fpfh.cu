@@ -4,6 +4,8 @@
 //      counts in shared memory (order-independent, hence exact), divided by the neighbourhood size INCLUDING the
 //      point itself. Rows are written in cell-sorted order so that stage 2 gathers them with good locality.
 //   P2 fpfh_kernel <- fpfh.py:97-116: spfh[i] + (sum_{j, d_j > 0} spfh[j] / d_j) / K_i on the keypoints.
+#include <cub/cub.cuh>
+
 #include "sf_common.cuh"
 
 namespace sf {
@@ -13,7 +15,9 @@ __constant__ double c_edges[3][kMaxBins + 1];
 
 __global__ void __launch_bounds__(256)
     spfh_kernel(GridView g, int64_t first, int64_t count, const int64_t* __restrict__ offsets,
-                const int32_t* __restrict__ nbr, int n_bins, int decorrelated, int width, float* __restrict__ spfh) {
+                const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr, int n_bins, int decorrelated,
+                int width, float* __restrict__ spfh) {
+  // counts == nullptr: CSR rows [offsets[s], offsets[s+1]); otherwise padded rows [offsets[s], offsets[s] + counts[s])
   extern __shared__ int hist_mem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -26,7 +30,7 @@ __global__ void __launch_bounds__(256)
     const double4 p = load_pt(g.pts + first + s);
     const double4 un = load_pt(g.nrm + first + s);
     const double u[3] = {un.x, un.y, un.z};
-    const int64_t begin = offsets[s], end = offsets[s + 1];
+    const int64_t begin = offsets[s], end = counts ? begin + counts[s] : offsets[s + 1];
     for (int64_t i = begin + lane; i < end; i += 32) {
       const int j = __ldg(nbr + i);
       const double4 pj = load_pt(g.pts + j);
@@ -57,6 +61,67 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Fused driver, stage 0: ONE scan of the candidate cells of every cloud point (cell-sorted order) writes the
+// neighbours into a PADDED list (slots sized by the candidate count, a cell_start lookup — no counting pass over
+// the candidates), the float32 weights 1/d that stage 2 needs (fpfh.py:112-114; 0 where d == 0) and the counts.
+__global__ void __launch_bounds__(256)
+    search_weights_kernel(GridView g, int64_t n, double r2, const int64_t* __restrict__ cand_offsets,
+                          int32_t* __restrict__ nbr, float* __restrict__ weights, int32_t* __restrict__ counts,
+                          unsigned long long* __restrict__ pair_counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (s >= n) return;
+  const double4 me = load_pt(g.pts + s);
+  const Runs runs = build_runs(g, me.x, me.y, me.z, lane);
+  const int total = runs.pref[9];
+  int64_t out = cand_offsets[s];
+  int count = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int v = base + lane;
+    bool hit = false;
+    int pos = 0;
+    double d2 = 0.0;
+    if (v < total) {
+      pos = run_position(runs, v);
+      const double4 p = load_pt(g.pts + pos);
+      d2 = rdist3(me.x - p.x, me.y - p.y, me.z - p.z);
+      hit = d2 <= r2;
+    }
+    const unsigned mask = __ballot_sync(kFull, hit);
+    if (hit) {
+      const int64_t o = out + __popc(mask & lanemask_lt());
+      nbr[o] = pos;
+      weights[o] = d2 > 0.0 ? float(1.0 / sqrt(d2)) : 0.0f;
+    }
+    out += __popc(mask);
+    count += __popc(mask);
+  }
+  if (lane == 0) {
+    counts[s] = count;
+    atomicAdd(pair_counter, static_cast<unsigned long long>(count));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    self_candidate_count_kernel(GridView g, int64_t n, int64_t* __restrict__ cand) {
+  const int64_t s = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (s >= n) return;
+  const double4 me = load_pt(g.pts + s);
+  const int cx = cell_coord(me.x, g.origin[0], g.inv_cell, g.dims[0]);
+  const int cy = cell_coord(me.y, g.origin[1], g.inv_cell, g.dims[1]);
+  const int cz = cell_coord(me.z, g.origin[2], g.inv_cell, g.dims[2]);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+  int total = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = cy + dy, zz = cz + dz;
+      if (yy < 0 || yy >= g.dims[1] || zz < 0 || zz >= g.dims[2]) continue;
+      const int64_t base = (int64_t(zz) * g.dims[1] + yy) * g.dims[0];
+      total += __ldg(g.cell_start + base + x1 + 1) - __ldg(g.cell_start + base + x0);
+    }
+  cand[s] = total;
+}
+
 // One warp per keypoint. The neighbour list is consumed in chunks of 32: each lane loads one (index, 1/d) pair,
 // then the pairs are broadcast by shuffle and every lane accumulates its own bins — the row loads of consecutive
 // neighbours are independent, so several are in flight at once. Column blocks of 32 bins are register tiles;
@@ -64,7 +129,8 @@ __global__ void __launch_bounds__(256)
 template <int kBlocks, typename OutT>
 __global__ void __launch_bounds__(256)
     fpfh_kernel(const int32_t* __restrict__ inv_perm, const int64_t* __restrict__ offsets,
-                const int32_t* __restrict__ nbr, const double* __restrict__ dist, int csr_by_keypoint,
+                const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr, const double* __restrict__ dist,
+                const float* __restrict__ weights, int csr_by_keypoint,
                 const float* __restrict__ spfh, int width, int bin_base, int rem,
                 const int64_t* __restrict__ keypoints, int64_t nq, OutT* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -72,7 +138,8 @@ __global__ void __launch_bounds__(256)
   if (q >= nq) return;
   const int64_t s = inv_perm[keypoints[q]];
   const int64_t row_id = csr_by_keypoint ? q : s;  // CSR rows follow the keypoints, or every cell-sorted point
-  const int64_t begin = offsets[row_id], end = offsets[row_id + 1];
+  // counts: padded rows (fused driver); weights: float32 1/d precomputed by the search (0 where d == 0)
+  const int64_t begin = offsets[row_id], end = counts ? begin + counts[row_id] : offsets[row_id + 1];
   float acc[kBlocks];
 #pragma unroll
   for (int r = 0; r < kBlocks; ++r) acc[r] = 0.0f;
@@ -84,9 +151,13 @@ __global__ void __launch_bounds__(256)
     int my_j = 0;
     float my_w = 0.0f;
     if (i < end) {
-      const double d = __ldg(dist + i);
       my_j = __ldg(nbr + i);
-      my_w = d > 0.0 ? float(1.0 / d) : 0.0f;  // fpfh.py:112-114: the tree's own distances decide
+      if (weights != nullptr) {
+        my_w = __ldg(weights + i);
+      } else {
+        const double d = __ldg(dist + i);
+        my_w = d > 0.0 ? float(1.0 / d) : 0.0f;  // fpfh.py:112-114: the tree's own distances decide
+      }
     }
     const int cnt = int(end - base < 32 ? end - base : 32);
     if (rem > 0 && my_w != 0.0f) {
@@ -121,9 +192,9 @@ __global__ void __launch_bounds__(256)
 
 using namespace sf;
 
-extern "C" int sf_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* offsets, const int32_t* nbr,
-                       int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* offsets, const int32_t* counts,
+                       const int32_t* nbr, int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh,
+                       cudaStream_t stream) {
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_spfh: grid built without normals");
   SF_REQUIRE(offsets && nbr && edges_host && spfh, SF_ERR_ARG, "sf_spfh: null argument");
   SF_REQUIRE(first >= 0 && count >= 0 && first + count <= g->n, SF_ERR_ARG, "sf_spfh: point range outside the cloud");
@@ -144,15 +215,22 @@ extern "C" int sf_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
     SF_CUDA(cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t blocks_needed = (count + warps - 1) / warps;
   const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
-  spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, nbr, n_bins, decorrelated, width,
-                                                    spfh);
+  spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, counts, nbr, n_bins, decorrelated,
+                                                    width, spfh);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
 
+extern "C" int sf_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* offsets, const int32_t* nbr,
+                       int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh, void* stream_) {
+  return launch_spfh(g, first, count, offsets, nullptr, nbr, n_bins, decorrelated, edges_host, spfh,
+                     static_cast<cudaStream_t>(stream_));
+}
+
 template <typename OutT>
-static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, const double* dist, int by_kp,
-                       const float* spfh, int width, const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
+static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts, const int32_t* nbr, const double* dist,
+                       const float* weights, int by_kp, const float* spfh, int width, const int64_t* keypoints,
+                       int64_t nq, OutT* out, cudaStream_t stream) {
   const int64_t threads = nq * 32;
   const unsigned blocks = unsigned((threads + 255) / 256);
   // Passes of up to 4 column blocks of 32 bins (register tiles). A final partial block is masked, except when it
@@ -168,7 +246,7 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
       else if (r > 0) blocks_n += 1;
     }
 #define SF_LAUNCH_FPFH(B) \
-  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, nbr, dist, by_kp, spfh, width, base, rem, keypoints, nq, out)
+  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, dist, weights, by_kp, spfh, width, base, rem, keypoints, nq, out)
     switch (blocks_n) {
       case 1: SF_LAUNCH_FPFH(1); break;
       case 2: SF_LAUNCH_FPFH(2); break;
@@ -189,6 +267,72 @@ extern "C" int sf_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_fpfh: grid not built");
   SF_REQUIRE(offsets && nbr && dist && spfh && keypoints && out && width > 0, SF_ERR_ARG, "sf_fpfh: null argument");
   if (nq == 0) return SF_OK;
-  return out_is_f64 ? launch_fpfh(g, offsets, nbr, dist, csr_by_keypoint, spfh, width, keypoints, nq, static_cast<double*>(out), stream)
-                    : launch_fpfh(g, offsets, nbr, dist, csr_by_keypoint, spfh, width, keypoints, nq, static_cast<float*>(out), stream);
+  return out_is_f64 ? launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, keypoints, nq,
+                                  static_cast<double*>(out), stream)
+                    : launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, keypoints, nq,
+                                  static_cast<float*>(out), stream);
+}
+
+// Fused driver: what compute_fpfh_descriptor (fpfh.py:16-117) does for one cloud — search around EVERY cloud point,
+// SPFH of every point, FPFH of the keypoints — with the neighbour list as an internal, padded temporary.
+extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t decorrelated, const double* edges_host,
+                             const int64_t* keypoints, int64_t nq, void* out, int32_t out_is_f64, int64_t* pairs_host,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_fpfh_cloud: grid built without normals");
+  SF_REQUIRE(edges_host && (nq == 0 || (keypoints && out)) && nq >= 0, SF_ERR_ARG, "sf_fpfh_cloud: bad arguments");
+  SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
+             "sf_fpfh_cloud: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
+  SF_REQUIRE(n_bins >= 1 && n_bins <= kMaxBins, SF_ERR_CAPACITY, "sf_fpfh_cloud: n_bins must be in [1, %d]", kMaxBins);
+  const int64_t width64 = decorrelated ? 3 * int64_t(n_bins) : int64_t(n_bins) * n_bins * n_bins;
+  SF_REQUIRE(width64 <= 8192, SF_ERR_CAPACITY, "sf_fpfh_cloud: histogram width %lld exceeds 8192", (long long)width64);
+  const int width = int(width64);
+  const int64_t n = g->n;
+  if (pairs_host) *pairs_host = 0;
+  int64_t *cand = nullptr, *cand_offsets = nullptr;
+  int32_t *counts = nullptr, *nbr = nullptr;
+  float *weights = nullptr, *spfh = nullptr;
+  unsigned long long* pair_counter = nullptr;
+  void* scan_temp = nullptr;
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cand, cand_offsets, int(n + 1), stream);
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand), size_t(n + 1) * 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand_offsets), size_t(n + 1) * 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&counts), size_t(n) * 4, stream));
+  SF_CUDA(scratch_alloc(&scan_temp, scan_bytes + 16, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pair_counter), 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&spfh), size_t(n) * width * sizeof(float), stream));
+  SF_CUDA(cudaMemsetAsync(cand + n, 0, 8, stream));
+  SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
+  const GridView view = g->view();
+  self_candidate_count_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(view, n, cand);
+  SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, cand, cand_offsets, int(n + 1), stream));
+  int64_t total = 0;
+  SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
+  SF_CUDA(cudaStreamSynchronize(stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * 4, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&weights), size_t(total > 0 ? total : 1) * 4, stream));
+  profile_mark(0, stream);
+  search_weights_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, stream>>>(view, n, radius * radius, cand_offsets, nbr,
+                                                                          weights, counts, pair_counter);
+  SF_CUDA(cudaGetLastError());
+  profile_mark(1, stream);
+  int rc = launch_spfh(g, 0, n, cand_offsets, counts, nbr, n_bins, decorrelated, edges_host, spfh, stream);
+  profile_mark(2, stream);
+  if (rc == SF_OK && nq > 0)
+    rc = out_is_f64 ? launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, keypoints, nq,
+                                  static_cast<double*>(out), stream)
+                    : launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, keypoints, nq,
+                                  static_cast<float*>(out), stream);
+  profile_mark(3, stream);
+  if (rc == SF_OK && pairs_host != nullptr) {
+    unsigned long long pairs = 0;
+    SF_CUDA(cudaMemcpyAsync(&pairs, pair_counter, 8, cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaStreamSynchronize(stream));
+    *pairs_host = int64_t(pairs);
+  }
+  void* to_free[] = {cand, cand_offsets, counts, nbr, weights, spfh, scan_temp, pair_counter};
+  for (void* p : to_free)
+    if (p) cudaFreeAsync(p, stream);
+  return rc;
 }

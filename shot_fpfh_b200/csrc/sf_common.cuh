@@ -14,6 +14,8 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // Last error text, readable through sf_last_error(). No exceptions cross the C ABI.
 void set_error(const char* fmt, ...);
+// Measurement hook (shot.cu): records event `i` (0..3) on `stream` when sf_profile_enable(1) is in effect.
+void profile_mark(int i, cudaStream_t stream);
 
 #define SF_CUDA(call)                                                                              \
   do {                                                                                             \

@@ -370,10 +370,16 @@ extern "C" int sf_shot_lrf(sf_grid* g, const double* queries, int64_t nq, double
   return SF_OK;
 }
 
-// Optional per-kernel timing of the fused driver (bench.py's roofline needs the dominant kernel's own duration and
-// the driver is a single C call): CUDA events recorded on the launching stream around its three kernels.
+// Optional per-kernel timing of the fused drivers (bench.py's roofline needs the dominant kernel's own duration and
+// a driver is a single C call): CUDA events recorded on the launching stream around its three stages.
 static bool g_profile = false;
 static cudaEvent_t g_events[4] = {nullptr, nullptr, nullptr, nullptr};
+
+namespace sf {
+void profile_mark(int i, cudaStream_t stream) {
+  if (g_profile) cudaEventRecord(g_events[i], stream);
+}
+}  // namespace sf
 
 extern "C" int sf_profile_enable(int32_t enable) {
   if (enable && g_events[0] == nullptr)
@@ -382,7 +388,8 @@ extern "C" int sf_profile_enable(int32_t enable) {
   return SF_OK;
 }
 
-// ms_out[0..2] = search+moments, eigen, votes+descriptor of the LAST sf_shot_single_scale call (synchronises).
+// ms_out[0..2] = the three stages of the LAST fused driver call (sf_shot_single_scale: search+moments, eigen,
+// votes+descriptor; sf_fpfh_cloud: search+weights, SPFH, FPFH). Synchronises.
 extern "C" int sf_profile_read(float* ms_out) {
   SF_REQUIRE(g_profile && g_events[0] != nullptr && ms_out != nullptr, SF_ERR_ARG, "sf_profile_read: profiling is off");
   SF_CUDA(cudaEventSynchronize(g_events[3]));
@@ -458,15 +465,15 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   SF_CUDA(cudaStreamSynchronize(stream));
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * 4, stream));
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
-  if (g_profile) cudaEventRecord(g_events[0], stream);
+  profile_mark(0, stream);
   search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets, nbr,
                                                         counts, lrf, pair_counter);
-  if (g_profile) cudaEventRecord(g_events[1], stream);
+  profile_mark(1, stream);
   lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf);
-  if (g_profile) cudaEventRecord(g_events[2], stream);
+  profile_mark(2, stream);
   int rc = launch_descriptor(g, queries, nq, radius, cand_offsets, counts, nbr, lrf, 1, min_nb, normalize, out, out_is_f64,
                              stream);
-  if (g_profile) cudaEventRecord(g_events[3], stream);
+  profile_mark(3, stream);
   if (rc == SF_OK && pairs_host != nullptr) {  // neighbour pairs found (logging / algorithmic-byte accounting)
     unsigned long long pairs = 0;
     SF_CUDA(cudaMemcpyAsync(&pairs, pair_counter, 8, cudaMemcpyDeviceToHost, stream));

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256)
 // One thread per voxel (the thread at the first sorted position of the voxel walks its members).
 __global__ void __launch_bounds__(256)
     voxel_pick_kernel(const double* __restrict__ xyz, int64_t n, const unsigned long long* __restrict__ keys,
-                      const int32_t* __restrict__ order, const int32_t* __restrict__ rank, int32_t* __restrict__ picked) {
+                      const int32_t* __restrict__ order, const int32_t* __restrict__ rank, int32_t* __restrict__ picked,
+                      int32_t* __restrict__ members) {
   const int64_t s = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
   const unsigned long long key = keys[s];
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256)
     if (d < best) { best = d; best_i = int32_t(i); }
   }
   picked[rank[s]] = best_i;
+  if (members != nullptr) members[rank[s]] = int32_t(e - s);
 }
 
 __global__ void __launch_bounds__(256)
@@ -116,8 +118,8 @@ __global__ void __launch_bounds__(256)
 
 using namespace sf;
 
-extern "C" int sf_voxel_subsample(const double* xyz, int64_t n, double voxel, int32_t* picked, int64_t* count_host,
-                                  void* stream_) {
+extern "C" int sf_voxel_subsample(const double* xyz, int64_t n, double voxel, int32_t* picked, int32_t* members,
+                                  int64_t* count_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(xyz && picked && count_host && n >= 0, SF_ERR_ARG, "sf_voxel_subsample: bad arguments");
   SF_REQUIRE(voxel > 0.0 && n < (int64_t(1) << 31), SF_ERR_ARG, "sf_voxel_subsample: voxel must be > 0, n < 2^31");
@@ -150,7 +152,7 @@ extern "C" int sf_voxel_subsample(const double* xyz, int64_t n, double voxel, in
   voxel_flag_kernel<<<blocks, 256, 0, stream>>>(keys_out, n, flags);
   bytes = temp_bytes;
   SF_CUDA(cub::DeviceScan::ExclusiveSum(temp, bytes, flags, rank, int(n), stream));
-  voxel_pick_kernel<<<blocks, 256, 0, stream>>>(xyz, n, keys_out, order, rank, picked);
+  voxel_pick_kernel<<<blocks, 256, 0, stream>>>(xyz, n, keys_out, order, rank, picked, members);
   int32_t last_rank = 0, last_flag = 0;
   int overflow_host = 0;
   SF_CUDA(cudaMemcpyAsync(&last_rank, rank + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));

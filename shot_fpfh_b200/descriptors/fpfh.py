@@ -22,11 +22,13 @@ from ..device import Grid, download, upload
 
 def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
                 out_dtype: torch.dtype = torch.float64):
-    """search over every cloud point -> SPFH (cell-sorted rows) -> FPFH on the keypoints. Returns (fpfh, mean K)."""
-    offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
-    spfh_rows = ops.spfh(grid, offsets, nbr, n_bins, decorrelated)
-    out = ops.fpfh(grid, offsets, nbr, dist, spfh_rows, keypoints_dev, out_dtype=out_dtype)
-    return out, float(offsets[-1].item()) / max(grid.n, 1)
+    """
+    search over every cloud point -> SPFH (cell-sorted rows) -> FPFH on the keypoints, by the fused driver
+    (sf_fpfh_cloud; the piecewise sf_radius_* / sf_spfh / sf_fpfh calls serve the multi-GPU path, where the SPFH
+    stage is sharded). Returns (fpfh, mean K).
+    """
+    out, pairs = ops.fpfh_cloud(grid, radius, n_bins, decorrelated, keypoints_dev, out_dtype=out_dtype)
+    return out, float(pairs) / max(grid.n, 1)
 
 
 def compute_fpfh_descriptor(

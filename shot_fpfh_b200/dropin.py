@@ -11,9 +11,11 @@ What is replaced (SURVEY.md §8b — exactly what pipeline.py imports at :15 and
     shot_fpfh.descriptors.ShotMultiprocessor / compute_fpfh_descriptor   (and in shot_fpfh.pipeline's namespace)
     shot_fpfh.descriptors.shot.{get_local_rf, compute_single_shot_descriptor, compute_shot_descriptor}
     shot_fpfh.matching.{basic_matching, match_descriptors, double_matching_with_rejects}
-    shot_fpfh.descriptors.compute_normals (also re-exported by `shot_fpfh`), shot_fpfh.core.grid_subsampling
+    shot_fpfh.descriptors.compute_normals (also re-exported by `shot_fpfh`), shot_fpfh.core.grid_subsampling,
+    shot_fpfh.keypoint_selection.{select_keypoints_subsampling, select_keypoints_with_density_threshold}
         — the two "next" rows immediately upstream of the hot path
-Everything else (keypoint selection logic, RANSAC, ICP, I/O, configuration, analysis) stays the reference's code.
+Everything else (iterative / random keypoint selection, RANSAC, ICP, I/O, configuration, analysis) stays the
+reference's code.
 (`scripts/register_point_clouds.py` does `from shot_fpfh import compute_normals` at import time: call install()
 before importing the script for the GPU normals to be picked up there.)
 """
@@ -37,6 +39,7 @@ def _bind(module_name: str, attr: str, value) -> None:
 def install() -> list[str]:
     """Rebinds the names; returns the list of `module.attr` that were replaced. Needs the built CUDA library."""
     from . import descriptors as d
+    from . import keypoint_selection as k
     from . import matching as m
     from .descriptors import shot as s
     from .subsampling import grid_subsampling_gpu as _grid_subsampling
@@ -53,6 +56,10 @@ def install() -> list[str]:
         ("shot_fpfh.core.subsampling", "grid_subsampling", _grid_subsampling),
         ("shot_fpfh.core", "grid_subsampling", _grid_subsampling),
         ("shot_fpfh.keypoint_selection", "grid_subsampling", _grid_subsampling),
+        ("shot_fpfh.keypoint_selection", "select_keypoints_subsampling", k.select_keypoints_subsampling),
+        ("shot_fpfh.keypoint_selection", "select_keypoints_with_density_threshold", k.select_keypoints_with_density_threshold),
+        ("shot_fpfh.pipeline", "select_keypoints_subsampling", k.select_keypoints_subsampling),
+        ("shot_fpfh.pipeline", "select_keypoints_with_density_threshold", k.select_keypoints_with_density_threshold),
         ("shot_fpfh.descriptors.shot", "get_local_rf", s.get_local_rf),
         ("shot_fpfh.descriptors.shot", "compute_single_shot_descriptor", s.compute_single_shot_descriptor),
         ("shot_fpfh.descriptors.shot", "compute_shot_descriptor", s.compute_shot_descriptor),

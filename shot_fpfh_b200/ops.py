@@ -25,9 +25,10 @@ def radius_csr(
     want_index: bool = False,
     want_dist: bool = False,
     self_range: tuple[int, int] | None = None,
+    count_only: bool = False,
 ):
     """
-    Fixed-radius search (sf_radius_count + sf_radius_fill). `queries=None` searches around the cloud's own
+    Fixed-radius search (sf_radius_count + sf_radius_fill; `count_only` stops after the count: offsets only). `queries=None` searches around the cloud's own
     points at cell-sorted positions `self_range = (first, count)` (default: all of them).
     Returns (offsets int64[q+1], nbr_sorted|None, nbr_index|None, dist|None).
     """
@@ -49,6 +50,8 @@ def radius_csr(
             grid.handle, ptr(queries), int(first), nq, float(radius), ptr(offsets), ctypes.byref(total), stream_ptr()
         )
     )
+    if count_only:
+        return offsets, None, None, None
     p = int(total.value)
     nbr_sorted = torch.empty(p, dtype=torch.int32, device=dev) if want_sorted else None
     nbr_index = torch.empty(p, dtype=torch.int32, device=dev) if want_index else None
@@ -71,15 +74,22 @@ def grid_permutation(grid: Grid) -> tuple[torch.Tensor, torch.Tensor]:
     return perm, inv
 
 
-def voxel_subsample(xyz: torch.Tensor, voxel_size: float) -> torch.Tensor:
-    """Indices (int64, device) of one point per occupied voxel — `grid_subsampling` semantics, see csrc/subsample.cu."""
+def voxel_subsample(xyz: torch.Tensor, voxel_size: float, want_members: bool = False):
+    """
+    Indices (int64, device) of one point per occupied voxel — `grid_subsampling` semantics, see csrc/subsample.cu.
+    With `want_members` also the number of points of each of those voxels: (indices, members).
+    """
     n = int(xyz.shape[0])
     if n == 0:
-        return torch.empty(0, dtype=torch.int64, device=xyz.device)
+        empty = torch.empty(0, dtype=torch.int64, device=xyz.device)
+        return (empty, empty.clone()) if want_members else empty
     picked = torch.empty(n, dtype=torch.int32, device=xyz.device)
+    members = torch.empty(n, dtype=torch.int32, device=xyz.device) if want_members else None
     count = ctypes.c_int64(0)
-    check(lib.sf_voxel_subsample(ptr(xyz), n, float(voxel_size), ptr(picked), ctypes.byref(count), stream_ptr()))
-    return picked[: int(count.value)].long()
+    check(lib.sf_voxel_subsample(ptr(xyz), n, float(voxel_size), ptr(picked), ptr(members), ctypes.byref(count),
+                                 stream_ptr()))
+    picked = picked[: int(count.value)].long()
+    return (picked, members[: int(count.value)].long()) if want_members else picked
 
 
 def knn_attempt(grid: Grid, queries: torch.Tensor, k: int, reach: float, nbr_index: torch.Tensor, status: torch.Tensor):
@@ -200,6 +210,29 @@ def spfh(
         )
     )
     return out
+
+
+def fpfh_cloud(grid: Grid, radius: float, n_bins: int, decorrelated: bool, keypoints: torch.Tensor,
+               out_dtype: torch.dtype = torch.float64, out: torch.Tensor | None = None, want_pairs: bool = True):
+    """
+    The fused FPFH driver (sf_fpfh_cloud): search around every cloud point, SPFH, FPFH rows of `keypoints` (original
+    point indices, int64). Returns (rows (Q, width), number of neighbour pairs | None).
+    """
+    width = 3 * n_bins if decorrelated else n_bins**3
+    nq = int(keypoints.shape[0])
+    if out is None:
+        out = torch.empty((nq, width), dtype=out_dtype, device=keypoints.device)
+    assert out.shape == (nq, width) and out.is_contiguous()
+    edges = fpfh_edges(n_bins)
+    pairs = ctypes.c_int64(0)
+    check(
+        lib.sf_fpfh_cloud(
+            grid.handle, float(radius), int(n_bins), int(bool(decorrelated)),
+            edges.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ptr(keypoints), nq, ptr(out),
+            int(out.dtype == torch.float64), ctypes.byref(pairs) if want_pairs else None, stream_ptr(),
+        )
+    )
+    return out, (int(pairs.value) if want_pairs else None)
 
 
 def fpfh(

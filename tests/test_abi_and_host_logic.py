@@ -105,6 +105,12 @@ def test_signatures_mirror_the_reference():
     for name in ("get_local_rf", "get_azimuth_idx", "interpolate_on_adjacent_husks", "interpolate_vertical_volumes",
                  "compute_single_shot_descriptor", "compute_shot_descriptor"):
         assert params(getattr(shot, name)) == params(getattr(ref_shot, name)), name
+    import shot_fpfh.keypoint_selection as ref_k
+
+    import shot_fpfh_b200.keypoint_selection as k
+
+    for name in ("select_keypoints_subsampling", "select_keypoints_with_density_threshold"):
+        assert params(getattr(k, name)) == params(getattr(ref_k, name)), name
     import dataclasses
 
     ref_fields = [(f.name, f.default) for f in dataclasses.fields(ref_d.ShotMultiprocessor)]

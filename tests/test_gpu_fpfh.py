@@ -84,13 +84,17 @@ def test_large_size_properties_1m():
     p_dev, n_dev = upload(pts), upload(normals)
     grid = Grid().build(p_dev, n_dev, radius)
     kp = torch.arange(n, dtype=torch.int64, device=p_dev.device)
-    out, mean_k = fpfh_device(grid, kp, radius, 11, True, out_dtype=torch.float32)
-    out = out.cpu().numpy().astype(np.float64)
+    out_dev, mean_k = fpfh_device(grid, kp, radius, 11, True, out_dtype=torch.float32)  # the fused driver
+    out = out_dev.cpu().numpy().astype(np.float64)
     assert out.shape == (n, 33) and np.isfinite(out).all() and (out >= 0).all()
     assert 60 < mean_k < 90
     # SPFH rows: each of the three 11-bin blocks sums to (#binned)/K <= (K-1)/K
-    offsets, nbr, _, _ = ops.radius_csr(grid, None, radius)
-    spfh = ops.spfh(grid, offsets, nbr, 11, True).cpu().numpy()
+    offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
+    spfh_dev = ops.spfh(grid, offsets, nbr, 11, True)
+    # the piecewise entry points (exact CSR, float64 distances) give the fused driver's rows bit for bit
+    assert torch.equal(ops.fpfh(grid, offsets, nbr, dist, spfh_dev, kp, out_dtype=torch.float32), out_dev)
+    assert abs(mean_k - float(offsets[-1].item()) / n) < 1e-9
+    spfh = spfh_dev.cpu().numpy()
     blocks = spfh.reshape(n, 3, 11).sum(axis=2)
     assert (blocks <= 1.0 + 1e-6).all() and (blocks[:, 1] > 0.9).all()  # phi is always in range
     # spot check: 200 rows against the oracle evaluated on their two-ring neighbourhoods only

@@ -140,6 +140,47 @@ def test_voxel_subsampling_equals_host_semantics():
     assert grid_subsampling_gpu(np.zeros((0, 3)), 0.1).shape == (0,)
 
 
+def test_keypoint_selectors_against_oracle():
+    """§8f row 1: select_keypoints_subsampling / select_keypoints_with_density_threshold (keypoint_selection.py:34-122)."""
+    from oracle import keypoints_oracle
+    from shot_fpfh_b200.keypoint_selection import select_keypoints_subsampling, select_keypoints_with_density_threshold
+
+    pts = synthetic.bumpy_sphere(30_000, seed=4)[0]
+    s = synthetic.mean_spacing(30_000)
+
+    def same_up_to_ties(got, want, keys):
+        """Same voxels in the same order; representatives may differ only where both are equidistant from the voxel's
+        barycentre (2-point voxels: the reference's pick then follows an unstable argsort and summation order)."""
+        got, want = got.astype(int), want.astype(int)
+        assert got.shape == want.shape and np.array_equal(keys[got], keys[want])
+        for i in np.nonzero(got != want)[0]:
+            members = np.nonzero((keys == keys[got[i]]).all(axis=1))[0]
+            centre = pts[members].mean(axis=0)
+            assert abs(np.linalg.norm(pts[got[i]] - centre) - np.linalg.norm(pts[want[i]] - centre)) < 1e-12
+        assert (got != want).mean() < 0.05
+
+    for voxel in (2.0 * s, 3.5 * s):
+        keys = ((pts - pts.min(axis=0)) // voxel).astype(int)
+        got_sub = select_keypoints_subsampling(pts, voxel)
+        want_sub = keypoints_oracle.select_keypoints_subsampling(pts, voxel)
+        same_up_to_ties(got_sub, want_sub, keys)
+        ambiguous = {tuple(k) for k in keys[got_sub[got_sub != want_sub]]}  # voxels whose representative is a tie
+
+        def settled(idx):
+            return np.array([i for i in idx.astype(int) if tuple(keys[i]) not in ambiguous])
+
+        for value, radius in ((3, None), (9, voxel), (25, 1.5 * voxel), (6, 0.6 * voxel), (10**6, None)):
+            want = keypoints_oracle.select_keypoints_with_density_threshold(pts, voxel, value, radius)
+            got = select_keypoints_with_density_threshold(pts, voxel, value, radius)
+            if radius is None or radius == voxel:  # thresholds the voxel's own population: independent of the pick
+                assert got.shape == want.shape, (voxel, value, radius, got.shape, want.shape)
+                if want.shape[0]:
+                    same_up_to_ties(got, want, keys)
+            else:  # thresholds the count AROUND the representative: compare where the representative is settled
+                assert np.array_equal(settled(got), settled(want)) and settled(want).shape[0] > 1000
+    assert select_keypoints_with_density_threshold(np.zeros((0, 3)), 0.1, 3).shape == (0,)
+
+
 def test_degenerate_clouds():
     from shot_fpfh_b200.neighbors import RadiusSearch
 
