@@ -12,6 +12,7 @@ namespace sf {
 
 constexpr int kMaxBins = 64;
 __constant__ double c_edges[3][kMaxBins + 1];
+__constant__ double c_scale[3];  // n_bins / (last edge - first edge), per feature
 
 __global__ void __launch_bounds__(256)
     spfh_kernel(GridView g, int64_t first, int64_t count, const int64_t* __restrict__ offsets,
@@ -39,11 +40,11 @@ __global__ void __launch_bounds__(256)
       if (d2 > 0.0) {
         const double4 nj4 = load_pt(g.nrm + j);
         const double nj[3] = {nj4.x, nj4.y, nj4.z};
-        double alpha, phi, theta;
-        fpfh_features(rel, sqrt(d2), u, nj, alpha, phi, theta);
-        const int ia = histogram_bin(alpha, c_edges[0], n_bins);
-        const int ip = histogram_bin(phi, c_edges[1], n_bins);
-        const int it = histogram_bin(theta, c_edges[2], n_bins);
+        double alpha, phi, ny, nx;
+        fpfh_features_raw(rel, sqrt(d2), u, nj, alpha, phi, ny, nx);
+        const int ia = histogram_bin_scaled(alpha, c_edges[0], n_bins, c_scale[0]);
+        const int ip = histogram_bin_scaled(phi, c_edges[1], n_bins, c_scale[1]);
+        const int it = fpfh_theta_bin(ny, nx, c_edges[2], n_bins, c_scale[2]);
         if (decorrelated) {  // three independent np.histogram calls: each feature dropped on its own
           if (ia >= 0) atomicAdd(hist + ia, 1);
           if (ip >= 0) atomicAdd(hist + n_bins + ip, 1);
@@ -122,6 +123,15 @@ __global__ void __launch_bounds__(256)
   cand[s] = total;
 }
 
+__global__ void __launch_bounds__(256)
+    keypoint_position_kernel(const int32_t* __restrict__ inv_perm, const int64_t* __restrict__ keypoints, int64_t nq,
+                             int32_t* __restrict__ pos, int32_t* __restrict__ ids) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= nq) return;
+  pos[q] = inv_perm[keypoints[q]];
+  ids[q] = int32_t(q);
+}
+
 // One warp per keypoint. The neighbour list is consumed in chunks of 32: each lane loads one (index, 1/d) pair,
 // then the pairs are broadcast by shuffle and every lane accumulates its own bins — the row loads of consecutive
 // neighbours are independent, so several are in flight at once. Column blocks of 32 bins are register tiles;
@@ -132,10 +142,14 @@ __global__ void __launch_bounds__(256)
                 const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr, const double* __restrict__ dist,
                 const float* __restrict__ weights, int csr_by_keypoint,
                 const float* __restrict__ spfh, int width, int bin_base, int rem,
-                const int64_t* __restrict__ keypoints, int64_t nq, OutT* __restrict__ out) {
+                const int64_t* __restrict__ keypoints, const int32_t* __restrict__ order, int64_t nq,
+                OutT* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
-  if (q >= nq) return;
+  const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (slot >= nq) return;
+  // `order`: the keypoints sorted by their cell-sorted position, so that the warps in flight gather SPFH rows of the
+  // same neighbourhood of the cloud (L1/L2 hits instead of DRAM: callers pass keypoints in arbitrary order)
+  const int64_t q = order ? order[slot] : slot;
   const int64_t s = inv_perm[keypoints[q]];
   const int64_t row_id = csr_by_keypoint ? q : s;  // CSR rows follow the keypoints, or every cell-sorted point
   // counts: padded rows (fused driver); weights: float32 1/d precomputed by the search (0 where d == 0)
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(256)
       const float* row = spfh + int64_t(my_j) * width + rem_base;
       for (int c = 0; c < rem; ++c) tail[c] += __ldg(row + c) * my_w;
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int t = 0; t < cnt; ++t) {
       const int j = __shfl_sync(kFull, my_j, t);
       const float w = __shfl_sync(kFull, my_w, t);
@@ -206,7 +220,10 @@ static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
   double edges[3][kMaxBins + 1] = {};
   for (int f = 0; f < 3; ++f)
     for (int b = 0; b <= n_bins; ++b) edges[f][b] = edges_host[f * (n_bins + 1) + b];
+  double scale[3];
+  for (int f = 0; f < 3; ++f) scale[f] = double(n_bins) / (edges[f][n_bins] - edges[f][0]);
   SF_CUDA(cudaMemcpyToSymbolAsync(c_edges, edges, sizeof(edges), 0, cudaMemcpyHostToDevice, stream));
+  SF_CUDA(cudaMemcpyToSymbolAsync(c_scale, scale, sizeof(scale), 0, cudaMemcpyHostToDevice, stream));
   SF_CUDA(cudaStreamSynchronize(stream));  // `edges` is a stack buffer
   int warps = 8;
   while (warps > 1 && size_t(warps) * width * sizeof(int) > 64 * 1024) warps >>= 1;
@@ -233,6 +250,23 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts
                        int64_t nq, OutT* out, cudaStream_t stream) {
   const int64_t threads = nq * 32;
   const unsigned blocks = unsigned((threads + 255) / 256);
+  // processing order: keypoints by cell-sorted position (see fpfh_kernel); not worth a sort for a handful
+  int32_t *pos = nullptr, *ids = nullptr, *pos_sorted = nullptr, *order = nullptr;
+  void* sort_temp = nullptr;
+  if (nq >= 4096 && nq < (int64_t(1) << 31)) {
+    size_t sort_bytes = 0;
+    int end_bit = 1;
+    while ((int64_t(1) << end_bit) < g->n) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, pos, pos_sorted, ids, order, int(nq), 0, end_bit, stream);
+    SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pos), size_t(nq) * 4, stream));
+    SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&ids), size_t(nq) * 4, stream));
+    SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pos_sorted), size_t(nq) * 4, stream));
+    SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&order), size_t(nq) * 4, stream));
+    SF_CUDA(scratch_alloc(&sort_temp, sort_bytes + 16, stream));
+    keypoint_position_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(g->inv_perm, keypoints, nq, pos, ids);
+    SF_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, sort_bytes, pos, pos_sorted, ids, order, int(nq), 0, end_bit,
+                                            stream));
+  }
   // Passes of up to 4 column blocks of 32 bins (register tiles). A final partial block is masked, except when it
   // is at most 4 columns wide and follows a full block (the 33-bin layout): then it rides along as the "tail".
   int base = 0;
@@ -246,7 +280,7 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts
       else if (r > 0) blocks_n += 1;
     }
 #define SF_LAUNCH_FPFH(B) \
-  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, dist, weights, by_kp, spfh, width, base, rem, keypoints, nq, out)
+  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, dist, weights, by_kp, spfh, width, base, rem, keypoints, order, nq, out)
     switch (blocks_n) {
       case 1: SF_LAUNCH_FPFH(1); break;
       case 2: SF_LAUNCH_FPFH(2); break;
@@ -256,6 +290,9 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts
 #undef SF_LAUNCH_FPFH
     base += blocks_n * 32 + rem;
   }
+  void* to_free[] = {pos, ids, pos_sorted, order, sort_temp};
+  for (void* p : to_free)
+    if (p) cudaFreeAsync(p, stream);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -135,11 +135,23 @@ void hm_spfh_counts(const double* point, const double* normal, const double* nbr
     const double rel[3] = {nbrs[3 * i] - point[0], nbrs[3 * i + 1] - point[1], nbrs[3 * i + 2] - point[2]};
     const double d2 = rdist3(rel[0], rel[1], rel[2]);
     if (!(d2 > 0.0)) continue;
-    double alpha, phi, theta;
-    fpfh_features(rel, sqrt(d2), normal, nbr_normals + 3 * i, alpha, phi, theta);
-    const int ia = histogram_bin(alpha, edges, n_bins);
-    const int ip = histogram_bin(phi, edges + (n_bins + 1), n_bins);
-    const int it = histogram_bin(theta, edges + 2 * (n_bins + 1), n_bins);
+    double alpha, phi, ny, nx;  // as the kernel: reciprocal first guess, float32-filtered theta bin
+    fpfh_features_raw(rel, sqrt(d2), normal, nbr_normals + 3 * i, alpha, phi, ny, nx);
+    const double* e[3] = {edges, edges + (n_bins + 1), edges + 2 * (n_bins + 1)};
+    double scale[3];
+    for (int f = 0; f < 3; ++f) scale[f] = double(n_bins) / (e[f][n_bins] - e[f][0]);
+    const int ia = histogram_bin_scaled(alpha, e[0], n_bins, scale[0]);
+    const int ip = histogram_bin_scaled(phi, e[1], n_bins, scale[1]);
+    const int it = fpfh_theta_bin(ny, nx, e[2], n_bins, scale[2]);
+    {  // the filtered path must give the bins of the plain float64 path
+      double a2, p2, theta;
+      fpfh_features(rel, sqrt(d2), normal, nbr_normals + 3 * i, a2, p2, theta);
+      if (ia != histogram_bin(a2, e[0], n_bins) || ip != histogram_bin(p2, e[1], n_bins) ||
+          it != histogram_bin(theta, e[2], n_bins)) {
+        hist[0] = -1000000;
+        return;
+      }
+    }
     if (decorrelated) {
       if (ia >= 0) ++hist[ia];
       if (ip >= 0) ++hist[n_bins + ip];
@@ -151,5 +163,14 @@ void hm_spfh_counts(const double* point, const double* normal, const double* nbr
 }
 
 int hm_histogram_bin(double x, const double* edges, int n) { return histogram_bin(x, edges, n); }
+int hm_histogram_bin_scaled(double x, const double* edges, int n) {
+  return histogram_bin_scaled(x, edges, n, double(n) / (edges[n] - edges[0]));
+}
+int hm_theta_bin_float64(double ny, double nx, const double* edges, int n) {  // the unfiltered path
+  return histogram_bin(atan2(ny, nx), edges, n);
+}
+int hm_theta_bin(double ny, double nx, const double* edges, int n) {
+  return fpfh_theta_bin(ny, nx, edges, n, double(n) / (edges[n] - edges[0]));
+}
 
 }  // extern "C"

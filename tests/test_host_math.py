@@ -31,6 +31,9 @@ def hm():
     lib.hm_rdist3.argtypes = [ctypes.c_double] * 3
     lib.hm_azimuth_octant.argtypes = [ctypes.c_double] * 2
     lib.hm_histogram_bin.argtypes = [ctypes.c_double, DP, ctypes.c_int]
+    lib.hm_histogram_bin_scaled.argtypes = [ctypes.c_double, DP, ctypes.c_int]
+    lib.hm_theta_bin.argtypes = [ctypes.c_double, ctypes.c_double, DP, ctypes.c_int]
+    lib.hm_theta_bin_float64.argtypes = [ctypes.c_double, ctypes.c_double, DP, ctypes.c_int]
     lib.hm_eigh3.argtypes = [DP, DP, DP]
     lib.hm_lrf.argtypes = [DP, DP, ctypes.c_int, ctypes.c_double, DP]
     lib.hm_shot_descriptor.argtypes = [DP, DP, DP, ctypes.c_int, ctypes.c_double, DP, ctypes.c_int, ctypes.c_int,
@@ -150,6 +153,30 @@ def test_histogram_bin_is_numpy(hm):
             assert (got[~finite] == -1).all()
             counts = np.bincount(got[got >= 0], minlength=n_bins)
             assert np.array_equal(counts, np.histogram(vals[finite], bins=n_bins, range=(lo, hi))[0])
+
+
+def test_filtered_theta_bin_equals_float64_bin(hm):
+    """sf_math.cuh::fpfh_theta_bin (float32 angle unless it lands near an edge) == bin of the float64 atan2, also
+    for angles ON the edges, one ulp / 1e-9 / 1e-6 / 2e-5 rad around them, the +-pi/2 ends and the axes."""
+    rng = np.random.default_rng(9)
+    for n_bins in (5, 11, 16):
+        e = np.ascontiguousarray(np.linspace(-np.pi / 2, np.pi / 2, n_bins + 1))
+        angles = [rng.uniform(-np.pi, np.pi, 20000)]
+        for eps in (0.0, 1e-16, 1e-12, 1e-9, 1e-7, 1e-6, 9e-6, 1.1e-5, 2e-5):
+            angles += [e + eps, e - eps]
+        angles = np.concatenate(angles)
+        radii = 10.0 ** rng.uniform(-6, 2, angles.shape[0])
+        ny, nx = radii * np.sin(angles), radii * np.cos(angles)
+        extra = np.array([[0.0, 1.0], [0.0, -1.0], [1.0, 0.0], [-1.0, 0.0], [0.0, 0.0], [-0.0, -1.0], [1e-40, 1e-40],
+                          [1e-300, -1e-300]])
+        ny, nx = np.concatenate([ny, extra[:, 0]]), np.concatenate([nx, extra[:, 1]])
+        for y, x in zip(ny, nx):
+            # against the same libm atan2 (np.arctan2 may differ from it by an ulp, which decides an angle that is
+            # exactly ON an edge)
+            want = hm.hm_theta_bin_float64(float(y), float(x), _p(e), n_bins)
+            assert hm.hm_theta_bin(float(y), float(x), _p(e), n_bins) == want, (y, x)
+            theta = float(np.arctan2(y, x))
+            assert hm.hm_histogram_bin_scaled(theta, _p(e), n_bins) == hm.hm_histogram_bin(theta, _p(e), n_bins)
 
 
 @pytest.mark.parametrize("n_bins,decorrelated", [(5, False), (11, True), (11, False)])
