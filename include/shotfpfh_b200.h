@@ -195,6 +195,24 @@ int sf_match_rerank(const double* a_desc_dev, const int64_t* rows_a_dev, int64_t
                     int32_t* nn_dev, double* d1_dev, double* d2_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Registration stages downstream of the matcher: their data-parallel part.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* RANSAC (`ransac_on_matches`, matching/ransac.py:55-62): for each of the n_draws candidate transforms
+ * (transforms_dev: (n_draws, 12) = rotation row-major then translation) the number of matches i with
+ * || R a_i + t - b_i || <= threshold; a_dev / b_dev: the matched scan / reference keypoints, float64 (m,3). */
+int sf_ransac_count_inliers(const double* a_dev, const double* b_dev, int64_t m, const double* transforms_dev,
+                            int64_t n_draws, double threshold, int32_t* counts_dev, void* stream);
+/* One ICP point-to-plane iteration (`icp_point_to_plane`, icp.py:157-182 with `solver_point_to_plane`,
+ * core/solvers.py:34-48) on a grid built over the REFERENCE cloud with its normals and radius >= d_max: the scan
+ * points are moved by transform_host (12 doubles, as above), each one's nearest reference point is found
+ * (`KDTree.query`), pairs farther than d_max are dropped, and sums_host[29] receives, over the remaining pairs
+ * (p, q, n = normal of q), with g = [p x n, n] and h = (q - p).n: the 21 entries g_i g_j (i <= j, row order), the 6
+ * entries g_i h, sum |(p - q).n| and the number of pairs. nearest_dev (optional, int32[n_scan]): original index of
+ * the nearest reference point, -1 where none is within d_max. Synchronises `stream`. */
+int sf_icp_plane_step(sf_grid* ref_grid, const double* scan_dev, int64_t n_scan, const double* transform_host,
+                      double d_max, double* sums_host, int32_t* nearest_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Result transport. The reference returns dense float64 rows on the host (shot_parallelization.py:183); a SHOT row
  * is ~86 % zeros and the kernels' values are float32, so the rows cross PCIe compacted and the dense float64
  * array is rebuilt by host threads (float64(float32 x) is exact: the array equals a dense float64 copy).

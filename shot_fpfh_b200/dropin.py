@@ -14,7 +14,9 @@ What is replaced (SURVEY.md §8b — exactly what pipeline.py imports at :15 and
     shot_fpfh.descriptors.compute_normals (also re-exported by `shot_fpfh`), shot_fpfh.core.grid_subsampling,
     shot_fpfh.keypoint_selection.{select_keypoints_subsampling, select_keypoints_with_density_threshold}
         — the two "next" rows immediately upstream of the hot path
-Everything else (iterative / random keypoint selection, RANSAC, ICP, I/O, configuration, analysis) stays the
+    shot_fpfh.matching.ransac_on_matches, shot_fpfh.icp.icp_point_to_plane   (they return this
+        package's RigidTransform, which has the reference class's interface)
+Everything else (iterative / random keypoint selection, point-to-point ICP, I/O, configuration, analysis) stays the
 reference's code.
 (`scripts/register_point_clouds.py` does `from shot_fpfh import compute_normals` at import time: call install()
 before importing the script for the GPU normals to be picked up there.)
@@ -39,6 +41,7 @@ def _bind(module_name: str, attr: str, value) -> None:
 def install() -> list[str]:
     """Rebinds the names; returns the list of `module.attr` that were replaced. Needs the built CUDA library."""
     from . import descriptors as d
+    from . import icp
     from . import keypoint_selection as k
     from . import matching as m
     from .descriptors import shot as s
@@ -69,6 +72,11 @@ def install() -> list[str]:
         ("shot_fpfh.matching", "basic_matching", m.basic_matching),
         ("shot_fpfh.matching", "match_descriptors", m.match_descriptors),
         ("shot_fpfh.matching", "double_matching_with_rejects", m.double_matching_with_rejects),
+        ("shot_fpfh.matching.ransac", "ransac_on_matches", m.ransac_on_matches),
+        ("shot_fpfh.matching", "ransac_on_matches", m.ransac_on_matches),
+        ("shot_fpfh.pipeline", "ransac_on_matches", m.ransac_on_matches),
+        ("shot_fpfh.icp", "icp_point_to_plane", icp.icp_point_to_plane),
+        ("shot_fpfh.pipeline", "icp_point_to_plane", icp.icp_point_to_plane),
         # pipeline.py did `from shot_fpfh.descriptors import ...` / `from shot_fpfh.matching import ...`
         ("shot_fpfh.pipeline", "ShotMultiprocessor", d.ShotMultiprocessor),
         ("shot_fpfh.pipeline", "compute_fpfh_descriptor", d.compute_fpfh_descriptor),

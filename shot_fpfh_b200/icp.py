@@ -1,0 +1,62 @@
+"""
+`icp_point_to_plane` with the reference's signature (shot_fpfh/icp.py:137-189).
+
+Per iteration the reference moves the subsampled scan, asks a KD-tree for each point's nearest reference point,
+drops the pairs farther than `d_max`, builds the point-to-plane system `g^T g x = g^T h` (core/solvers.py:34-48),
+composes the step and reports the mean residual. Here one device call per iteration does everything up to the
+29 sums of that system (`sf_icp_plane_step`, csrc/registration.cu: warp per point on a uniform grid over the
+reference cloud, fixed summation order); the 6x6 solve, the Euler step and the composition are the reference's
+host arithmetic on those sums.
+
+`icp_point_to_point` / `icp_point_to_point_with_sampling` of the reference are not provided: the first computes its
+RMS with mismatched shapes whenever a pair is rejected (icp.py:119), the second draws from NumPy's
+global unseeded generator.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import numpy.typing as npt
+
+from .core import RigidTransform
+from .core.solvers import transform_from_plane_system
+
+
+def icp_point_to_plane(
+    scan: npt.NDArray[np.float64],
+    ref: npt.NDArray[np.float64],
+    ref_normals: npt.NDArray[np.float64],
+    transformation_init: RigidTransform,
+    d_max: float,
+    voxel_size: float = 0.2,
+    max_iter: int = 50,
+    rms_threshold: float = 1e-2,
+    disable_progress_bar: bool = False,
+) -> tuple[RigidTransform, float, bool]:
+    """Returns (transformation, last mean point-to-plane residual, whether it fell below `rms_threshold`)."""
+    from . import ops
+    from .device import Grid, upload
+
+    ref_dev, normals_dev, scan_dev = upload(ref), upload(ref_normals), upload(scan)
+    grid = Grid().build(ref_dev, normals_dev, float(d_max))
+    subsampled = scan_dev[ops.voxel_subsample(scan_dev, float(voxel_size))].contiguous()  # icp.py:156
+    transformation_icp = transformation_init
+    rms = 0.0
+    upper = np.triu_indices(6)
+    try:
+        for _ in range(max_iter):
+            sums = ops.icp_plane_step(grid, subsampled, transformation_icp.as_row(), float(d_max))
+            gtg = np.zeros((6, 6))
+            gtg[upper] = sums[:21]
+            gtg = gtg + np.triu(gtg, 1).T
+            step = transform_from_plane_system(gtg, sums[21:27])  # raises LinAlgError without inliers, like the reference
+            transformation_icp = step @ transformation_icp
+            rms = sums[27] / sums[28]
+            if rms < rms_threshold:
+                logging.info("RMS threshold reached.")
+                break
+    finally:
+        grid.close()
+    return transformation_icp, rms, rms < rms_threshold

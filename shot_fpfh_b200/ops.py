@@ -320,3 +320,33 @@ def match_rerank(a_desc, rows_a, b_desc, rows_b, cand_idx):
         )
     )
     return nn, d1, d2
+
+
+def ransac_count_inliers(matched_scan: torch.Tensor, matched_ref: torch.Tensor, transforms: torch.Tensor,
+                         threshold: float) -> torch.Tensor:
+    """Inliers of each candidate transform ((D, 12) rows: rotation row-major, translation) -> int32 (D,)."""
+    m, d = int(matched_scan.shape[0]), int(transforms.shape[0])
+    assert transforms.dtype == torch.float64 and transforms.shape[1:] == (12,) and matched_ref.shape == matched_scan.shape
+    counts = torch.zeros(d, dtype=torch.int32, device=matched_scan.device)
+    check(lib.sf_ransac_count_inliers(ptr(matched_scan), ptr(matched_ref), m, ptr(transforms), d, float(threshold),
+                                      ptr(counts), stream_ptr()))
+    return counts
+
+
+def icp_plane_step(ref_grid: Grid, scan: torch.Tensor, transform_row, d_max: float, want_nearest: bool = False):
+    """
+    One point-to-plane ICP iteration's sums (sf_icp_plane_step): float64 (29,) host array = 21 entries of g^T g
+    (upper triangle, row order), 6 of g^T h, sum of |residual|, number of pairs. With `want_nearest` also the
+    int32 device tensor of each scan point's nearest reference index (-1: none within d_max).
+    """
+    import numpy as np
+
+    row = np.ascontiguousarray(transform_row, dtype=np.float64)
+    assert row.shape == (12,)
+    sums = np.zeros(29, dtype=np.float64)
+    n = int(scan.shape[0])
+    nearest = torch.empty(n, dtype=torch.int32, device=scan.device) if want_nearest else None
+    dp = ctypes.POINTER(ctypes.c_double)
+    check(lib.sf_icp_plane_step(ref_grid.handle, ptr(scan), n, row.ctypes.data_as(dp), float(d_max),
+                                sums.ctypes.data_as(dp), ptr(nearest), stream_ptr()))
+    return (sums, nearest) if want_nearest else sums

@@ -50,3 +50,39 @@ def edge_case_inputs(g):
     pts = np.concatenate([pts, pts[:40]])
     nrm = np.concatenate([dirs, dirs[:40]])
     return pts, nrm, g["edge_queries"], float(g["edge_radius"])
+
+
+def registration_case(n=4000, seed=31):
+    """
+    A scan, its rigidly moved, permuted and slightly noisy copy with normals, and 600 matches, a third wrong.
+    The scan is three mutually orthogonal unit faces (a box corner) with a ripple on each: point-to-plane ICP is
+    well conditioned on it (on the near-spherical benchmark cloud it slides around the centre and does not
+    converge — in the reference just the same).
+    """
+    from shot_fpfh_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    face = rng.integers(0, 3, n)
+    uv = rng.uniform(0.0, 1.0, size=(n, 2))
+    ripple = 0.03 * np.sin(7.0 * uv[:, 0]) * np.cos(5.0 * uv[:, 1])
+    scan = np.zeros((n, 3))
+    normals = np.zeros((n, 3))
+    for k in range(3):
+        on = face == k
+        a, b = (k + 1) % 3, (k + 2) % 3
+        scan[on, a], scan[on, b], scan[on, k] = uv[on, 0], uv[on, 1], ripple[on]
+        # normal of the rippled face: (-dh/da, -dh/db, 1) normalised
+        da = 0.21 * np.cos(7.0 * uv[on, 0]) * np.cos(5.0 * uv[on, 1])
+        db = -0.15 * np.sin(7.0 * uv[on, 0]) * np.sin(5.0 * uv[on, 1])
+        nrm = np.stack([-da, -db, np.ones(on.sum())], axis=1)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        normals[on, a], normals[on, b], normals[on, k] = nrm[:, 0], nrm[:, 1], nrm[:, 2]
+    ref, ref_normals, perm, _, _ = synthetic.rigid_pair(scan, normals)
+    ref = ref + 0.002 * rng.normal(size=ref.shape)
+    true_ref = np.empty(n, dtype=np.int64)
+    true_ref[perm] = np.arange(n)  # ref[k] is scan point perm[k]
+    scan_idx = rng.choice(n, 600, replace=False)
+    ref_idx = true_ref[scan_idx].copy()
+    wrong = rng.random(600) < 0.33
+    ref_idx[wrong] = rng.integers(0, n, wrong.sum())
+    return scan, ref, ref_normals, scan_idx, ref_idx

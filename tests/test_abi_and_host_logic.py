@@ -111,6 +111,19 @@ def test_signatures_mirror_the_reference():
 
     for name in ("select_keypoints_subsampling", "select_keypoints_with_density_threshold"):
         assert params(getattr(k, name)) == params(getattr(ref_k, name)), name
+    import shot_fpfh.core as ref_core
+    import shot_fpfh.icp as ref_icp
+
+    import shot_fpfh_b200.core as core
+    import shot_fpfh_b200.icp as icp
+
+    assert params(m.ransac_on_matches) == params(ref_m.ransac_on_matches)
+    assert params(icp.icp_point_to_plane) == params(ref_icp.icp_point_to_plane)
+    for name in ("solver_point_to_point", "solver_point_to_plane"):
+        assert params(getattr(core, name)) == params(getattr(ref_core, name)), name
+    for method in ("__init__", "__matmul__", "__invert__", "__getitem__", "transform", "inv", "normalize_rotation"):
+        got, want = params(getattr(core.RigidTransform, method)), params(getattr(ref_core.RigidTransform, method))
+        assert [p[:2] for p in got] == [p[:2] for p in want], method  # the defaults are arrays: compared by name/kind
     import dataclasses
 
     ref_fields = [(f.name, f.default) for f in dataclasses.fields(ref_d.ShotMultiprocessor)]
