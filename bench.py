@@ -409,6 +409,65 @@ def bench_fpfh(args, pk):
     }
 
 
+def bench_registration(args, pk):
+    """
+    The stages after the matcher, through the reference-shaped API with host arrays in and
+    out: `ransac_on_matches` (10 000 draws over 20 000 matches, a third of them wrong) and `icp_point_to_plane`
+    (1M-point pair, ~100k voxel-subsampled scan points, 10 iterations). CPU figures: the oracle on a bounded part
+    of the same work (RANSAC: 100 draws, ICP: tree build + 2 iterations), scaled and labelled.
+    """
+    import shot_fpfh_b200.matching.ransac as ransac
+    from oracle import registration_oracle as ro
+    from shot_fpfh_b200 import synthetic
+    from shot_fpfh_b200.core import RigidTransform
+    from shot_fpfh_b200.icp import icp_point_to_plane
+
+    scan, normals = synthetic.bumpy_sphere(N_POINTS, seed=0)
+    ref, ref_normals, perm, rot, trans = synthetic.rigid_pair(scan, normals)
+    s = synthetic.mean_spacing(N_POINTS)
+    true_ref = np.empty(N_POINTS, dtype=np.int64)
+    true_ref[perm] = np.arange(N_POINTS)
+    rng = np.random.default_rng(5)
+    m = 20_000
+    scan_idx = rng.choice(N_POINTS, m, replace=False)
+    ref_idx = true_ref[scan_idx].copy()
+    wrong = rng.random(m) < 0.33
+    ref_idx[wrong] = rng.integers(0, N_POINTS, int(wrong.sum()))
+    out = {"workload": f"RANSAC 10000 draws x {m} matches; point-to-plane ICP, 1M-point pair, 10 iterations"}
+    times = []
+    for _ in range(3):
+        ransac.rng = np.random.default_rng(seed=72)
+        t0 = time.perf_counter()
+        ratio, best = ransac.ransac_on_matches(scan_idx, ref_idx, scan, ref, n_draws=10_000, distance_threshold=2 * s)
+        times.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    draws = [ransac.rng.choice(m, 4, replace=False, shuffle=False) for _ in range(10_000)]
+    t_draws = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ro.ransac_on_matches(scan_idx, ref_idx, scan, ref, np.random.default_rng(seed=72), n_draws=100, distance_threshold=2 * s)
+    cpu_ransac = (time.perf_counter() - t0) * 100
+    out["ransac"] = {"ms": min(times) * 1e3, "of_which_host_draw_replay_ms": t_draws * 1e3, "inlier_ratio": ratio,
+                     "cpu_oracle_ms_extrapolated_from_100_draws": cpu_ransac * 1e3}
+    init = RigidTransform(best.rotation, best.translation)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        t_icp, rms, _ = icp_point_to_plane(scan, ref, ref_normals, init, d_max=2 * s, voxel_size=QUERY_VOXEL_IN_SPACINGS * s,
+                                           max_iter=10, rms_threshold=0.0)
+        times.append(time.perf_counter() - t0)
+    from shot_fpfh_b200.subsampling import grid_subsampling
+
+    sub = grid_subsampling(scan, QUERY_VOXEL_IN_SPACINGS * s)
+    t0 = time.perf_counter()
+    ro.icp_point_to_plane(scan, ref, ref_normals, (best.rotation, best.translation), 2 * s, sub, max_iter=2, rms_threshold=0.0)
+    cpu_icp2 = time.perf_counter() - t0
+    out["icp_point_to_plane"] = {"ms": min(times) * 1e3, "iterations": 10, "subsampled_points": int(sub.shape[0]),
+                                 "final_mean_residual": float(rms),
+                                 "rotation_error_max_abs": float(np.abs(t_icp.rotation - rot).max()),
+                                 "cpu_oracle_ms_tree_build_plus_2_iterations": cpu_icp2 * 1e3}
+    return out
+
+
 def bench_match(args, pk, q: int = 200_000):
     """C4: 200k x 200k 352-d exact NN (+ second NN for the ratio test): shortlist GEMM on tensor cores + fp64 re-rank."""
     import torch
@@ -469,7 +528,7 @@ def main():
         v, info = cpu_shot_sample(pts, normals, kp, radius, args.cpu_seconds)
         cpu = {"value": v, "unit": "descriptors/s", **info}
         if not args.skip_extra:
-            for name, fn in (("fpfh_c3", bench_fpfh), ("match_c4", bench_match)):
+            for name, fn in (("fpfh_c3", bench_fpfh), ("match_c4", bench_match), ("registration", bench_registration)):
                 try:
                     extra[name] = fn(args, pk)
                 except Exception as exc:  # noqa: BLE001  (the headline line must still be printed)
