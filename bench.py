@@ -361,6 +361,14 @@ def bench_shot(args, dist, rank, world, pk):
             "host": (pts, normals, kp, radius), "launches": OWN_KERNELS_PER_SHOT_STEP * args.steps}
 
 
+def _pinned(a):
+    import torch
+
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+    t.numpy()[...] = a
+    return t.numpy()
+
+
 def bench_fpfh(args, pk):
     """C3: FPFH 33-d on the full 1M-point cloud, every point a query."""
     import torch
@@ -400,9 +408,25 @@ def bench_fpfh(args, pk):
            "fpfh": (4 * d + 8) * p + 4 * d * n + 4 * n}
     dominant = max(stages, key=stages.get)
     grid.close()
+    # end to end through the reference-shaped call: host float64 arrays in (pinned), (N, 33) float64 host array out
+    from shot_fpfh_b200.descriptors import compute_fpfh_descriptor
+
+    h_pts, h_nrm = _pinned(pts), _pinned(normals)
+    h_kp = np.arange(N_POINTS, dtype=np.int64)
+    e2e_times = []
+    for i in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rows = compute_fpfh_descriptor(h_kp, h_pts, h_nrm, radius, n_bins=11, decorrelated=True, verbose=False)
+        if i >= 2:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_ms = float(np.mean(e2e_times)) * 1e3
     return {
         "workload": "C3: FPFH 33-d (n_bins=11, decorrelated), 1M-point cloud, every point a query, 1 GPU",
         "value": n / (ms * 1e-3), "unit": "descriptors/s", "ms_per_step": ms, "steps": steps, "neighbour_pairs": p,
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "descriptors/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h_pts.nbytes + h_nrm.nbytes + h_kp.nbytes), "d2h_bytes_per_step": int(rows.nbytes),
+                "api": "compute_fpfh_descriptor(keypoints_indices, cloud_points, normals, radius, n_bins=11, decorrelated=True)"},
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": alg[dominant] / (stages[dominant] * 1e-3) / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg[dominant] / (stages[dominant] * 1e-3) / 1e9 / pk["hbm_gbs"],
                      "per_stage": {k: {"ms": stages[k], "algorithmic_GBps": alg[k] / (stages[k] * 1e-3) / 1e9} for k in stages}},
@@ -492,9 +516,24 @@ def bench_match(args, pk, q: int = 200_000):
     ms, stages = timed_steps(step, steps, min(args.warmup, 3), lambda: flush_buf.fill_(1))
     flops = 2.0 * q * q * 352
     tf = flops / (stages["shortlist_gemm"] * 1e-3) / 1e12
+    # end to end through the reference-shaped call: two (q, 352) float64 host arrays in (pinned), index pairs out
+    from shot_fpfh_b200.matching import basic_matching
+
+    h_a, h_b = _pinned(a.cpu().numpy()), _pinned(b.cpu().numpy())
+    e2e_times = []
+    for i in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pairs = basic_matching(h_a, h_b)
+        if i >= 1:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_ms = float(np.mean(e2e_times)) * 1e3
     return {
         "workload": f"C4: {q} x {q} x 352 exact nearest + second-nearest neighbour, synthetic sparse unit rows, 1 GPU",
         "value": q / (ms * 1e-3), "unit": "match queries/s", "ms_per_step": ms, "steps": steps,
+        "e2e": {"value": q / (e2e_ms * 1e-3), "unit": "match queries/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h_a.nbytes + h_b.nbytes), "d2h_bytes_per_step": int(pairs[0].nbytes + pairs[1].nbytes),
+                "api": "basic_matching(scan_descriptors, ref_descriptors)"},
         "roofline": {"kernel": "topk_tc_kernel", "bound": "tensor", "achieved": tf, "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": tf / pk["tflops"], "flops": flops,
                      "per_stage_ms": stages},
