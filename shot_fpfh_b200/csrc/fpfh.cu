@@ -65,42 +65,115 @@ __global__ void __launch_bounds__(256)
 // Fused driver, stage 0: ONE scan of the candidate cells of every cloud point (cell-sorted order) writes the
 // neighbours into a PADDED list (slots sized by the candidate count, a cell_start lookup — no counting pass over
 // the candidates), the float32 weights 1/d that stage 2 needs (fpfh.py:112-114; 0 where d == 0) and the counts.
-__global__ void __launch_bounds__(256)
+//
+// Work unit: a TILE of 32 consecutive cell-sorted points, one warp. The points of a tile lie in one to three cells,
+// and all the points of a cell share their candidate set (the 9 runs around the cell): per distinct cell of the
+// tile the warp stages the candidates in shared memory once (chunks of kSearchChunk), then each of the cell's
+// points in the tile scans them from there with all 32 lanes. Against one warp per point walking the runs in
+// global memory this removes the per-point run setup, the run lookup per candidate and the L1 traffic
+// (measured at C3: 1.28 -> 0.93 ms), and the neighbour order is the same (run order, ascending position).
+constexpr int kSearchChunk = 256;
+constexpr int kSearchWarps = 8;
+
+struct SearchStage {  // per warp, in shared memory
+  double x[kSearchChunk], y[kSearchChunk], z[kSearchChunk];
+  int pos[kSearchChunk];
+  // ring of hits waiting for their weight: the float64 sqrt and reciprocal are evaluated 32 hits at a time with
+  // every lane busy (about a third of the candidates are hits) and the list is written with full-warp stores
+  double hit_d2[64];
+  int hit_pos[64];
+};
+
+__global__ void __launch_bounds__(kSearchWarps * 32)
     search_weights_kernel(GridView g, int64_t n, double r2, const int64_t* __restrict__ cand_offsets,
                           int32_t* __restrict__ nbr, float* __restrict__ weights, int32_t* __restrict__ counts,
                           unsigned long long* __restrict__ pair_counter) {
+  extern __shared__ unsigned char stage_mem[];
   const int lane = threadIdx.x & 31;
-  const int64_t s = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
-  if (s >= n) return;
-  const double4 me = load_pt(g.pts + s);
-  const Runs runs = build_runs(g, me.x, me.y, me.z, lane);
-  const int total = runs.pref[9];
-  int64_t out = cand_offsets[s];
-  int count = 0;
-  for (int base = 0; base < total; base += 32) {
-    const int v = base + lane;
-    bool hit = false;
-    int pos = 0;
-    double d2 = 0.0;
-    if (v < total) {
-      pos = run_position(runs, v);
-      const double4 p = load_pt(g.pts + pos);
-      d2 = rdist3(me.x - p.x, me.y - p.y, me.z - p.z);
-      hit = d2 <= r2;
-    }
-    const unsigned mask = __ballot_sync(kFull, hit);
-    if (hit) {
-      const int64_t o = out + __popc(mask & lanemask_lt());
-      nbr[o] = pos;
-      weights[o] = d2 > 0.0 ? float(1.0 / sqrt(d2)) : 0.0f;
-    }
-    out += __popc(mask);
-    count += __popc(mask);
+  SearchStage& st = reinterpret_cast<SearchStage*>(stage_mem)[threadIdx.x >> 5];
+  const int64_t tile = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t s0 = tile * 32;
+  if (s0 >= n) return;
+  const int in_tile = int(n - s0 < 32 ? n - s0 : 32);
+  // lane l owns point s0 + l: its coordinates, its cell, its running count and output cursor
+  double4 me = make_double4(0, 0, 0, 0);
+  int cx = 0, cy = 0, cz = 0;
+  int64_t cursor = 0;
+  if (lane < in_tile) {
+    me = load_pt(g.pts + s0 + lane);
+    cx = cell_coord(me.x, g.origin[0], g.inv_cell, g.dims[0]);
+    cy = cell_coord(me.y, g.origin[1], g.inv_cell, g.dims[1]);
+    cz = cell_coord(me.z, g.origin[2], g.inv_cell, g.dims[2]);
+    cursor = cand_offsets[s0 + lane];
   }
-  if (lane == 0) {
-    counts[s] = count;
-    atomicAdd(pair_counter, static_cast<unsigned long long>(count));
+  int my_count = 0;
+  int first = 0;  // first lane of the current group (lanes of one cell are consecutive: the points are cell-sorted)
+  while (first < in_tile) {
+    const int gx = __shfl_sync(kFull, cx, first), gy = __shfl_sync(kFull, cy, first), gz = __shfl_sync(kFull, cz, first);
+    const unsigned same = __ballot_sync(kFull, lane >= first && lane < in_tile && cx == gx && cy == gy && cz == gz);
+    const int last = 32 - __clz(same);  // one past the group's last lane
+    const Runs runs = build_runs_cell(g, gx, gy, gz, lane);
+    const int total = runs.pref[9];
+    for (int chunk = 0; chunk < total; chunk += kSearchChunk) {
+      const int len = total - chunk < kSearchChunk ? total - chunk : kSearchChunk;
+      __syncwarp();  // the previous chunk has been consumed
+      for (int v = lane; v < len; v += 32) {
+        const int pos = run_position(runs, chunk + v);
+        const double4 p = load_pt(g.pts + pos);
+        st.x[v] = p.x; st.y[v] = p.y; st.z[v] = p.z;
+        st.pos[v] = pos;
+      }
+      __syncwarp();
+      for (int owner = first; owner < last; ++owner) {
+        const double qx = __shfl_sync(kFull, me.x, owner), qy = __shfl_sync(kFull, me.y, owner),
+                     qz = __shfl_sync(kFull, me.z, owner);
+        int64_t out = __shfl_sync(kFull, cursor, owner);
+        int found = 0, head = 0, tail = 0;  // found = hits written out; ring entries [head, tail)
+        for (int base = 0; base < len; base += 32) {
+          const int v = base + lane;
+          bool hit = false;
+          double d2 = 0.0;
+          if (v < len) {
+            d2 = rdist3(qx - st.x[v], qy - st.y[v], qz - st.z[v]);
+            hit = d2 <= r2;
+          }
+          const unsigned mask = __ballot_sync(kFull, hit);
+          if (hit) {
+            const int slot = (tail + __popc(mask & lanemask_lt())) & 63;
+            st.hit_d2[slot] = d2;
+            st.hit_pos[slot] = st.pos[v];
+          }
+          tail += __popc(mask);
+          __syncwarp();
+          if (tail - head >= 32) {
+            const int slot = (head + lane) & 63;
+            const double h2 = st.hit_d2[slot];
+            nbr[out + found + lane] = st.hit_pos[slot];
+            weights[out + found + lane] = h2 > 0.0 ? float(1.0 / sqrt(h2)) : 0.0f;
+            head += 32;
+            found += 32;
+            __syncwarp();
+          }
+        }
+        if (lane < tail - head) {  // what is left in the ring
+          const int slot = (head + lane) & 63;
+          const double h2 = st.hit_d2[slot];
+          nbr[out + found + lane] = st.hit_pos[slot];
+          weights[out + found + lane] = h2 > 0.0 ? float(1.0 / sqrt(h2)) : 0.0f;
+        }
+        found += tail - head;
+        __syncwarp();
+        if (lane == owner) {
+          cursor += found;
+          my_count += found;
+        }
+      }
+    }
+    first = last;
   }
+  if (lane < in_tile) counts[s0 + lane] = my_count;
+  const int tile_pairs = warp_sum(my_count);
+  if (lane == 0) atomicAdd(pair_counter, static_cast<unsigned long long>(tile_pairs));
 }
 
 __global__ void __launch_bounds__(256)
@@ -350,8 +423,17 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * 4, stream));
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&weights), size_t(total > 0 ? total : 1) * 4, stream));
   profile_mark(0, stream);
-  search_weights_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, stream>>>(view, n, radius * radius, cand_offsets, nbr,
-                                                                          weights, counts, pair_counter);
+  {
+    const size_t smem = size_t(kSearchWarps) * sizeof(SearchStage);
+    static bool configured = false;
+    if (!configured) {
+      SF_CUDA(cudaFuncSetAttribute(search_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      configured = true;
+    }
+    const int64_t tiles = (n + 31) / 32;
+    search_weights_kernel<<<unsigned((tiles + kSearchWarps - 1) / kSearchWarps), kSearchWarps * 32, smem, stream>>>(
+        view, n, radius * radius, cand_offsets, nbr, weights, counts, pair_counter);
+  }
   SF_CUDA(cudaGetLastError());
   profile_mark(1, stream);
   int rc = launch_spfh(g, 0, n, cand_offsets, counts, nbr, n_bins, decorrelated, edges_host, spfh, stream);

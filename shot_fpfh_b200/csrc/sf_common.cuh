@@ -148,10 +148,8 @@ __device__ __forceinline__ int cell_coord(double q, double origin, double inv_ce
   return int(c);
 }
 
-__device__ __forceinline__ Runs build_runs(const GridView& g, double qx, double qy, double qz, int lane) {
-  const int cx = cell_coord(qx, g.origin[0], g.inv_cell, g.dims[0]);
-  const int cy = cell_coord(qy, g.origin[1], g.inv_cell, g.dims[1]);
-  const int cz = cell_coord(qz, g.origin[2], g.inv_cell, g.dims[2]);
+// The runs around cell (cx, cy, cz) — coordinates may lie outside the grid (queries off the cloud).
+__device__ __forceinline__ Runs build_runs_cell(const GridView& g, int cx, int cy, int cz, int lane) {
   int s = 0, len = 0;
   if (lane < 9) {
     const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
@@ -176,6 +174,12 @@ __device__ __forceinline__ Runs build_runs(const GridView& g, double qx, double 
   }
   r.pref[0] = 0;
   return r;
+}
+
+__device__ __forceinline__ Runs build_runs(const GridView& g, double qx, double qy, double qz, int lane) {
+  return build_runs_cell(g, cell_coord(qx, g.origin[0], g.inv_cell, g.dims[0]),
+                         cell_coord(qy, g.origin[1], g.inv_cell, g.dims[1]),
+                         cell_coord(qz, g.origin[2], g.inv_cell, g.dims[2]), lane);
 }
 
 // Position in the cell-sorted array of virtual candidate v (0 <= v < pref[9]).

@@ -66,7 +66,10 @@ def host_threads(requested: int | None = None) -> int:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover
         avail = os.cpu_count() or 1
-    return max(1, min(avail - 2, 8 if requested is None else int(requested)))
+    # one process per GPU (torchrun): the ranks of a node share its cores
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    share = avail // ranks - 2
+    return max(1, min(share, 8 if requested is None else int(requested)))
 
 
 class SparseRowsDownload:
