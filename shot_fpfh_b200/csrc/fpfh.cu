@@ -13,11 +13,13 @@ namespace sf {
 constexpr int kMaxBins = 64;
 __constant__ double c_edges[3][kMaxBins + 1];
 __constant__ double c_scale[3];  // n_bins / (last edge - first edge), per feature
+__constant__ float c_lo32[3], c_scale32[3];  // float32 roundings of the first edges and of the scales (filtered bins)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     spfh_kernel(GridView g, int64_t first, int64_t count, const int64_t* __restrict__ offsets,
                 const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr, int n_bins, int decorrelated,
-                int width, float* __restrict__ spfh) {
+                int width, int allow_fast, float* __restrict__ spfh) {
+  // allow_fast: bins from the float32-filtered features (sf_math.cuh::fpfh_bins_fast), float64 where unsure
   // counts == nullptr: CSR rows [offsets[s], offsets[s+1]); otherwise padded rows [offsets[s], offsets[s] + counts[s])
   extern __shared__ int hist_mem[];
   const int lane = threadIdx.x & 31;
@@ -31,20 +33,18 @@ __global__ void __launch_bounds__(256)
     const double4 p = load_pt(g.pts + first + s);
     const double4 un = load_pt(g.nrm + first + s);
     const double u[3] = {un.x, un.y, un.z};
+    const float u32[3] = {float(un.x), float(un.y), float(un.z)};
+    const float u_norm = sqrtf(u32[0] * u32[0] + u32[1] * u32[1] + u32[2] * u32[2]);
     const int64_t begin = offsets[s], end = counts ? begin + counts[s] : offsets[s + 1];
     for (int64_t i = begin + lane; i < end; i += 32) {
       const int j = __ldg(nbr + i);
       const double4 pj = load_pt(g.pts + j);
+      const double4 nj4 = load_pt(g.nrm + j);
       const double rel[3] = {pj.x - p.x, pj.y - p.y, pj.z - p.z};
-      const double d2 = rdist3(rel[0], rel[1], rel[2]);
-      if (d2 > 0.0) {
-        const double4 nj4 = load_pt(g.nrm + j);
-        const double nj[3] = {nj4.x, nj4.y, nj4.z};
-        double alpha, phi, ny, nx;
-        fpfh_features_raw(rel, sqrt(d2), u, nj, alpha, phi, ny, nx);
-        const int ia = histogram_bin_scaled(alpha, c_edges[0], n_bins, c_scale[0]);
-        const int ip = histogram_bin_scaled(phi, c_edges[1], n_bins, c_scale[1]);
-        const int it = fpfh_theta_bin(ny, nx, c_edges[2], n_bins, c_scale[2]);
+      const double nj[3] = {nj4.x, nj4.y, nj4.z};
+      int ia, ip, it;
+      if (fpfh_pair_bins(rel, u, u32, u_norm, nj, n_bins, &c_edges[0][0], kMaxBins + 1, c_scale, c_lo32, c_scale32,
+                         allow_fast != 0, ia, ip, it)) {
         if (decorrelated) {  // three independent np.histogram calls: each feature dropped on its own
           if (ia >= 0) atomicAdd(hist + ia, 1);
           if (ip >= 0) atomicAdd(hist + n_bins + ip, 1);
@@ -55,9 +55,12 @@ __global__ void __launch_bounds__(256)
       }
     }
     __syncwarp();
-    const double k_all = double(end - begin);
+    // hist / K (fpfh.py:79: K counts the point itself and duplicates). The rows are float32 values: the quotient
+    // is formed in float32 (two roundings, 1.2e-7 relative, against the 1e-4 bar) instead of a float64 division
+    // per bin.
+    const float inv_k = end > begin ? 1.0f / float(end - begin) : 0.0f;
     float* row = spfh + s * int64_t(width);
-    for (int b = lane; b < width; b += 32) row[b] = end > begin ? float(double(hist[b]) / k_all) : 0.0f;
+    for (int b = lane; b < width; b += 32) row[b] = float(hist[b]) * inv_k;
     __syncwarp();
   }
 }
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
 }  // namespace sf
 
 using namespace sf;
@@ -297,6 +301,16 @@ static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
   for (int f = 0; f < 3; ++f) scale[f] = double(n_bins) / (edges[f][n_bins] - edges[f][0]);
   SF_CUDA(cudaMemcpyToSymbolAsync(c_edges, edges, sizeof(edges), 0, cudaMemcpyHostToDevice, stream));
   SF_CUDA(cudaMemcpyToSymbolAsync(c_scale, scale, sizeof(scale), 0, cudaMemcpyHostToDevice, stream));
+  float lo32[3], scale32[3];
+  for (int f = 0; f < 3; ++f) {
+    lo32[f] = float(edges[f][0]);
+    scale32[f] = float(scale[f]);
+  }
+  SF_CUDA(cudaMemcpyToSymbolAsync(c_lo32, lo32, sizeof(lo32), 0, cudaMemcpyHostToDevice, stream));
+  SF_CUDA(cudaMemcpyToSymbolAsync(c_scale32, scale32, sizeof(scale32), 0, cudaMemcpyHostToDevice, stream));
+  // SF_SPFH_EXACT=1 (tests, measurements): every pair through the float64 path
+  const char* exact_env = getenv("SF_SPFH_EXACT");
+  const int allow_fast = (exact_env != nullptr && exact_env[0] == '1') ? 0 : 1;
   SF_CUDA(cudaStreamSynchronize(stream));  // `edges` is a stack buffer
   int warps = 8;
   while (warps > 1 && size_t(warps) * width * sizeof(int) > 64 * 1024) warps >>= 1;
@@ -306,7 +320,7 @@ static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
   const int64_t blocks_needed = (count + warps - 1) / warps;
   const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
   spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, counts, nbr, n_bins, decorrelated,
-                                                    width, spfh);
+                                                    width, allow_fast, spfh);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

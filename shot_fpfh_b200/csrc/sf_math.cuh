@@ -290,4 +290,91 @@ SF_HD int fpfh_theta_bin(double ny, double nx, const double* e, int n, double sc
   return histogram_bin_scaled(atan2(ny, nx), e, n, scale);
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// The three SPFH bins of one pair, float32-filtered. Only the BINS of (alpha, phi, theta) are used, and a bin is
+// 1/n of the feature's range wide, so the features are first evaluated in float32 from the float32 roundings of
+// rel = p_j - p_i (formed in float64), u and n_j, together with a bound on how far the float32 value can be from
+// the reference's float64 value; a bin is accepted only when the value keeps that distance (times a safety factor
+// of 4) from every edge and from the ends of the range. Otherwise — a few pairs in 100 000 on generic data, every
+// pair on degenerate data such as alpha == 0 on an edge — the caller evaluates the exact float64 path.
+//
+// Error bounds, eps = 2^-24, C = |rel|, U = |u|, N = |n_j| (Euclidean norms), first order, worst case:
+//   v = rel x u      each component  <= 4 eps C U   (two roundings of the inputs, product and sum roundings)
+//   alpha = v . n_j  <= 7 eps CUN (from v) + eps CUN (n_j) + 3 eps CUN (sum)              <= 16 eps C U N
+//   phi = rel.u / d  <= 5 eps U (dot) + 4 eps U (rsqrt, product)                           <= 16 eps U
+//   w = u x v        <= 12 eps U^2 C ;  ny = n_j . w <= 16 eps N U^2 C ;  nx = n_j . u <= 5 eps N U
+//   theta            <= (err ny + err nx) / hypot(ny, nx)  +  5e-7 (atan2f, 2 ulp at pi)
+// The float64 reference carries its own rounding (1e-16 relative): far below these margins.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int kBinUnsure = -2;
+
+SF_HD float sf_rsqrtf(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+// Bin of x in n equal bins over [lo, lo + n / scale] when x is known to `margin` (same units as x); -1 when x is
+// safely outside the range; kBinUnsure when an edge or an end of the range is within the margin.
+SF_HD int fpfh_bin_fast(float x, float lo, float scale, int n, float margin) {
+  const float eps = 5.9604645e-8f;
+  const float pos = (x - lo) * scale;                      // in bin widths
+  const float mm = margin * scale + 8.0f * eps * float(n);  // + the roundings of lo, the difference and the product
+  if (pos < -mm || pos > float(n) + mm) return -1;
+  const float cell = floorf(pos), frac = pos - cell;
+  if (pos > mm && pos < float(n) - mm && frac > mm && 1.0f - frac > mm) return int(cell);
+  return kBinUnsure;  // also NaN
+}
+
+// rel, u, nj: float32 roundings; U = |u| in float32. Returns false when any of the three bins is unsure (or the
+// pair is too short / too long for float32 — the caller's float64 path then also decides whether d > 0).
+SF_HD bool fpfh_bins_fast(const float rel[3], const float u[3], float U, const float nj[3], int n, const float lo[3],
+                          const float scale[3], int& ia, int& ip, int& it) {
+  const float eps = 5.9604645e-8f;
+  const float c2 = rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2];
+  if (!(c2 > 1e-30f && c2 < 1e30f)) return false;
+  const float inv_c = sf_rsqrtf(c2), C = c2 * inv_c;
+  // |n_j| enters the margins only: max(1, |n_j|^2) >= |n_j| saves the square root (unit normals: 1 + 1e-7)
+  const float N = fmaxf(1.0f, nj[0] * nj[0] + nj[1] * nj[1] + nj[2] * nj[2]);
+  const float v0 = rel[1] * u[2] - rel[2] * u[1], v1 = rel[2] * u[0] - rel[0] * u[2], v2 = rel[0] * u[1] - rel[1] * u[0];
+  const float w0 = u[1] * v2 - u[2] * v1, w1 = u[2] * v0 - u[0] * v2, w2 = u[0] * v1 - u[1] * v0;
+  const float alpha = v0 * nj[0] + v1 * nj[1] + v2 * nj[2];
+  const float phi = (rel[0] * u[0] + rel[1] * u[1] + rel[2] * u[2]) * inv_c;
+  const float ny = nj[0] * w0 + nj[1] * w1 + nj[2] * w2;
+  const float nx = nj[0] * u[0] + nj[1] * u[1] + nj[2] * u[2];
+  const float r2 = ny * ny + nx * nx;
+  if (!(r2 > 1e-30f && r2 < 1e30f)) return false;
+  const float NU = N * U, CU = C * U;
+  const float m_alpha = 64.0f * eps * CU * N;
+  const float m_phi = 64.0f * eps * U;
+  const float m_theta = 4.0f * eps * NU * (16.0f * CU + 5.0f) * sf_rsqrtf(r2) + 2e-6f;
+  ia = fpfh_bin_fast(alpha, lo[0], scale[0], n, m_alpha);
+  ip = fpfh_bin_fast(phi, lo[1], scale[1], n, m_phi);
+  it = fpfh_bin_fast(atan2f(ny, nx), lo[2], scale[2], n, m_theta);
+  return ia != kBinUnsure && ip != kBinUnsure && it != kBinUnsure;
+}
+
+// One pair of the SPFH loop (fpfh.py:47-76): false when the pair is dropped (d == 0), else the three NumPy bins
+// (-1 = outside the feature's range). `e` = float64 edges [3][stride], `scale` = n / (e[n] - e[0]) per feature,
+// lo32 / scale32 their float32 roundings, u32 / U the float32 rounding of u and its norm (per point, by the caller).
+SF_HD bool fpfh_pair_bins(const double rel[3], const double u[3], const float u32[3], float U, const double nj[3], int n,
+                          const double* e, int stride, const double scale[3], const float lo32[3],
+                          const float scale32[3], bool allow_fast, int& ia, int& ip, int& it) {
+  if (allow_fast) {
+    const float rel32[3] = {float(rel[0]), float(rel[1]), float(rel[2])};
+    const float nj32[3] = {float(nj[0]), float(nj[1]), float(nj[2])};
+    if (fpfh_bins_fast(rel32, u32, U, nj32, n, lo32, scale32, ia, ip, it)) return true;
+  }
+  const double d2 = rdist3(rel[0], rel[1], rel[2]);
+  if (!(d2 > 0.0)) return false;
+  double alpha, phi, ny, nx;
+  fpfh_features_raw(rel, sqrt(d2), u, nj, alpha, phi, ny, nx);
+  ia = histogram_bin_scaled(alpha, e, n, scale[0]);
+  ip = histogram_bin_scaled(phi, e + stride, n, scale[1]);
+  it = fpfh_theta_bin(ny, nx, e + 2 * stride, n, scale[2]);
+  return true;
+}
+
 }  // namespace sf

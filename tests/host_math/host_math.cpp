@@ -134,15 +134,25 @@ void hm_spfh_counts(const double* point, const double* normal, const double* nbr
   for (int i = 0; i < k; ++i) {
     const double rel[3] = {nbrs[3 * i] - point[0], nbrs[3 * i + 1] - point[1], nbrs[3 * i + 2] - point[2]};
     const double d2 = rdist3(rel[0], rel[1], rel[2]);
-    if (!(d2 > 0.0)) continue;
-    double alpha, phi, ny, nx;  // as the kernel: reciprocal first guess, float32-filtered theta bin
-    fpfh_features_raw(rel, sqrt(d2), normal, nbr_normals + 3 * i, alpha, phi, ny, nx);
     const double* e[3] = {edges, edges + (n_bins + 1), edges + 2 * (n_bins + 1)};
     double scale[3];
-    for (int f = 0; f < 3; ++f) scale[f] = double(n_bins) / (e[f][n_bins] - e[f][0]);
-    const int ia = histogram_bin_scaled(alpha, e[0], n_bins, scale[0]);
-    const int ip = histogram_bin_scaled(phi, e[1], n_bins, scale[1]);
-    const int it = fpfh_theta_bin(ny, nx, e[2], n_bins, scale[2]);
+    float lo32[3], scale32[3];
+    for (int f = 0; f < 3; ++f) {
+      scale[f] = double(n_bins) / (e[f][n_bins] - e[f][0]);
+      lo32[f] = float(e[f][0]);
+      scale32[f] = float(scale[f]);
+    }
+    // as the kernel: float32-filtered bins, float64 (reciprocal first guess, filtered theta) where unsure
+    const float u32[3] = {float(normal[0]), float(normal[1]), float(normal[2])};
+    const float u_norm = sqrtf(u32[0] * u32[0] + u32[1] * u32[1] + u32[2] * u32[2]);
+    int ia, ip, it;
+    const bool counted = fpfh_pair_bins(rel, normal, u32, u_norm, nbr_normals + 3 * i, n_bins, edges, n_bins + 1, scale,
+                                        lo32, scale32, true, ia, ip, it);
+    if (counted != (d2 > 0.0)) {
+      hist[0] = -2000000;
+      return;
+    }
+    if (!counted) continue;
     {  // the filtered path must give the bins of the plain float64 path
       double a2, p2, theta;
       fpfh_features(rel, sqrt(d2), normal, nbr_normals + 3 * i, a2, p2, theta);
@@ -158,6 +168,50 @@ void hm_spfh_counts(const double* point, const double* normal, const double* nbr
       if (it >= 0) ++hist[2 * n_bins + it];
     } else if (ia >= 0 && ip >= 0 && it >= 0) {
       ++hist[(ia * n_bins + ip) * n_bins + it];
+    }
+  }
+}
+
+// One pair through the float32 filter alone: returns 1 and the three bins when the filter is sure, 0 otherwise.
+int hm_fpfh_bins_fast(const double* rel, const double* u, const double* nj, int n_bins, const double* edges, int* bins) {
+  float lo32[3], scale32[3];
+  for (int f = 0; f < 3; ++f) {
+    const double* e = edges + f * (n_bins + 1);
+    lo32[f] = float(e[0]);
+    scale32[f] = float(double(n_bins) / (e[n_bins] - e[0]));
+  }
+  const float rel32[3] = {float(rel[0]), float(rel[1]), float(rel[2])};
+  const float u32[3] = {float(u[0]), float(u[1]), float(u[2])};
+  const float nj32[3] = {float(nj[0]), float(nj[1]), float(nj[2])};
+  const float u_norm = sqrtf(u32[0] * u32[0] + u32[1] * u32[1] + u32[2] * u32[2]);
+  return fpfh_bins_fast(rel32, u32, u_norm, nj32, n_bins, lo32, scale32, bins[0], bins[1], bins[2]) ? 1 : 0;
+}
+// The same pair through the plain float64 path (np.histogram semantics): bins, or returns 0 when d == 0.
+int hm_fpfh_bins_float64(const double* rel, const double* u, const double* nj, int n_bins, const double* edges, int* bins) {
+  const double d2 = rdist3(rel[0], rel[1], rel[2]);
+  if (!(d2 > 0.0)) return 0;
+  double a, p, theta;
+  fpfh_features(rel, sqrt(d2), u, nj, a, p, theta);
+  bins[0] = histogram_bin(a, edges, n_bins);
+  bins[1] = histogram_bin(p, edges + (n_bins + 1), n_bins);
+  bins[2] = histogram_bin(theta, edges + 2 * (n_bins + 1), n_bins);
+  return 1;
+}
+
+// Batch of pairs: stats[0] = pairs the filter was sure about, stats[1] = of those, pairs whose bins differ from the
+// float64 path's (or that the float64 path drops) — must be 0; first_bad = index of the first such pair or -1.
+void hm_fpfh_fast_check(long n_pairs, const double* rel, const double* u, const double* nj, int n_bins,
+                        const double* edges, long* stats, long* first_bad) {
+  stats[0] = stats[1] = 0;
+  *first_bad = -1;
+  for (long i = 0; i < n_pairs; ++i) {
+    int fast[3], exact[3];
+    if (!hm_fpfh_bins_fast(rel + 3 * i, u + 3 * i, nj + 3 * i, n_bins, edges, fast)) continue;
+    ++stats[0];
+    const int counted = hm_fpfh_bins_float64(rel + 3 * i, u + 3 * i, nj + 3 * i, n_bins, edges, exact);
+    if (!counted || fast[0] != exact[0] || fast[1] != exact[1] || fast[2] != exact[2]) {
+      ++stats[1];
+      if (*first_bad < 0) *first_bad = i;
     }
   }
 }

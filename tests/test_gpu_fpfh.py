@@ -4,6 +4,8 @@ fixtures — 125-d from the unmodified reference, 33-d from the reference with t
 (the unpatched reference raises) — and against the oracle. Bar: <= 1e-4 relative L2 per row.
 """
 
+import os
+
 import numpy as np
 import pytest
 from conftest import edge_case_inputs, golden_pair_inputs, load_golden, rel_l2
@@ -70,6 +72,35 @@ def test_oracle_parity_all_points_are_queries(n_bins, decorrelated):
     _check(got, want, f"oracle/{n_bins}/{'dec' if decorrelated else 'cor'}")
 
 
+@pytest.mark.parametrize("n_bins,decorrelated", [(11, True), (4, False), (10, True)])
+def test_filtered_bins_equal_float64_bins_noisy_normals_and_flat_cloud(n_bins, decorrelated):
+    """SPFH with the float32 filter == SPFH with every pair through float64, bit for bit: a 300k cloud with noisy
+    (and non-unit) normals, and a flat lattice whose alpha is 0 up to rounding (an edge when n_bins is even)."""
+    import torch
+    from shot_fpfh_b200 import ops
+    from shot_fpfh_b200.device import Grid, upload
+
+    rng = np.random.default_rng(12)
+    n = 300_000
+    pts, dirs = synthetic.bumpy_sphere(n, seed=8)
+    normals = (dirs + 0.3 * rng.normal(size=dirs.shape)) * rng.uniform(0.5, 2.0, size=(n, 1))
+    gx, gy = np.meshgrid(np.arange(300.0), np.arange(300.0))
+    flat = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1) * 0.01
+    flat_n = np.tile([0.0, 0.0, 1.0], (flat.shape[0], 1))
+    for cloud, nrm, radius in ((pts, normals, 5.0 * synthetic.mean_spacing(n)), (flat, flat_n, 0.035)):
+        grid = Grid().build(upload(cloud), upload(nrm), radius)
+        offsets, nbr, _, _ = ops.radius_csr(grid, None, radius)
+        fast = ops.spfh(grid, offsets, nbr, n_bins, decorrelated)
+        os.environ["SF_SPFH_EXACT"] = "1"
+        try:
+            exact = ops.spfh(grid, offsets, nbr, n_bins, decorrelated)
+        finally:
+            del os.environ["SF_SPFH_EXACT"]
+        assert torch.equal(fast, exact)
+        assert float(fast.sum()) > 0
+        grid.close()
+
+
 def test_large_size_properties_1m():
     """C3 size: 1M points, every point a query, 33-d. Properties + a spot check against the oracle's formulas."""
     import torch
@@ -91,9 +122,32 @@ def test_large_size_properties_1m():
     # SPFH rows: each of the three 11-bin blocks sums to (#binned)/K <= (K-1)/K
     offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
     spfh_dev = ops.spfh(grid, offsets, nbr, 11, True)
-    # the piecewise entry points (exact CSR, float64 distances) give the fused driver's rows bit for bit
-    assert torch.equal(ops.fpfh(grid, offsets, nbr, dist, spfh_dev, kp, out_dtype=torch.float32), out_dev)
+    # the piecewise entry points (exact CSR, float64 distances) give the fused driver's rows: bit for bit when the
+    # driver gathers per keypoint like they do, to float32 summation order when it stages the rows per cell
+    piecewise = ops.fpfh(grid, offsets, nbr, dist, spfh_dev, kp, out_dtype=torch.float32)
+    assert torch.allclose(piecewise, out_dev, rtol=2e-5, atol=1e-7)
+    os.environ["SF_FPFH_NO_CELLS"] = "1"
+    try:
+        per_keypoint, _ = fpfh_device(grid, kp, radius, 11, True, out_dtype=torch.float32)
+    finally:
+        del os.environ["SF_FPFH_NO_CELLS"]
+    assert torch.equal(piecewise, per_keypoint)
+    # a permuted subset of more than half the points takes the cell-staged path too: same rows
+    sub = torch.randperm(n, device=kp.device)[: (3 * n) // 4]
+    sub_rows, _ = fpfh_device(grid, sub, radius, 11, True, out_dtype=torch.float32)
+    assert torch.equal(sub_rows, out_dev[sub])
+    del piecewise, per_keypoint, sub_rows
     assert abs(mean_k - float(offsets[-1].item()) / n) < 1e-9
+    # the float32-filtered bins (sf_math.cuh::fpfh_bins_fast) == the float64 bins on all 74M pairs x 3 features
+    os.environ["SF_SPFH_EXACT"] = "1"
+    try:
+        spfh_exact = ops.spfh(grid, offsets, nbr, 11, True)
+        spfh125_exact = ops.spfh(grid, offsets, nbr, 5, False)
+    finally:
+        del os.environ["SF_SPFH_EXACT"]
+    assert torch.equal(spfh_exact, spfh_dev)
+    assert torch.equal(spfh125_exact, ops.spfh(grid, offsets, nbr, 5, False))
+    del spfh_exact, spfh125_exact
     spfh = spfh_dev.cpu().numpy()
     blocks = spfh.reshape(n, 3, 11).sum(axis=2)
     assert (blocks <= 1.0 + 1e-6).all() and (blocks[:, 1] > 0.9).all()  # phi is always in range

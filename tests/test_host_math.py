@@ -40,6 +40,8 @@ def hm():
                                        ctypes.POINTER(ctypes.c_float)]
     lib.hm_spfh_counts.argtypes = [DP, DP, DP, DP, ctypes.c_int, ctypes.c_int, ctypes.c_int, DP,
                                    ctypes.POINTER(ctypes.c_int)]
+    lib.hm_fpfh_fast_check.argtypes = [ctypes.c_long, DP, DP, DP, ctypes.c_int, DP, ctypes.POINTER(ctypes.c_long),
+                                       ctypes.POINTER(ctypes.c_long)]
     return lib
 
 
@@ -177,6 +179,62 @@ def test_filtered_theta_bin_equals_float64_bin(hm):
             assert hm.hm_theta_bin(float(y), float(x), _p(e), n_bins) == want, (y, x)
             theta = float(np.arctan2(y, x))
             assert hm.hm_histogram_bin_scaled(theta, _p(e), n_bins) == hm.hm_histogram_bin(theta, _p(e), n_bins)
+
+
+def _unit(v):
+    return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("n_bins", [5, 11, 4, 16])
+def test_float32_filtered_bins_never_disagree_with_float64(hm, n_bins):
+    """sf_math.cuh::fpfh_bins_fast: whenever the float32 filter accepts a pair, its three bins are the float64
+    path's. Random pairs at several scales, non-unit normals, and pairs built to put phi / theta / alpha ON a bin
+    edge or 1e-16 .. 1e-5 away from it (the filter must then either agree or decline)."""
+    rng = np.random.default_rng(21)
+    edges = np.ascontiguousarray(fpfh_oracle.bin_edges(n_bins))
+    rels, us, njs = [], [], []
+    m = 60_000
+    for scale_c, scale_n, spread in ((0.02, 1.0, 0.3), (1.0, 1.0, 3.0), (5.0, 0.5, 0.05), (1e-4, 2.0, 1.0), (0.02, 1.0, 0.0)):
+        u = _unit(rng.normal(size=(m, 3))) * scale_n
+        nj = _unit(u / scale_n + spread * rng.normal(size=(m, 3))) * rng.choice([1.0, scale_n], size=(m, 1))
+        rel = rng.normal(size=(m, 3)) * scale_c
+        rels.append(rel); us.append(u); njs.append(nj)
+    # phi = (rel . u) / |rel| on / next to every edge: rel = cos(phi) u^ + sin(phi) t, u unit
+    for delta in (0.0, 1e-16, 1e-12, 1e-9, 1e-8, 1e-7, 1e-6, 3e-6, 1e-5, -1e-16, -1e-9, -1e-7, -1e-6, -1e-5):
+        for e in edges[1]:
+            k = 200
+            u = _unit(rng.normal(size=(k, 3)))
+            t = _unit(np.cross(u, rng.normal(size=(k, 3))))
+            c = np.clip(e + delta, -1.0, 1.0)
+            rel = (c * u + np.sqrt(max(0.0, 1.0 - c * c)) * t) * 10.0 ** rng.uniform(-3, 0, size=(k, 1))
+            rels.append(rel); us.append(u); njs.append(_unit(u + 0.2 * rng.normal(size=(k, 3))))
+    # theta = atan2(nj . w, nj . u) on / next to every edge: nj = cos(theta) u + sin(theta) w^, w = u x (rel x u)
+    for delta in (0.0, 1e-16, 1e-9, 1e-7, 1e-6, 3e-6, 1e-5, -1e-9, -1e-7, -1e-6, -1e-5):
+        for e in edges[2]:
+            k = 200
+            u = _unit(rng.normal(size=(k, 3)))
+            rel = rng.normal(size=(k, 3))
+            w = np.cross(u, np.cross(rel, u))
+            theta = e + delta
+            # ny = nj . w = sin(theta) |w| s, nx = cos(theta) s  with nj = s (cos(theta) u + sin(theta) w / |w|^2)
+            nj = np.cos(theta) * u + np.sin(theta) * w / np.sum(w * w, axis=1, keepdims=True)
+            rels.append(rel); us.append(u); njs.append(nj)
+    # alpha = (rel x u) . nj == 0 up to rounding (an edge when n_bins is even): nj in the plane of rel and u
+    k = 5000
+    u = _unit(rng.normal(size=(k, 3)))
+    rel = rng.normal(size=(k, 3)) * 0.02
+    nj = _unit(u + rng.uniform(-1, 1, size=(k, 1)) * rel)
+    rels.append(rel); us.append(u); njs.append(nj)
+    # degenerate: zero and denormal offsets, zero normals, huge offsets
+    rels.append(np.array([[0.0, 0.0, 0.0], [1e-200, 0.0, 0.0], [1e-20, 1e-20, 0.0], [1e20, 0.0, 0.0], [0.1, 0.0, 0.0]]))
+    us.append(np.array([[0.0, 0.0, 1.0]] * 4 + [[0.0, 0.0, 0.0]]))
+    njs.append(np.array([[0.0, 0.0, 1.0]] * 3 + [[0.0, 1.0, 0.0], [0.0, 0.0, 0.0]]))
+    rel, u, nj = (np.ascontiguousarray(np.concatenate(a)) for a in (rels, us, njs))
+    stats = (ctypes.c_long * 2)()
+    first_bad = ctypes.c_long(-1)
+    hm.hm_fpfh_fast_check(rel.shape[0], _p(rel), _p(u), _p(nj), n_bins, _p(edges), stats, ctypes.byref(first_bad))
+    assert stats[1] == 0, (first_bad.value, rel[first_bad.value], u[first_bad.value], nj[first_bad.value])
+    assert stats[0] > 0.7 * 5 * m  # and the filter decides the generic pairs (alpha == 0 is an edge when n_bins is even)
 
 
 @pytest.mark.parametrize("n_bins,decorrelated", [(5, False), (11, True), (11, False)])
