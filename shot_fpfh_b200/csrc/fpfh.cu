@@ -18,7 +18,8 @@ __constant__ float c_lo32[3], c_scale32[3];  // float32 roundings of the first e
 __global__ void __launch_bounds__(256, 4)
     spfh_kernel(GridView g, int64_t first, int64_t count, const int64_t* __restrict__ offsets,
                 const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr, int n_bins, int decorrelated,
-                int width, int allow_fast, float* __restrict__ spfh) {
+                int width, int stride, int allow_fast, float* __restrict__ spfh) {
+  // stride >= width: floats between consecutive rows (the fused driver pads rows to 16 bytes; the pad holds zeros)
   // allow_fast: bins from the float32-filtered features (sf_math.cuh::fpfh_bins_fast), float64 where unsure
   // counts == nullptr: CSR rows [offsets[s], offsets[s+1]); otherwise padded rows [offsets[s], offsets[s] + counts[s])
   extern __shared__ int hist_mem[];
@@ -59,8 +60,8 @@ __global__ void __launch_bounds__(256, 4)
     // is formed in float32 (two roundings, 1.2e-7 relative, against the 1e-4 bar) instead of a float64 division
     // per bin.
     const float inv_k = end > begin ? 1.0f / float(end - begin) : 0.0f;
-    float* row = spfh + s * int64_t(width);
-    for (int b = lane; b < width; b += 32) row[b] = float(hist[b]) * inv_k;
+    float* row = spfh + s * int64_t(stride);
+    for (int b = lane; b < stride; b += 32) row[b] = b < width ? float(hist[b]) * inv_k : 0.0f;
     __syncwarp();
   }
 }
@@ -279,13 +280,81 @@ __global__ void __launch_bounds__(256)
 }
 
 
+
+// The fused driver's FPFH stage: SPFH rows padded to a multiple of four floats (16-byte aligned), L = stride / 4
+// lanes per row, each loading one float4, so that ONE load instruction of the warp fetches the rows of
+// G = 32 / L neighbours (33 bins: L = 9, three neighbours per instruction; fpfh_kernel spends a load, two shuffles
+// and the address arithmetic on every single neighbour and was issue-bound). Lane l serves neighbour slot l / L and
+// columns 4 (l % L) .. 4 (l % L) + 3; the G partial sums of a column are added at the end. Rows of up to 128 bins.
+template <int L, typename OutT>
+__global__ void __launch_bounds__(256)
+    fpfh_rows4_kernel(const int32_t* __restrict__ inv_perm, const int64_t* __restrict__ offsets,
+                      const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr,
+                      const float* __restrict__ weights, const float4* __restrict__ spfh4, int width,
+                      const int64_t* __restrict__ keypoints, const int32_t* __restrict__ order, int64_t nq,
+                      OutT* __restrict__ out) {
+  constexpr int G = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (slot >= nq) return;
+  const int64_t q = order ? order[slot] : slot;
+  const int64_t s = inv_perm[keypoints[q]];
+  const int64_t begin = offsets[s];
+  const int cnt = counts[s];
+  const int grp = lane / L, sub = lane - grp * L;
+  const bool serving = grp < G;
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int base = 0; base < cnt; base += 32) {
+    const int i = base + lane;
+    int my_j = 0;
+    float my_w = 0.0f;  // 0 beyond the list and for the point itself (d == 0): contributes nothing
+    if (i < cnt) {
+      my_j = __ldg(nbr + begin + i);
+      my_w = __ldg(weights + begin + i);
+    }
+    const int left = cnt - base < 32 ? cnt - base : 32;
+    const int steps = (left + G - 1) / G;
+#pragma unroll 4
+    for (int t = 0; t < steps; ++t) {
+      const int src = t * G + grp;
+      const int j = __shfl_sync(kFull, my_j, src & 31);
+      const float w = __shfl_sync(kFull, my_w, src & 31);
+      if (serving && src < 32) {
+        const float4 x = __ldg(spfh4 + int64_t(j) * L + sub);
+        acc.x = fmaf(x.x, w, acc.x);
+        acc.y = fmaf(x.y, w, acc.y);
+        acc.z = fmaf(x.z, w, acc.z);
+        acc.w = fmaf(x.w, w, acc.w);
+      }
+    }
+  }
+  const float4 part = acc;  // lanes sub + gi * L hold the other partial sums of column block `sub` (read unmodified:
+                            // a shuffle from beyond lane 31 returns the caller's own value)
+#pragma unroll
+  for (int gi = 1; gi < G; ++gi) {
+    acc.x += __shfl_down_sync(kFull, part.x, gi * L);
+    acc.y += __shfl_down_sync(kFull, part.y, gi * L);
+    acc.z += __shfl_down_sync(kFull, part.z, gi * L);
+    acc.w += __shfl_down_sync(kFull, part.w, gi * L);
+  }
+  if (lane < L) {  // fpfh.py:115: spfh[i] + sum / K, K counting the point itself
+    const float k_all = float(cnt);
+    const float4 own = __ldg(spfh4 + s * L + lane);
+    const float v[4] = {own.x + acc.x / k_all, own.y + acc.y / k_all, own.z + acc.z / k_all, own.w + acc.w / k_all};
+    OutT* dst = out + q * int64_t(width) + 4 * lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (4 * lane + c < width) dst[c] = OutT(cnt > 0 ? v[c] : 0.0f);
+  }
+}
+
 }  // namespace sf
 
 using namespace sf;
 
 static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* offsets, const int32_t* counts,
                        const int32_t* nbr, int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh,
-                       cudaStream_t stream) {
+                       int stride, cudaStream_t stream) {
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_spfh: grid built without normals");
   SF_REQUIRE(offsets && nbr && edges_host && spfh, SF_ERR_ARG, "sf_spfh: null argument");
   SF_REQUIRE(first >= 0 && count >= 0 && first + count <= g->n, SF_ERR_ARG, "sf_spfh: point range outside the cloud");
@@ -320,21 +389,22 @@ static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
   const int64_t blocks_needed = (count + warps - 1) / warps;
   const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
   spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, counts, nbr, n_bins, decorrelated,
-                                                    width, allow_fast, spfh);
+                                                    width, stride > 0 ? stride : width, allow_fast, spfh);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
 
 extern "C" int sf_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* offsets, const int32_t* nbr,
                        int32_t n_bins, int32_t decorrelated, const double* edges_host, float* spfh, void* stream_) {
-  return launch_spfh(g, first, count, offsets, nullptr, nbr, n_bins, decorrelated, edges_host, spfh,
+  return launch_spfh(g, first, count, offsets, nullptr, nbr, n_bins, decorrelated, edges_host, spfh, 0,
                      static_cast<cudaStream_t>(stream_));
 }
 
 template <typename OutT>
 static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts, const int32_t* nbr, const double* dist,
-                       const float* weights, int by_kp, const float* spfh, int width, const int64_t* keypoints,
-                       int64_t nq, OutT* out, cudaStream_t stream) {
+                       const float* weights, int by_kp, const float* spfh, int width, int stride, int rows4,
+                       const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
+  // rows4: the fused driver's rows, `stride` a multiple of four floats (at most 128) -> fpfh_rows4_kernel
   const int64_t threads = nq * 32;
   const unsigned blocks = unsigned((threads + 255) / 256);
   // processing order: keypoints by cell-sorted position (see fpfh_kernel); not worth a sort for a handful
@@ -353,6 +423,26 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts
     keypoint_position_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(g->inv_perm, keypoints, nq, pos, ids);
     SF_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, sort_bytes, pos, pos_sorted, ids, order, int(nq), 0, end_bit,
                                             stream));
+  }
+  if (rows4) {
+    const float4* spfh4 = reinterpret_cast<const float4*>(spfh);
+#define SF_LAUNCH_ROWS4(LL) \
+  case LL: fpfh_rows4_kernel<LL, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, weights, spfh4, width, keypoints, order, nq, out); break;
+    switch (stride / 4) {
+      SF_LAUNCH_ROWS4(1) SF_LAUNCH_ROWS4(2) SF_LAUNCH_ROWS4(3) SF_LAUNCH_ROWS4(4) SF_LAUNCH_ROWS4(5) SF_LAUNCH_ROWS4(6)
+      SF_LAUNCH_ROWS4(7) SF_LAUNCH_ROWS4(8) SF_LAUNCH_ROWS4(9) SF_LAUNCH_ROWS4(10) SF_LAUNCH_ROWS4(11) SF_LAUNCH_ROWS4(12)
+      SF_LAUNCH_ROWS4(13) SF_LAUNCH_ROWS4(14) SF_LAUNCH_ROWS4(15) SF_LAUNCH_ROWS4(16) SF_LAUNCH_ROWS4(17) SF_LAUNCH_ROWS4(18)
+      SF_LAUNCH_ROWS4(19) SF_LAUNCH_ROWS4(20) SF_LAUNCH_ROWS4(21) SF_LAUNCH_ROWS4(22) SF_LAUNCH_ROWS4(23) SF_LAUNCH_ROWS4(24)
+      SF_LAUNCH_ROWS4(25) SF_LAUNCH_ROWS4(26) SF_LAUNCH_ROWS4(27) SF_LAUNCH_ROWS4(28) SF_LAUNCH_ROWS4(29) SF_LAUNCH_ROWS4(30)
+      SF_LAUNCH_ROWS4(31) SF_LAUNCH_ROWS4(32)
+      default: set_error("fpfh: padded stride %d unsupported", stride); return SF_ERR_ARG;
+    }
+#undef SF_LAUNCH_ROWS4
+    void* to_free4[] = {pos, ids, pos_sorted, order, sort_temp};
+    for (void* p : to_free4)
+      if (p) cudaFreeAsync(p, stream);
+    SF_CUDA(cudaGetLastError());
+    return SF_OK;
   }
   // Passes of up to 4 column blocks of 32 bins (register tiles). A final partial block is masked, except when it
   // is at most 4 columns wide and follows a full block (the 33-bin layout): then it rides along as the "tail".
@@ -391,10 +481,10 @@ extern "C" int sf_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_fpfh: grid not built");
   SF_REQUIRE(offsets && nbr && dist && spfh && keypoints && out && width > 0, SF_ERR_ARG, "sf_fpfh: null argument");
   if (nq == 0) return SF_OK;
-  return out_is_f64 ? launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, keypoints, nq,
-                                  static_cast<double*>(out), stream)
-                    : launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, keypoints, nq,
-                                  static_cast<float*>(out), stream);
+  return out_is_f64 ? launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, width, 0, keypoints,
+                                  nq, static_cast<double*>(out), stream)
+                    : launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, width, 0, keypoints,
+                                  nq, static_cast<float*>(out), stream);
 }
 
 // Fused driver: what compute_fpfh_descriptor (fpfh.py:16-117) does for one cloud — search around EVERY cloud point,
@@ -425,7 +515,12 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&counts), size_t(n) * 4, stream));
   SF_CUDA(scratch_alloc(&scan_temp, scan_bytes + 16, stream));
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pair_counter), 8, stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&spfh), size_t(n) * width * sizeof(float), stream));
+  // rows of up to 128 bins are padded to a multiple of four floats for fpfh_rows4_kernel (SF_FPFH_NO_ROWS4=1:
+  // measurement / test switch back to the per-neighbour gather of fpfh_kernel)
+  const char* no_rows4 = getenv("SF_FPFH_NO_ROWS4");
+  const int rows4 = (width <= 128 && !(no_rows4 != nullptr && no_rows4[0] == '1')) ? 1 : 0;
+  const int stride = rows4 ? (width + 3) / 4 * 4 : width;
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&spfh), size_t(n) * stride * sizeof(float), stream));
   SF_CUDA(cudaMemsetAsync(cand + n, 0, 8, stream));
   SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
   const GridView view = g->view();
@@ -450,13 +545,13 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
   }
   SF_CUDA(cudaGetLastError());
   profile_mark(1, stream);
-  int rc = launch_spfh(g, 0, n, cand_offsets, counts, nbr, n_bins, decorrelated, edges_host, spfh, stream);
+  int rc = launch_spfh(g, 0, n, cand_offsets, counts, nbr, n_bins, decorrelated, edges_host, spfh, stride, stream);
   profile_mark(2, stream);
   if (rc == SF_OK && nq > 0)
-    rc = out_is_f64 ? launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, keypoints, nq,
-                                  static_cast<double*>(out), stream)
-                    : launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, keypoints, nq,
-                                  static_cast<float*>(out), stream);
+    rc = out_is_f64 ? launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, stride, rows4, keypoints,
+                                  nq, static_cast<double*>(out), stream)
+                    : launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, stride, rows4, keypoints,
+                                  nq, static_cast<float*>(out), stream);
   profile_mark(3, stream);
   if (rc == SF_OK && pairs_host != nullptr) {
     unsigned long long pairs = 0;

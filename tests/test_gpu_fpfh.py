@@ -123,16 +123,16 @@ def test_large_size_properties_1m():
     offsets, nbr, _, dist = ops.radius_csr(grid, None, radius, want_dist=True)
     spfh_dev = ops.spfh(grid, offsets, nbr, 11, True)
     # the piecewise entry points (exact CSR, float64 distances) give the fused driver's rows: bit for bit when the
-    # driver gathers per keypoint like they do, to float32 summation order when it stages the rows per cell
+    # driver gathers per neighbour like they do, to float32 summation order with its float4-row kernel
     piecewise = ops.fpfh(grid, offsets, nbr, dist, spfh_dev, kp, out_dtype=torch.float32)
     assert torch.allclose(piecewise, out_dev, rtol=2e-5, atol=1e-7)
-    os.environ["SF_FPFH_NO_CELLS"] = "1"
+    os.environ["SF_FPFH_NO_ROWS4"] = "1"
     try:
         per_keypoint, _ = fpfh_device(grid, kp, radius, 11, True, out_dtype=torch.float32)
     finally:
-        del os.environ["SF_FPFH_NO_CELLS"]
+        del os.environ["SF_FPFH_NO_ROWS4"]
     assert torch.equal(piecewise, per_keypoint)
-    # a permuted subset of more than half the points takes the cell-staged path too: same rows
+    # a permuted subset of the points: same rows
     sub = torch.randperm(n, device=kp.device)[: (3 * n) // 4]
     sub_rows, _ = fpfh_device(grid, sub, radius, 11, True, out_dtype=torch.float32)
     assert torch.equal(sub_rows, out_dev[sub])
