@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ weights, const float4* __restrict__ spfh4, int width,
                       const int64_t* __restrict__ keypoints, const int32_t* __restrict__ order, int64_t nq,
                       OutT* __restrict__ out) {
-  constexpr int G = 32 / L;
+  constexpr int G = 32 / L, kSteps = (32 + G - 1) / G;
   const int lane = threadIdx.x & 31;
   const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (slot >= nq) return;
@@ -301,9 +301,25 @@ __global__ void __launch_bounds__(256)
   const int64_t s = inv_perm[keypoints[q]];
   const int64_t begin = offsets[s];
   const int cnt = counts[s];
-  const int grp = lane / L, sub = lane - grp * L;
-  const bool serving = grp < G;
+  // lanes beyond G * L ride along with the last slot (their loads hit sectors that slot fetches anyway) and their
+  // sums are never read: no predication inside the loop
+  const int grp = lane / L < G ? lane / L : G - 1;
+  const int sub = lane - (lane / L) * L;
+  const float4* col = spfh4 + sub;
   float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  // one step: the G slots fetch the rows of neighbours src = t * G + slot of this batch of 32 list entries
+#define SF_ROWS4_STEP(t, guard)                                             \
+  {                                                                         \
+    const int src = (t) * G + grp;                                          \
+    const int j = __shfl_sync(kFull, my_j, src);                            \
+    float w = __shfl_sync(kFull, my_w, src);                                \
+    if (guard) w = src < 32 ? w : 0.0f; /* the shuffle wraps beyond 31 */   \
+    const float4 x = __ldg(col + int64_t(j) * L);                           \
+    acc.x = fmaf(x.x, w, acc.x);                                            \
+    acc.y = fmaf(x.y, w, acc.y);                                            \
+    acc.z = fmaf(x.z, w, acc.z);                                            \
+    acc.w = fmaf(x.w, w, acc.w);                                            \
+  }
   for (int base = 0; base < cnt; base += 32) {
     const int i = base + lane;
     int my_j = 0;
@@ -312,22 +328,17 @@ __global__ void __launch_bounds__(256)
       my_j = __ldg(nbr + begin + i);
       my_w = __ldg(weights + begin + i);
     }
-    const int left = cnt - base < 32 ? cnt - base : 32;
-    const int steps = (left + G - 1) / G;
-#pragma unroll 4
-    for (int t = 0; t < steps; ++t) {
-      const int src = t * G + grp;
-      const int j = __shfl_sync(kFull, my_j, src & 31);
-      const float w = __shfl_sync(kFull, my_w, src & 31);
-      if (serving && src < 32) {
-        const float4 x = __ldg(spfh4 + int64_t(j) * L + sub);
-        acc.x = fmaf(x.x, w, acc.x);
-        acc.y = fmaf(x.y, w, acc.y);
-        acc.z = fmaf(x.z, w, acc.z);
-        acc.w = fmaf(x.w, w, acc.w);
-      }
+    const int left = cnt - base;
+    if (left >= 32) {
+#pragma unroll
+      for (int t = 0; t < kSteps; ++t) SF_ROWS4_STEP(t, G * kSteps > 32 && t == kSteps - 1)
+    } else {
+      const int steps = (left + G - 1) / G;  // entries beyond `left` carry weight 0
+#pragma unroll 2
+      for (int t = 0; t < steps; ++t) SF_ROWS4_STEP(t, G * kSteps > 32)
     }
   }
+#undef SF_ROWS4_STEP
   const float4 part = acc;  // lanes sub + gi * L hold the other partial sums of column block `sub` (read unmodified:
                             // a shuffle from beyond lane 31 returns the caller's own value)
 #pragma unroll
