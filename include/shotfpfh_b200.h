@@ -231,6 +231,10 @@ int sf_rows_compact_fill(const float* dense_dev, int64_t n_rows, int32_t width, 
  * everything started has finished and reports a malformed input. The buffers must stay valid until then. */
 int sf_host_expand_rows_begin(const int64_t* offsets_host, const uint16_t* cols_host, const float* vals_host,
                               int64_t n_rows, int32_t width, double* dst_host, int32_t threads);
+/* dst[i] = (double)src[i] for i in [0, n) by the same pool (started, not awaited: the float32 rows of one block are
+ * widened into the float64 result the reference API returns while the next block crosses PCIe; a float32 D2H copy
+ * plus this costs less than copying float64). Jobs run in the order they were started; sf_host_wait awaits all. */
+int sf_host_widen_begin(const float* src_host, int64_t n, double* dst_host, int32_t threads);
 int sf_host_wait(void);
 
 #ifdef __cplusplus

@@ -147,6 +147,20 @@ bool expand_rows(const int64_t* offsets, const uint16_t* cols, const float* vals
   return true;
 }
 
+// dst[i] = double(src[i]) (exact), streamed out with non-temporal stores: the float64 array is written once and not
+// read back by these threads.
+__attribute__((target("avx2"))) void widen_avx2(const float* src, double* dst, int64_t n) {
+  int64_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31u)) { dst[i] = double(src[i]); ++i; }
+  for (; i + 8 <= n; i += 8) {
+    const __m256 v = _mm256_loadu_ps(src + i);
+    _mm256_stream_pd(dst + i, _mm256_cvtps_pd(_mm256_castps256_ps128(v)));
+    _mm256_stream_pd(dst + i + 4, _mm256_cvtps_pd(_mm256_extractf128_ps(v, 1)));
+  }
+  for (; i < n; ++i) dst[i] = double(src[i]);
+  _mm_sfence();
+}
+
 // part p of `parts` of [0, n), cut on multiples of `quantum`
 void share(int64_t n, int p, int parts, int64_t quantum, int64_t& lo, int64_t& hi) {
   const int64_t per = ((n + parts - 1) / parts + quantum - 1) / quantum * quantum;
@@ -175,6 +189,26 @@ extern "C" int sf_host_expand_rows_begin(const int64_t* offsets, const uint16_t*
     int64_t lo, hi;
     share(n_rows, p, parts, 1, lo, hi);
     if (hi > lo && !expand_rows(offsets, cols, vals, width, dst, lo, hi, avx2)) g_job_failed.store(1);
+  });
+  return SF_OK;
+}
+
+extern "C" int sf_host_widen_begin(const float* src, int64_t n, double* dst, int32_t threads) {
+  if (n < 0 || (n > 0 && (src == nullptr || dst == nullptr))) {
+    sf::set_error("sf_host_widen_begin: bad arguments");
+    return SF_ERR_ARG;
+  }
+  if (n == 0) return SF_OK;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  Pool& pool = pool_for(clamp_threads(threads));
+  const int parts = int(std::max<int64_t>(1, std::min<int64_t>(std::min(clamp_threads(threads), pool.workers()), n / 4096)));
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  pool.start(parts, [=](int p) {  // waits for the previous job first
+    int64_t lo, hi;
+    share(n, p, parts, 16, lo, hi);
+    if (hi <= lo) return;
+    if (avx2) widen_avx2(src + lo, dst + lo, hi - lo);
+    else for (int64_t i = lo; i < hi; ++i) dst[i] = double(src[i]);
   });
   return SF_OK;
 }

@@ -17,7 +17,7 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import Grid, download, upload
+from ..device import Grid, download_widened, upload
 
 
 def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
@@ -54,10 +54,13 @@ def compute_fpfh_descriptor(
         if lowest < 0:  # NumPy's negative indexing, as `cloud_points[keypoints_indices]` would resolve it
             kp = np.where(kp < 0, kp + cloud_points.shape[0], kp)
     grid = _cached_grid().build(pts, nrm, radius)
-    out, mean_k = fpfh_device(grid, upload(kp, torch.int64), float(radius), int(n_bins), bool(decorrelated))
+    # float32 rows on the device (the kernels' values), widened exactly to the float64 array the reference returns
+    # by host threads while the rows cross PCIe
+    out, mean_k = fpfh_device(grid, upload(kp, torch.int64), float(radius), int(n_bins), bool(decorrelated),
+                              out_dtype=torch.float32)
     if verbose:
         logging.info(f"Mean neighborhood size over the whole point cloud: {mean_k:.2f}")
-    return download(out)
+    return download_widened(out)
 
 
 _GRIDS: dict[int, Grid] = {}

@@ -72,6 +72,40 @@ def host_threads(requested: int | None = None) -> int:
     return max(1, min(share, 8 if requested is None else int(requested)))
 
 
+def download_widened(t: torch.Tensor, threads: int | None = None, blocks: int = 4) -> np.ndarray:
+    """
+    float32 device tensor -> fresh float64 host array holding the same values (float64(float32 x) is exact): the
+    array a float64 kernel output + `download` would deliver, for half the PCIe bytes. The tensor crosses in
+    `blocks` pieces through page-locked float32 staging; the library's host threads (csrc/host_io.cpp) widen piece
+    b into the result while piece b + 1 is in flight.
+    """
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    n = t.numel()
+    result = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)  # cached page-locked block (see `download`)
+    if n == 0:
+        return result.numpy()
+    staging = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    flat = t.reshape(-1)
+    blocks = max(1, min(int(blocks), n // (1 << 20)))
+    bounds = [n * b // blocks for b in range(blocks + 1)]
+    stream = torch.cuda.current_stream()
+    events = []
+    for b in range(blocks):  # all the copies are queued at once; the host follows them event by event
+        staging[bounds[b]:bounds[b + 1]].copy_(flat[bounds[b]:bounds[b + 1]], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        events.append(ev)
+    n_threads = host_threads(threads)
+    try:
+        for b in range(blocks):
+            events[b].synchronize()
+            check(lib.sf_host_widen_begin(staging.data_ptr() + 4 * bounds[b], bounds[b + 1] - bounds[b],
+                                          result.data_ptr() + 8 * bounds[b], n_threads))
+    finally:
+        check(lib.sf_host_wait())  # the staging buffer is read by the pool until here
+    return result.numpy()
+
+
 class SparseRowsDownload:
     """
     Dense float32 device rows that are mostly zeros (SHOT: ~86 %) -> the dense float64 host array the reference API

@@ -101,6 +101,18 @@ def test_filtered_bins_equal_float64_bins_noisy_normals_and_flat_cloud(n_bins, d
         grid.close()
 
 
+def test_widened_download_equals_a_float64_copy():
+    """device.download_widened: float32 rows -> float64 host array == rows.double().cpu(), any shape / size."""
+    import torch
+    from shot_fpfh_b200.device import download_widened
+
+    for shape in ((0, 33), (1, 33), (777, 125), (300_001, 33), (5_000_000,)):
+        rows = torch.randn(shape, device="cuda", dtype=torch.float32)
+        got = download_widened(rows)
+        assert got.dtype == np.float64 and got.shape == tuple(shape)
+        assert np.array_equal(got, rows.double().cpu().numpy())
+
+
 def test_large_size_properties_1m():
     """C3 size: 1M points, every point a query, 33-d. Properties + a spot check against the oracle's formulas."""
     import torch
