@@ -66,6 +66,95 @@ __global__ void __launch_bounds__(256, 4)
   }
 }
 
+// SPFH by TILES of 32 consecutive cell-sorted points, one warp per tile: the tile's neighbour pairs (about 2 400 at
+// C3) are flattened and dealt to the lanes 32 at a time, whatever point they belong to. Against one warp per point
+// (spfh_kernel: K = 74 pairs in three rounds of 32 lanes, i.e. 77 % of the lanes busy, plus a prologue / epilogue of
+// ~360 instructions per point for 780 of pair arithmetic) every round but the tile's last is full and the per-point
+// work (coordinates, normal, clearing and writing the histogram) is done once per tile with all lanes. The owners'
+// data and the 32 integer histograms live in shared memory. Rows of up to 128 bins; wider rows use spfh_kernel.
+constexpr int kSpfhTileWarps = 4;
+struct SpfhTile {  // per warp
+  double px[32], py[32], pz[32], ux[32], uy[32], uz[32];
+  float4 u32[32];  // float32 rounding of the normal, .w = its norm
+  int64_t cursor[32];
+  int prefix[33];
+  float inv_k[32];
+};
+
+__global__ void __launch_bounds__(kSpfhTileWarps * 32, 8)
+    spfh_tile_kernel(GridView g, int64_t first, int64_t count, const int64_t* __restrict__ offsets,
+                     const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr, int n_bins, int decorrelated,
+                     int width, int stride, int allow_fast, float* __restrict__ spfh) {
+  extern __shared__ unsigned char tile_mem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const size_t per_warp = sizeof(SpfhTile) + size_t(32) * width * sizeof(int);
+  SpfhTile& st = *reinterpret_cast<SpfhTile*>(tile_mem + warp * per_warp);
+  int* hist = reinterpret_cast<int*>(tile_mem + warp * per_warp + sizeof(SpfhTile));
+  const int64_t tiles = (count + 31) / 32;
+  const int64_t warps_total = int64_t(gridDim.x) * kSpfhTileWarps;
+  for (int64_t tile = blockIdx.x * int64_t(kSpfhTileWarps) + warp; tile < tiles; tile += warps_total) {
+    const int64_t s0 = tile * 32;
+    const int in_tile = int(count - s0 < 32 ? count - s0 : 32);
+    int cnt = 0;
+    if (lane < in_tile) {
+      const double4 p = load_pt(g.pts + first + s0 + lane);
+      const double4 un = load_pt(g.nrm + first + s0 + lane);
+      st.px[lane] = p.x; st.py[lane] = p.y; st.pz[lane] = p.z;
+      st.ux[lane] = un.x; st.uy[lane] = un.y; st.uz[lane] = un.z;
+      const float fx = float(un.x), fy = float(un.y), fz = float(un.z);
+      st.u32[lane] = make_float4(fx, fy, fz, sqrtf(fx * fx + fy * fy + fz * fz));
+      const int64_t begin = offsets[s0 + lane];
+      cnt = counts ? counts[s0 + lane] : int(offsets[s0 + lane + 1] - begin);
+      st.cursor[lane] = begin;
+      // hist / K (fpfh.py:79: K counts the point itself and duplicates); float32 quotient, see spfh_kernel
+      st.inv_k[lane] = cnt > 0 ? 1.0f / float(cnt) : 0.0f;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    st.prefix[lane + 1] = incl;
+    if (lane == 0) st.prefix[0] = 0;
+    const int total = __shfl_sync(kFull, incl, 31);
+    for (int b = lane; b < in_tile * width; b += 32) hist[b] = 0;
+    __syncwarp();
+    int owner = 0;
+    for (int idx = lane; idx < total; idx += 32) {
+      while (idx >= st.prefix[owner + 1]) ++owner;  // idx < total = prefix[32]: stops at an owner with pairs
+      const int j = __ldg(nbr + st.cursor[owner] + (idx - st.prefix[owner]));
+      const double4 pj = load_pt(g.pts + j);
+      const double4 nj4 = load_pt(g.nrm + j);
+      const double rel[3] = {pj.x - st.px[owner], pj.y - st.py[owner], pj.z - st.pz[owner]};
+      const double u[3] = {st.ux[owner], st.uy[owner], st.uz[owner]};
+      const double nj[3] = {nj4.x, nj4.y, nj4.z};
+      const float4 uf = st.u32[owner];
+      const float u32[3] = {uf.x, uf.y, uf.z};
+      int ia, ip, it;
+      if (fpfh_pair_bins(rel, u, u32, uf.w, nj, n_bins, &c_edges[0][0], kMaxBins + 1, c_scale, c_lo32, c_scale32,
+                         allow_fast != 0, ia, ip, it)) {
+        int* h = hist + owner * width;
+        if (decorrelated) {  // three independent np.histogram calls: each feature dropped on its own
+          if (ia >= 0) atomicAdd(h + ia, 1);
+          if (ip >= 0) atomicAdd(h + n_bins + ip, 1);
+          if (it >= 0) atomicAdd(h + 2 * n_bins + it, 1);
+        } else if (ia >= 0 && ip >= 0 && it >= 0) {  // np.histogramdd: dropped when any coordinate is outside
+          atomicAdd(h + (ia * n_bins + ip) * n_bins + it, 1);
+        }
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < in_tile; ++r) {
+      float* row = spfh + (s0 + r) * int64_t(stride);
+      const float inv_k = st.inv_k[r];
+      for (int b = lane; b < stride; b += 32) row[b] = b < width ? float(hist[r * width + b]) * inv_k : 0.0f;
+    }
+    __syncwarp();  // the tables are rewritten by the next tile
+  }
+}
+
 // Fused driver, stage 0: ONE scan of the candidate cells of every cloud point (cell-sorted order) writes the
 // neighbours into a PADDED list (slots sized by the candidate count, a cell_start lookup — no counting pass over
 // the candidates), the float32 weights 1/d that stage 2 needs (fpfh.py:112-114; 0 where d == 0) and the counts.
@@ -392,15 +481,27 @@ static int launch_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
   const char* exact_env = getenv("SF_SPFH_EXACT");
   const int allow_fast = (exact_env != nullptr && exact_env[0] == '1') ? 0 : 1;
   SF_CUDA(cudaStreamSynchronize(stream));  // `edges` is a stack buffer
-  int warps = 8;
-  while (warps > 1 && size_t(warps) * width * sizeof(int) > 64 * 1024) warps >>= 1;
-  const size_t smem = size_t(warps) * width * sizeof(int);
-  if (smem > 48 * 1024)
-    SF_CUDA(cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int64_t blocks_needed = (count + warps - 1) / warps;
-  const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
-  spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, counts, nbr, n_bins, decorrelated,
-                                                    width, stride > 0 ? stride : width, allow_fast, spfh);
+  const int row_stride = stride > 0 ? stride : width;
+  const char* no_tiles = getenv("SF_SPFH_NO_TILES");  // measurement / test switch
+  if (width <= 128 && !(no_tiles != nullptr && no_tiles[0] == '1')) {
+    const size_t smem = size_t(kSpfhTileWarps) * (sizeof(SpfhTile) + size_t(32) * width * sizeof(int));
+    if (smem > 48 * 1024)
+      SF_CUDA(cudaFuncSetAttribute(spfh_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int64_t blocks_needed = ((count + 31) / 32 + kSpfhTileWarps - 1) / kSpfhTileWarps;
+    const unsigned blocks = unsigned(blocks_needed < 148 * 16 ? blocks_needed : 148 * 16);
+    spfh_tile_kernel<<<blocks, kSpfhTileWarps * 32, smem, stream>>>(g->view(), first, count, offsets, counts, nbr, n_bins,
+                                                                    decorrelated, width, row_stride, allow_fast, spfh);
+  } else {
+    int warps = 8;
+    while (warps > 1 && size_t(warps) * width * sizeof(int) > 64 * 1024) warps >>= 1;
+    const size_t smem = size_t(warps) * width * sizeof(int);
+    if (smem > 48 * 1024)
+      SF_CUDA(cudaFuncSetAttribute(spfh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int64_t blocks_needed = (count + warps - 1) / warps;
+    const unsigned blocks = unsigned(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
+    spfh_kernel<<<blocks, warps * 32, smem, stream>>>(g->view(), first, count, offsets, counts, nbr, n_bins, decorrelated,
+                                                      width, row_stride, allow_fast, spfh);
+  }
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

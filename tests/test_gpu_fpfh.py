@@ -98,6 +98,17 @@ def test_filtered_bins_equal_float64_bins_noisy_normals_and_flat_cloud(n_bins, d
             del os.environ["SF_SPFH_EXACT"]
         assert torch.equal(fast, exact)
         assert float(fast.sum()) > 0
+        # the warp-per-tile kernel (flattened pairs) == the warp-per-point kernel, also on a sub-range of the cloud
+        os.environ["SF_SPFH_NO_TILES"] = "1"
+        try:
+            per_point = ops.spfh(grid, offsets, nbr, n_bins, decorrelated)
+        finally:
+            del os.environ["SF_SPFH_NO_TILES"]
+        assert torch.equal(fast, per_point)
+        lo, cnt = 1000, 70_001
+        sub_offsets = (offsets[lo : lo + cnt + 1] - offsets[lo]).contiguous()
+        sub_nbr = nbr[int(offsets[lo]) : int(offsets[lo + cnt])].contiguous()
+        assert torch.equal(ops.spfh(grid, sub_offsets, sub_nbr, n_bins, decorrelated, self_range=(lo, cnt)), fast[lo : lo + cnt])
         grid.close()
 
 
