@@ -48,6 +48,8 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--skip-extra", action="store_true", help="only the headline SHOT workload")
+    p.add_argument("--multi-extra", action="store_true",
+                   help="N > 1: also time the sharded FPFH and matching paths (the ones with an all-gather)")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     return p.parse_args()
 
@@ -548,6 +550,55 @@ def bench_match(args, pk, q: int = 200_000):
     }
 
 
+def bench_distributed(args, dist, rank, world):
+    """
+    N > 1 only: the two sharded paths that DO exchange data, strong scaling of one job over the ranks,
+    through `shot_fpfh_b200.distributed` with host arrays in: FPFH C3 (SPFH by blocks of the cell-sorted cloud, ONE
+    all-gather of the SPFH rows over NVLink, FPFH by keypoint blocks) and matching (target set sharded, every rank
+    emits its exact nearest / second nearest, ONE all-gather of a (Q, 3) float64 tensor, merge). Wall clock between
+    barriers, max over ranks, best of 3.
+    """
+    import torch
+
+    from shot_fpfh_b200 import distributed, synthetic
+
+    out = {}
+    pts, normals = synthetic.bumpy_sphere(N_POINTS, seed=0)
+    radius = RADIUS_IN_SPACINGS * synthetic.mean_spacing(N_POINTS)
+    h_pts, h_nrm = _pinned(pts), _pinned(normals)
+    kp = np.arange(N_POINTS, dtype=np.int64)
+
+    def timed(fn, reps=3):
+        best = float("inf")
+        for _ in range(reps + 1):  # first call warms the pools
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t.item()))
+        return best * 1e3
+
+    ms = timed(lambda: distributed.fpfh(kp, h_pts, h_nrm, radius, 11, decorrelated=True, gather=False))
+    out["fpfh_c3_sharded"] = {
+        "workload": f"C3 over {world} GPUs: every rank uploads the cloud and builds the grid, SPFH of its block of the "
+                    "cell-sorted cloud, one all-gather of SPFH rows (132 MB in all), FPFH of its block of keypoints",
+        "ms": ms, "value": N_POINTS / (ms * 1e-3), "unit": "descriptors/s", "scaling": "strong",
+    }
+    qm = 200_000
+    a = _pinned(synthetic.sparse_unit_rows(qm, 352, seed=2).astype(np.float64))
+    b = _pinned(synthetic.sparse_unit_rows(qm, 352, seed=3).astype(np.float64))
+    ms = timed(lambda: distributed.nearest_neighbors(a, b), reps=2)
+    out["match_c4_sharded"] = {
+        "workload": f"C4 over {world} GPUs: {qm} x {qm} x 352, target set sharded, every rank uploads both sets "
+                    "(1.13 GB of float64 rows over its own PCIe link), one all-gather of (Q, 3) float64, merge",
+        "ms": ms, "value": qm / (ms * 1e-3), "unit": "match queries/s", "scaling": "strong",
+    }
+    return out
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -580,6 +631,11 @@ def main():
                     extra[name] = fn(args, pk)
                 except Exception as exc:  # noqa: BLE001  (the headline line must still be printed)
                     extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+    if world > 1 and args.multi_extra:
+        try:
+            extra["multi_gpu"] = bench_distributed(args, dist, rank, world)
+        except Exception as exc:  # noqa: BLE001
+            extra["multi_gpu"] = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         line = {
             "metric": "SHOT descriptors/sec",
