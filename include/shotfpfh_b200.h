@@ -164,6 +164,29 @@ int sf_fpfh_cloud(sf_grid* grid, double radius, int32_t n_bins, int32_t decorrel
                   const int64_t* keypoint_index_dev, int64_t nq, void* out_dev, int32_t out_is_f64, int64_t* pairs_host,
                   void* stream);
 
+/* sf_fpfh_cloud by BLOCKS of the cell-sorted cloud, for one block per GPU (north_star: "FPFH ... query-sharded at
+ * 1/2/4/8 B200"; SURVEY.md 8e: SPFH by blocks, ONE all-gather of the SPFH rows, FPFH by blocks). The caller owns the
+ * temporaries and does the all-gather between the second and the third call:
+ *   sf_fpfh_block_begin  cand_offsets_dev[count + 1]: padded list offsets of the cell-sorted points
+ *                        [first, first + count); *total_host = list capacity to allocate (synchronises `stream`)
+ *   sf_fpfh_block_spfh   ONE scan of the candidate cells writes nbr_dev / weights_dev [total] (cell-sorted positions,
+ *                        float32 1/d) and counts_dev[count], then the block's SPFH rows spfh_block_dev
+ *                        [count x stride] floats, stride = sf_fpfh_row_stride(width) (rows padded to 16 bytes)
+ *   sf_fpfh_block_rows   FPFH rows of keypoint_index_dev[nq] — original point indices whose cell-sorted position
+ *                        lies in the block — from the block's lists and the SPFH rows of the WHOLE cloud
+ *                        spfh_all_dev [n x stride] (cell-sorted order: the concatenation of the blocks' rows)
+ * first = 0, count = n reproduces sf_fpfh_cloud bit for bit. */
+int sf_fpfh_row_stride(int32_t width, int32_t* stride_out);
+int sf_fpfh_block_begin(sf_grid* grid, double radius, int64_t first, int64_t count, int64_t* cand_offsets_dev,
+                        int64_t* total_host, void* stream);
+int sf_fpfh_block_spfh(sf_grid* grid, double radius, int32_t n_bins, int32_t decorrelated, const double* edges_host,
+                       int64_t first, int64_t count, const int64_t* cand_offsets_dev, int32_t* nbr_dev,
+                       float* weights_dev, int32_t* counts_dev, float* spfh_block_dev, int64_t* pairs_host, void* stream);
+int sf_fpfh_block_rows(sf_grid* grid, int64_t first, int64_t count, const int64_t* cand_offsets_dev,
+                       const int32_t* counts_dev, const int32_t* nbr_dev, const float* weights_dev,
+                       const float* spfh_all_dev, int32_t width, const int64_t* keypoint_index_dev, int64_t nq,
+                       void* out_dev, int32_t out_is_f64, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * M — descriptor matching.  Replaces `cdist(...).argmin(axis=1)` in `basic_matching` (matching.py:162-169),
  * `match_descriptors` (matching.py:43-52) and the ratio test `double_matching_with_rejects` (matching.py:172-221).

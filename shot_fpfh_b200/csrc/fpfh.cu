@@ -178,7 +178,8 @@ struct SearchStage {  // per warp, in shared memory
 };
 
 __global__ void __launch_bounds__(kSearchWarps * 32)
-    search_weights_kernel(GridView g, int64_t n, double r2, const int64_t* __restrict__ cand_offsets,
+    search_weights_kernel(GridView g, int64_t block_first, int64_t n, double r2,
+                          const int64_t* __restrict__ cand_offsets,
                           int32_t* __restrict__ nbr, float* __restrict__ weights, int32_t* __restrict__ counts,
                           unsigned long long* __restrict__ pair_counter) {
   extern __shared__ unsigned char stage_mem[];
@@ -192,8 +193,8 @@ __global__ void __launch_bounds__(kSearchWarps * 32)
   double4 me = make_double4(0, 0, 0, 0);
   int cx = 0, cy = 0, cz = 0;
   int64_t cursor = 0;
-  if (lane < in_tile) {
-    me = load_pt(g.pts + s0 + lane);
+  if (lane < in_tile) {  // the cell-sorted points [block_first, block_first + n); offsets / counts relative to it
+    me = load_pt(g.pts + block_first + s0 + lane);
     cx = cell_coord(me.x, g.origin[0], g.inv_cell, g.dims[0]);
     cy = cell_coord(me.y, g.origin[1], g.inv_cell, g.dims[1]);
     cz = cell_coord(me.z, g.origin[2], g.inv_cell, g.dims[2]);
@@ -270,10 +271,10 @@ __global__ void __launch_bounds__(kSearchWarps * 32)
 }
 
 __global__ void __launch_bounds__(256)
-    self_candidate_count_kernel(GridView g, int64_t n, int64_t* __restrict__ cand) {
+    self_candidate_count_kernel(GridView g, int64_t first, int64_t n, int64_t* __restrict__ cand) {
   const int64_t s = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
-  const double4 me = load_pt(g.pts + s);
+  const double4 me = load_pt(g.pts + first + s);
   const int cx = cell_coord(me.x, g.origin[0], g.inv_cell, g.dims[0]);
   const int cy = cell_coord(me.y, g.origin[1], g.inv_cell, g.dims[1]);
   const int cz = cell_coord(me.z, g.origin[2], g.inv_cell, g.dims[2]);
@@ -309,7 +310,8 @@ __global__ void __launch_bounds__(256)
                 const float* __restrict__ weights, int csr_by_keypoint,
                 const float* __restrict__ spfh, int width, int bin_base, int rem,
                 const int64_t* __restrict__ keypoints, const int32_t* __restrict__ order, int64_t nq,
-                OutT* __restrict__ out) {
+                int64_t first, OutT* __restrict__ out) {
+  // first: the CSR rows cover the cell-sorted points [first, ...) (a block of the cloud, multi-GPU)
   const int lane = threadIdx.x & 31;
   const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (slot >= nq) return;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(256)
   // same neighbourhood of the cloud (L1/L2 hits instead of DRAM: callers pass keypoints in arbitrary order)
   const int64_t q = order ? order[slot] : slot;
   const int64_t s = inv_perm[keypoints[q]];
-  const int64_t row_id = csr_by_keypoint ? q : s;  // CSR rows follow the keypoints, or every cell-sorted point
+  const int64_t row_id = csr_by_keypoint ? q : s - first;  // CSR rows follow the keypoints, or the cell-sorted points
   // counts: padded rows (fused driver); weights: float32 1/d precomputed by the search (0 where d == 0)
   const int64_t begin = offsets[row_id], end = counts ? begin + counts[row_id] : offsets[row_id + 1];
   float acc[kBlocks];
@@ -381,15 +383,15 @@ __global__ void __launch_bounds__(256)
                       const int32_t* __restrict__ counts, const int32_t* __restrict__ nbr,
                       const float* __restrict__ weights, const float4* __restrict__ spfh4, int width,
                       const int64_t* __restrict__ keypoints, const int32_t* __restrict__ order, int64_t nq,
-                      OutT* __restrict__ out) {
+                      int64_t first, OutT* __restrict__ out) {
   constexpr int G = 32 / L, kSteps = (32 + G - 1) / G;
   const int lane = threadIdx.x & 31;
   const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (slot >= nq) return;
   const int64_t q = order ? order[slot] : slot;
   const int64_t s = inv_perm[keypoints[q]];
-  const int64_t begin = offsets[s];
-  const int cnt = counts[s];
+  const int64_t begin = offsets[s - first];  // the lists cover the cell-sorted points [first, ...)
+  const int cnt = counts[s - first];
   // lanes beyond G * L ride along with the last slot (their loads hit sectors that slot fetches anyway) and their
   // sums are never read: no predication inside the loop
   const int grp = lane / L < G ? lane / L : G - 1;
@@ -515,7 +517,7 @@ extern "C" int sf_spfh(sf_grid* g, int64_t first, int64_t count, const int64_t* 
 template <typename OutT>
 static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts, const int32_t* nbr, const double* dist,
                        const float* weights, int by_kp, const float* spfh, int width, int stride, int rows4,
-                       const int64_t* keypoints, int64_t nq, OutT* out, cudaStream_t stream) {
+                       const int64_t* keypoints, int64_t nq, int64_t first, OutT* out, cudaStream_t stream) {
   // rows4: the fused driver's rows, `stride` a multiple of four floats (at most 128) -> fpfh_rows4_kernel
   const int64_t threads = nq * 32;
   const unsigned blocks = unsigned((threads + 255) / 256);
@@ -539,7 +541,7 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts
   if (rows4) {
     const float4* spfh4 = reinterpret_cast<const float4*>(spfh);
 #define SF_LAUNCH_ROWS4(LL) \
-  case LL: fpfh_rows4_kernel<LL, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, weights, spfh4, width, keypoints, order, nq, out); break;
+  case LL: fpfh_rows4_kernel<LL, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, weights, spfh4, width, keypoints, order, nq, first, out); break;
     switch (stride / 4) {
       SF_LAUNCH_ROWS4(1) SF_LAUNCH_ROWS4(2) SF_LAUNCH_ROWS4(3) SF_LAUNCH_ROWS4(4) SF_LAUNCH_ROWS4(5) SF_LAUNCH_ROWS4(6)
       SF_LAUNCH_ROWS4(7) SF_LAUNCH_ROWS4(8) SF_LAUNCH_ROWS4(9) SF_LAUNCH_ROWS4(10) SF_LAUNCH_ROWS4(11) SF_LAUNCH_ROWS4(12)
@@ -569,7 +571,7 @@ static int launch_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* counts
       else if (r > 0) blocks_n += 1;
     }
 #define SF_LAUNCH_FPFH(B) \
-  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, dist, weights, by_kp, spfh, width, base, rem, keypoints, order, nq, out)
+  fpfh_kernel<B, OutT><<<blocks, 256, 0, stream>>>(g->inv_perm, offsets, counts, nbr, dist, weights, by_kp, spfh, width, base, rem, keypoints, order, nq, first, out)
     switch (blocks_n) {
       case 1: SF_LAUNCH_FPFH(1); break;
       case 2: SF_LAUNCH_FPFH(2); break;
@@ -594,9 +596,9 @@ extern "C" int sf_fpfh(sf_grid* g, const int64_t* offsets, const int32_t* nbr, c
   SF_REQUIRE(offsets && nbr && dist && spfh && keypoints && out && width > 0, SF_ERR_ARG, "sf_fpfh: null argument");
   if (nq == 0) return SF_OK;
   return out_is_f64 ? launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, width, 0, keypoints,
-                                  nq, static_cast<double*>(out), stream)
+                                  nq, 0, static_cast<double*>(out), stream)
                     : launch_fpfh(g, offsets, nullptr, nbr, dist, nullptr, csr_by_keypoint, spfh, width, width, 0, keypoints,
-                                  nq, static_cast<float*>(out), stream);
+                                  nq, 0, static_cast<float*>(out), stream);
 }
 
 // Fused driver: what compute_fpfh_descriptor (fpfh.py:16-117) does for one cloud — search around EVERY cloud point,
@@ -636,7 +638,7 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
   SF_CUDA(cudaMemsetAsync(cand + n, 0, 8, stream));
   SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
   const GridView view = g->view();
-  self_candidate_count_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(view, n, cand);
+  self_candidate_count_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(view, 0, n, cand);
   SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, cand, cand_offsets, int(n + 1), stream));
   int64_t total = 0;
   SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + n, 8, cudaMemcpyDeviceToHost, stream));
@@ -653,7 +655,7 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
     }
     const int64_t tiles = (n + 31) / 32;
     search_weights_kernel<<<unsigned((tiles + kSearchWarps - 1) / kSearchWarps), kSearchWarps * 32, smem, stream>>>(
-        view, n, radius * radius, cand_offsets, nbr, weights, counts, pair_counter);
+        view, 0, n, radius * radius, cand_offsets, nbr, weights, counts, pair_counter);
   }
   SF_CUDA(cudaGetLastError());
   profile_mark(1, stream);
@@ -661,9 +663,9 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
   profile_mark(2, stream);
   if (rc == SF_OK && nq > 0)
     rc = out_is_f64 ? launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, stride, rows4, keypoints,
-                                  nq, static_cast<double*>(out), stream)
+                                  nq, 0, static_cast<double*>(out), stream)
                     : launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh, width, stride, rows4, keypoints,
-                                  nq, static_cast<float*>(out), stream);
+                                  nq, 0, static_cast<float*>(out), stream);
   profile_mark(3, stream);
   if (rc == SF_OK && pairs_host != nullptr) {
     unsigned long long pairs = 0;
@@ -675,4 +677,108 @@ extern "C" int sf_fpfh_cloud(sf_grid* g, double radius, int32_t n_bins, int32_t 
   for (void* p : to_free)
     if (p) cudaFreeAsync(p, stream);
   return rc;
+}
+
+// ---- the fused driver by BLOCKS of the cell-sorted cloud (multi-GPU: one block per rank) ---------------------------------
+// The same three stages as sf_fpfh_cloud with the all-gather of the SPFH rows between the second and the third, so the
+// temporaries belong to the caller:
+//   sf_fpfh_block_begin  padded list offsets of the cell-sorted points [first, first + count)  -> total list length
+//   sf_fpfh_block_spfh   one scan of the candidates writes lists, weights, counts; SPFH rows of the block (stride floats)
+//   (caller: all-gather of the blocks' SPFH rows)
+//   sf_fpfh_block_rows   FPFH rows of the keypoints whose cell-sorted position lies in the block
+static int fpfh_row_layout(int width, int* stride, int* rows4) {
+  *rows4 = width <= 128 ? 1 : 0;
+  *stride = *rows4 ? (width + 3) / 4 * 4 : width;
+  return SF_OK;
+}
+
+extern "C" int sf_fpfh_row_stride(int32_t width, int32_t* stride_out) {
+  int stride = 0, rows4 = 0;
+  SF_REQUIRE(width > 0 && stride_out != nullptr, SF_ERR_ARG, "sf_fpfh_row_stride: bad arguments");
+  fpfh_row_layout(width, &stride, &rows4);
+  *stride_out = stride;
+  return SF_OK;
+}
+
+extern "C" int sf_fpfh_block_begin(sf_grid* g, double radius, int64_t first, int64_t count, int64_t* cand_offsets,
+                                   int64_t* total_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_fpfh_block_begin: grid not built");
+  SF_REQUIRE(first >= 0 && count >= 0 && first + count <= g->n && cand_offsets && total_host, SF_ERR_ARG,
+             "sf_fpfh_block_begin: bad arguments");
+  SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
+             "sf_fpfh_block_begin: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
+  *total_host = 0;
+  if (count == 0) {
+    SF_CUDA(cudaMemsetAsync(cand_offsets, 0, 8, stream));
+    return SF_OK;
+  }
+  int64_t* cand = nullptr;
+  void* scan_temp = nullptr;
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cand, cand_offsets, int(count + 1), stream);
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand), size_t(count + 1) * 8, stream));
+  SF_CUDA(scratch_alloc(&scan_temp, scan_bytes + 16, stream));
+  SF_CUDA(cudaMemsetAsync(cand + count, 0, 8, stream));
+  self_candidate_count_kernel<<<unsigned((count + 255) / 256), 256, 0, stream>>>(g->view(), first, count, cand);
+  SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, cand, cand_offsets, int(count + 1), stream));
+  SF_CUDA(cudaMemcpyAsync(total_host, cand_offsets + count, 8, cudaMemcpyDeviceToHost, stream));
+  SF_CUDA(cudaStreamSynchronize(stream));
+  cudaFreeAsync(cand, stream);
+  cudaFreeAsync(scan_temp, stream);
+  return SF_OK;
+}
+
+extern "C" int sf_fpfh_block_spfh(sf_grid* g, double radius, int32_t n_bins, int32_t decorrelated,
+                                  const double* edges_host, int64_t first, int64_t count, const int64_t* cand_offsets,
+                                  int32_t* nbr, float* weights, int32_t* counts, float* spfh_block, int64_t* pairs_host,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_fpfh_block_spfh: grid built without normals");
+  SF_REQUIRE(first >= 0 && count >= 0 && first + count <= g->n && edges_host, SF_ERR_ARG, "sf_fpfh_block_spfh: bad arguments");
+  if (pairs_host) *pairs_host = 0;
+  if (count == 0) return SF_OK;
+  SF_REQUIRE(cand_offsets && nbr && weights && counts && spfh_block, SF_ERR_ARG, "sf_fpfh_block_spfh: null argument");
+  SF_REQUIRE(n_bins >= 1 && n_bins <= kMaxBins, SF_ERR_CAPACITY, "sf_fpfh_block_spfh: n_bins must be in [1, %d]", kMaxBins);
+  const int64_t width64 = decorrelated ? 3 * int64_t(n_bins) : int64_t(n_bins) * n_bins * n_bins;
+  SF_REQUIRE(width64 <= 8192, SF_ERR_CAPACITY, "sf_fpfh_block_spfh: histogram width %lld exceeds 8192", (long long)width64);
+  int stride = 0, rows4 = 0;
+  fpfh_row_layout(int(width64), &stride, &rows4);
+  unsigned long long* pair_counter = nullptr;
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pair_counter), 8, stream));
+  SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
+  const size_t smem = size_t(kSearchWarps) * sizeof(SearchStage);
+  SF_CUDA(cudaFuncSetAttribute(search_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int64_t tiles = (count + 31) / 32;
+  search_weights_kernel<<<unsigned((tiles + kSearchWarps - 1) / kSearchWarps), kSearchWarps * 32, smem, stream>>>(
+      g->view(), first, count, radius * radius, cand_offsets, nbr, weights, counts, pair_counter);
+  SF_CUDA(cudaGetLastError());
+  int rc = launch_spfh(g, first, count, cand_offsets, counts, nbr, n_bins, decorrelated, edges_host, spfh_block, stride, stream);
+  if (rc == SF_OK && pairs_host != nullptr) {
+    unsigned long long pairs = 0;
+    SF_CUDA(cudaMemcpyAsync(&pairs, pair_counter, 8, cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaStreamSynchronize(stream));
+    *pairs_host = int64_t(pairs);
+  }
+  cudaFreeAsync(pair_counter, stream);
+  return rc;
+}
+
+extern "C" int sf_fpfh_block_rows(sf_grid* g, int64_t first, int64_t count, const int64_t* cand_offsets,
+                                  const int32_t* counts, const int32_t* nbr, const float* weights, const float* spfh_all,
+                                  int32_t width, const int64_t* keypoints, int64_t nq, void* out, int32_t out_is_f64,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_fpfh_block_rows: grid not built");
+  SF_REQUIRE(first >= 0 && count >= 0 && first + count <= g->n && width > 0 && nq >= 0, SF_ERR_ARG,
+             "sf_fpfh_block_rows: bad arguments");
+  if (nq == 0) return SF_OK;
+  SF_REQUIRE(cand_offsets && counts && nbr && weights && spfh_all && keypoints && out, SF_ERR_ARG,
+             "sf_fpfh_block_rows: null argument");
+  int stride = 0, rows4 = 0;
+  fpfh_row_layout(width, &stride, &rows4);
+  return out_is_f64 ? launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh_all, width, stride, rows4, keypoints,
+                                  nq, first, static_cast<double*>(out), stream)
+                    : launch_fpfh(g, cand_offsets, counts, nbr, nullptr, weights, 0, spfh_all, width, stride, rows4, keypoints,
+                                  nq, first, static_cast<float*>(out), stream);
 }

@@ -5,7 +5,8 @@ SURVEY.md §8e):
 
   * SHOT:     query points by contiguous blocks, cloud replicated; rows are only all-gathered if the caller asks.
   * FPFH:     SPFH of the cloud points by contiguous blocks of the cell-sorted order -> ONE all-gather of the SPFH
-              rows (they are needed for every neighbour) -> FPFH of the keypoints by contiguous blocks.
+              rows (they are needed for every neighbour) -> FPFH of the keypoints that live in the rank's block
+              (same blocks for both stages: the neighbour lists are built once per point).
   * matching: the TARGET (reference) descriptor set by contiguous blocks, every rank sees all queries; each rank
               produces its exact (nearest index, d1, d2) against its shard -> ONE all-gather -> merge.
 
@@ -45,10 +46,15 @@ def all_gather_blocks(local: torch.Tensor, n_total: int, group=None) -> torch.Te
     lo, hi = block_bounds(n_total, size, rank)
     assert local.shape[0] == hi - lo, (local.shape, lo, hi)
     pad = block_bounds(n_total, size, 0)[1]
-    padded = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    padded[: hi - lo] = local
+    if hi - lo == pad:
+        padded = local.contiguous()
+    else:
+        padded = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[: hi - lo] = local
     out = torch.empty((size * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
+    if n_total % size == 0:  # equal blocks: the gathered tensor IS the concatenation
+        return out
     pieces = []
     for r in range(size):
         rlo, rhi = block_bounds(n_total, size, r)
@@ -142,28 +148,67 @@ def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, m
     return out
 
 
+def sharded_fpfh_by_position(
+    n_points: int,
+    positions: torch.Tensor,
+    width: int,
+    spfh_block: Callable[[int, int], torch.Tensor],
+    fpfh_rows: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+    gather: bool = True,
+    group=None,
+):
+    """
+    FPFH with BOTH stages sharded by the same blocks of the cell-sorted cloud, so that the neighbour lists a rank
+    builds for its SPFH rows also serve its FPFH rows: `positions[q]` = cell-sorted position of keypoint q;
+    `spfh_block(first, end)` -> SPFH rows of the block; ONE all-gather; `fpfh_rows(spfh_all, mine)` -> rows of the
+    keypoints `mine` (ascending indices into `positions`) whose position lies in this rank's block.
+    Returns (mine, rows) when `gather` is false; else the (Q, width) rows in keypoint order on every rank (each
+    row is written by exactly one rank: a sum-reduction of otherwise zero rows moves them exactly).
+    """
+    rank, size = world(group)
+    first, end = block_bounds(n_points, size, rank)
+    spfh_all = all_gather_blocks(spfh_block(first, end), n_points, group)
+    mine = torch.nonzero((positions >= first) & (positions < end)).squeeze(1)
+    local = fpfh_rows(spfh_all, mine)
+    if not gather:
+        return mine, local
+    full = torch.zeros((positions.shape[0], width), dtype=local.dtype, device=local.device)
+    full[mine] = local
+    if size > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full
+
+
 def fpfh(keypoints_indices, cloud_points, normals, radius, n_bins, decorrelated=False, gather=True,
-         out_dtype=torch.float32, group=None) -> torch.Tensor:
-    """FPFH rows (device tensor) of the keypoint INDICES; SPFH sharded over cell-sorted blocks, one all-gather."""
+         out_dtype=torch.float32, group=None):
+    """
+    FPFH rows (device tensor) of the keypoint INDICES over the ranks: every rank builds the grid of the (replicated)
+    cloud and runs the fused driver on ITS block of the cell-sorted points — one scan of the candidates for the
+    lists, SPFH rows of the block — then ONE all-gather of the SPFH rows, then the FPFH rows of the keypoints that
+    live in the block, from the same lists. `gather`: (Q, width) rows on every rank, else (keypoint ordinals, rows)
+    of this rank.
+    """
     from . import ops
-    from .device import Grid, upload
+    from .descriptors.fpfh import _cached_grid
+    from .device import upload
 
     pts, nrm = upload(cloud_points), upload(normals)
     kp = upload(keypoints_indices, torch.int64)
-    grid = Grid().build(pts, nrm, radius)
+    grid = _cached_grid().build(pts, nrm, radius)  # the handle keeps its buffers between calls
+    _, inv_perm = ops.grid_permutation(grid)
+    positions = inv_perm[kp].long()
+    state = {}
 
     def spfh_block(first, end):
-        offsets, nbr, _, _ = ops.radius_csr(grid, None, radius, self_range=(first, end - first))
-        return ops.spfh(grid, offsets, nbr, n_bins, decorrelated, self_range=(first, end - first))
+        state["block"] = ops.FpfhBlock(grid, radius, n_bins, decorrelated, first, end - first, pts.device)
+        return state["block"].spfh()
 
-    def fpfh_block(spfh_all, lo, hi):
-        mine = kp[lo:hi].contiguous()
-        offsets, nbr, _, d = ops.radius_csr(grid, pts[mine].contiguous(), radius, want_dist=True)
-        return ops.fpfh(grid, offsets, nbr, d, spfh_all.contiguous(), mine, out_dtype=out_dtype, csr_by_keypoint=True)
+    def fpfh_rows(spfh_all, mine):
+        return state["block"].rows(spfh_all.contiguous(), kp[mine].contiguous(), out_dtype=out_dtype)
 
-    out = sharded_fpfh(grid.n, int(kp.shape[0]), spfh_block, fpfh_block, gather, group)
+    width = 3 * n_bins if decorrelated else n_bins**3
+    out = sharded_fpfh_by_position(grid.n, positions, width, spfh_block, fpfh_rows, gather, group)
     torch.cuda.synchronize()
-    grid.close()
     return out
 
 

@@ -235,6 +235,62 @@ def fpfh_cloud(grid: Grid, radius: float, n_bins: int, decorrelated: bool, keypo
     return out, (int(pairs.value) if want_pairs else None)
 
 
+
+def fpfh_row_stride(width: int) -> int:
+    """Floats between consecutive rows of the fused drivers' SPFH tables (rows padded to 16 bytes up to 128 bins)."""
+    stride = ctypes.c_int32(0)
+    check(lib.sf_fpfh_row_stride(int(width), ctypes.byref(stride)))
+    return int(stride.value)
+
+
+class FpfhBlock:
+    """
+    The fused FPFH driver on ONE block [first, first + count) of the cell-sorted cloud (one block per GPU):
+    `spfh()` scans the candidates once (padded lists + weights kept here) and returns the block's SPFH rows;
+    after the caller's all-gather, `rows(spfh_all, keypoints)` gives the FPFH rows of the keypoints (original
+    indices) whose cell-sorted position lies in the block. first = 0, count = n reproduces `fpfh_cloud` bit for bit.
+    """
+
+    def __init__(self, grid: Grid, radius: float, n_bins: int, decorrelated: bool, first: int, count: int, device):
+        self.grid, self.radius, self.n_bins, self.decorrelated = grid, float(radius), int(n_bins), bool(decorrelated)
+        self.first, self.count = int(first), int(count)
+        self.width = 3 * self.n_bins if self.decorrelated else self.n_bins**3
+        self.stride = fpfh_row_stride(self.width)
+        self.offsets = torch.empty(self.count + 1, dtype=torch.int64, device=device)
+        total = ctypes.c_int64(0)
+        check(lib.sf_fpfh_block_begin(grid.handle, self.radius, self.first, self.count, ptr(self.offsets),
+                                      ctypes.byref(total), stream_ptr()))
+        cap = max(int(total.value), 1)
+        self.nbr = torch.empty(cap, dtype=torch.int32, device=device)
+        self.weights = torch.empty(cap, dtype=torch.float32, device=device)
+        self.counts = torch.empty(max(self.count, 1), dtype=torch.int32, device=device)
+        self.pairs = 0
+
+    def spfh(self, want_pairs: bool = False) -> torch.Tensor:
+        rows = torch.empty((self.count, self.stride), dtype=torch.float32, device=self.offsets.device)
+        edges = fpfh_edges(self.n_bins)
+        pairs = ctypes.c_int64(0)
+        check(lib.sf_fpfh_block_spfh(
+            self.grid.handle, self.radius, self.n_bins, int(self.decorrelated),
+            edges.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self.first, self.count, ptr(self.offsets),
+            ptr(self.nbr), ptr(self.weights), ptr(self.counts), ptr(rows),
+            ctypes.byref(pairs) if want_pairs else None, stream_ptr(),
+        ))
+        self.pairs = int(pairs.value)
+        return rows
+
+    def rows(self, spfh_all: torch.Tensor, keypoints: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        assert spfh_all.shape == (self.grid.n, self.stride) and spfh_all.dtype == torch.float32 and spfh_all.is_contiguous()
+        nq = int(keypoints.shape[0])
+        out = torch.empty((nq, self.width), dtype=out_dtype, device=spfh_all.device)
+        check(lib.sf_fpfh_block_rows(
+            self.grid.handle, self.first, self.count, ptr(self.offsets), ptr(self.counts), ptr(self.nbr),
+            ptr(self.weights), ptr(spfh_all), self.width, ptr(keypoints), nq, ptr(out),
+            int(out_dtype == torch.float64), stream_ptr(),
+        ))
+        return out
+
+
 def fpfh(
     grid: Grid,
     offsets: torch.Tensor,

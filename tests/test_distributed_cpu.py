@@ -89,6 +89,48 @@ def _check_fpfh(rank, size):
     assert np.array_equal(got.numpy(), full)
 
 
+def _check_fpfh_by_position(rank, size):
+    """Both FPFH stages on the same blocks of the (permuted) "cell-sorted" order; keypoints scattered over the blocks."""
+    from sklearn.neighbors import KDTree
+
+    pts, normals, radius = _cloud()
+    n = pts.shape[0]
+    kp = np.random.default_rng(8).permutation(n)[:701]  # arbitrary order, not all points
+    full, spfh_full = fpfh_oracle.fpfh(kp, pts, normals, radius, 11, True, return_spfh=True)
+    perm = np.random.default_rng(9).permutation(n)  # sorted position -> original index
+    inv_perm = np.empty(n, dtype=np.int64)
+    inv_perm[perm] = np.arange(n)
+    tree = KDTree(pts)
+    edges = fpfh_oracle.bin_edges(11)
+
+    def spfh_block(first, end):
+        rows = np.zeros((end - first, 33))
+        nbh = tree.query_radius(pts[perm[first:end]], radius)
+        for r, i in enumerate(perm[first:end]):
+            a, p, t = fpfh_oracle.pair_features(pts[i], normals[i], pts[nbh[r]], normals[nbh[r]])
+            rows[r] = fpfh_oracle.spfh_row(a, p, t, nbh[r].shape[0], 11, True, edges)
+        return torch.from_numpy(rows)
+
+    def fpfh_rows(spfh_all, mine):
+        s = spfh_all.numpy()  # rows in sorted order
+        assert np.array_equal(s, spfh_full[perm])
+        first, end = sfd.block_bounds(n, size, rank)
+        ids = kp[mine.numpy()]
+        assert ((inv_perm[ids] >= first) & (inv_perm[ids] < end)).all()
+        nbh, d = tree.query_radius(pts[ids], radius, return_distance=True)
+        out = np.zeros((ids.shape[0], 33))
+        for r, i in enumerate(ids):
+            far = d[r] > 0
+            out[r] = s[inv_perm[i]] + (s[inv_perm[nbh[r][far]]] / d[r][far][:, None]).sum(axis=0) / nbh[r].shape[0]
+        return torch.from_numpy(out)
+
+    positions = torch.from_numpy(inv_perm[kp])
+    got = sfd.sharded_fpfh_by_position(n, positions, 33, spfh_block, fpfh_rows, gather=True)
+    assert np.array_equal(got.numpy(), full)
+    mine, local = sfd.sharded_fpfh_by_position(n, positions, 33, spfh_block, fpfh_rows, gather=False)
+    assert np.array_equal(local.numpy(), full[mine.numpy()])
+
+
 def _check_matching(rank, size):
     rng = np.random.default_rng(3)
     a = synthetic.sparse_unit_rows(90, 64, seed=1).astype(np.float64)
@@ -117,7 +159,7 @@ def _check_matching(rank, size):
 
 
 @pytest.mark.parametrize("size", [2, 3])
-@pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_matching"])
+@pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_fpfh_by_position", "_check_matching"])
 def test_sharded_equals_unsharded(fn, size):
     _spawn(fn, size)
 

@@ -64,6 +64,24 @@ def test_virtual_ranks_shot_and_fpfh_bit_exact():
         o, nb, _, d = ops.radius_csr(grid, p[mine].contiguous(), radius, want_dist=True)
         rows.append(ops.fpfh(grid, o, nb, d, spfh_cat, mine, out_dtype=torch.float32, csr_by_keypoint=True))
     assert torch.equal(torch.cat(rows), want)
+
+    # FPFH, the fused driver by blocks (what distributed.fpfh runs): both stages on the same 4 blocks of the
+    # cell-sorted cloud == the fused driver on the whole cloud, bit for bit; keypoints in arbitrary order
+    kp_any = kp_idx[torch.randperm(kp_idx.shape[0], device=kp_idx.device)].contiguous()
+    want_fused, _ = ops.fpfh_cloud(grid, radius, 11, True, kp_any, out_dtype=torch.float32)
+    _, inv_perm = ops.grid_permutation(grid)
+    positions = inv_perm[kp_any].long()
+    blocks4 = [ops.FpfhBlock(grid, radius, 11, True, *(lambda b: (b[0], b[1] - b[0]))(sfd.block_bounds(grid.n, 4, r)), p.device)
+               for r in range(4)]
+    spfh_all = torch.cat([b.spfh() for b in blocks4]).contiguous()
+    got_fused = torch.zeros_like(want_fused)
+    for r, b in enumerate(blocks4):
+        first, end = sfd.block_bounds(grid.n, 4, r)
+        mine = torch.nonzero((positions >= first) & (positions < end)).squeeze(1)
+        got_fused[mine] = b.rows(spfh_all, kp_any[mine].contiguous())
+    assert torch.equal(got_fused, want_fused)
+    assert torch.allclose(got_fused, ops.fpfh(grid, offsets, nbr, dist, spfh_full, kp_any, out_dtype=torch.float32),
+                          rtol=2e-5, atol=1e-7)
     grid.close()
 
 
