@@ -215,27 +215,36 @@ def fpfh(keypoints_indices, cloud_points, normals, radius, n_bins, decorrelated=
 def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None):
     """
     Exact nearest / second-nearest reference row of every non-empty scan row, the reference set sharded over the
-    ranks. Returns host arrays (scan row ids, ref row ids of the nearest, d1, d2) identical on every rank.
+    ranks by contiguous blocks of rows: a rank uploads all the scan rows but only ITS block of reference rows, emits
+    its exact (nearest, d1, d2) against the block, and ONE all-gather + merge gives the result against the union
+    (lowest reference index on ties, as `cdist().argmin()`). The float16 shortlist uses the same scale on every rank
+    (a MAX all-reduce of one scalar). Returns host arrays (scan row ids, ref row ids of the nearest, d1, d2),
+    identical on every rank.
     """
     from . import ops
     from .device import upload
 
-    a, b = upload(scan_descriptors), upload(ref_descriptors)
-    rows_a, rows_b = ops.nonempty_rows(a), ops.nonempty_rows(b)
-    scale = 1.0 / max(float(a.abs().max().item()), float(b.abs().max().item()), 1e-300)
-    a_packed, _ = ops.match_pack(a, rows_a, scale)
+    ref = ref_descriptors
+    a = upload(scan_descriptors)
+    rows_a = ops.nonempty_rows(a)
     qa = int(rows_a.shape[0])
 
     def shard(lo, hi):
-        if hi == lo:
+        b = upload(ref[lo:hi])  # only this rank's block crosses PCIe
+        rows_b = ops.nonempty_rows(b) if hi > lo else torch.empty(0, dtype=torch.int64, device=a.device)
+        top = torch.stack([a.abs().max() if a.numel() else a.new_zeros(()), b.abs().max() if b.numel() else a.new_zeros(())]).max()
+        if world(group)[1] > 1:
+            dist.all_reduce(top, op=dist.ReduceOp.MAX, group=group)
+        scale = 1.0 / max(float(top.item()), 1e-300)
+        if int(rows_b.shape[0]) == 0 or qa == 0:
             inf = torch.full((qa,), float("inf"), dtype=torch.float64, device=a.device)
             return torch.full((qa,), -1, dtype=torch.int64, device=a.device), inf, inf.clone()
-        rb = rows_b[lo:hi].contiguous()
-        b_packed, b_sqnorm = ops.match_pack(b, rb, scale)
+        a_packed, _ = ops.match_pack(a, rows_a, scale)
+        b_packed, b_sqnorm = ops.match_pack(b, rows_b, scale)
         _, cand = ops.match_topk(a_packed, b_packed, b_sqnorm, k, 0, True)
-        nn, d1, d2 = ops.match_rerank(a, rows_a, b, rb, cand)
-        return nn.long() + lo, d1, d2
+        nn, d1, d2 = ops.match_rerank(a, rows_a, b, rows_b, cand)
+        return rows_b[nn.long()].long() + lo, d1, d2  # original reference row ids
 
-    nn, d1, d2 = sharded_nearest(int(rows_b.shape[0]), shard, group)
+    nn, d1, d2 = sharded_nearest(int(ref.shape[0]), shard, group)
     torch.cuda.synchronize()
-    return rows_a.cpu().numpy(), rows_b[nn].cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()
+    return rows_a.cpu().numpy(), nn.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()
