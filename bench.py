@@ -435,8 +435,9 @@ def bench_fpfh(args, pk):
         "workload": "C3: FPFH 33-d (n_bins=11, decorrelated), 1M-point cloud, every point a query, 1 GPU",
         "value": n / (ms * 1e-3), "unit": "descriptors/s", "ms_per_step": ms, "steps": steps, "neighbour_pairs": p,
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "descriptors/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h_pts.nbytes + h_nrm.nbytes + h_kp.nbytes), "d2h_bytes_per_step": int(rows.nbytes),
-                "api": "compute_fpfh_descriptor(keypoints_indices, cloud_points, normals, radius, n_bins=11, decorrelated=True)"},
+                "h2d_bytes_per_step": int(h_pts.nbytes + h_nrm.nbytes + h_kp.nbytes), "d2h_bytes_per_step": int(rows.nbytes // 2),
+                "transport": "float32 rows cross PCIe by blocks of keypoints while the next block is computed; host threads widen them exactly into the float64 result",
+                "api": "compute_fpfh_descriptor(keypoints_indices, cloud_points, normals, radius, n_bins=11, decorrelated=True) -> float64 (N,33)"},
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": alg[dominant] / (stages[dominant] * 1e-3) / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg[dominant] / (stages[dominant] * 1e-3) / 1e9 / pk["hbm_gbs"],
                      "per_stage": {k: {"ms": stages[k], "algorithmic_GBps": alg[k] / (stages[k] * 1e-3) / 1e9} for k in stages}},

@@ -17,7 +17,7 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import Grid, download_widened, upload
+from ..device import DenseRowsDownload, Grid, upload
 
 
 def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
@@ -54,15 +54,27 @@ def compute_fpfh_descriptor(
         if lowest < 0:  # NumPy's negative indexing, as `cloud_points[keypoints_indices]` would resolve it
             kp = np.where(kp < 0, kp + cloud_points.shape[0], kp)
     grid = _cached_grid().build(pts, nrm, radius)
-    # float32 rows on the device (the kernels' values), widened exactly to the float64 array the reference returns
-    # by host threads while the rows cross PCIe
-    out, mean_k = fpfh_device(grid, upload(kp, torch.int64), float(radius), int(n_bins), bool(decorrelated),
-                              out_dtype=torch.float32)
+    kp_dev = upload(kp, torch.int64)
+    n_kp = int(kp_dev.shape[0])
+    width = 3 * int(n_bins) if decorrelated else int(n_bins) ** 3
+    if n_kp == 0:
+        return np.zeros((0, width))
+    # The fused driver in its block form (one block = the whole cloud): one scan of the candidates + SPFH of every
+    # point, then the FPFH rows by blocks of keypoints, so that the float32 rows of block b cross PCIe (and are
+    # widened exactly to the float64 array the reference returns by host threads) while block b + 1 is computed.
+    block = ops.FpfhBlock(grid, float(radius), int(n_bins), bool(decorrelated), 0, grid.n, pts.device)
+    spfh_all = block.spfh(want_pairs=verbose)
     if verbose:
-        logging.info(f"Mean neighborhood size over the whole point cloud: {mean_k:.2f}")
-    return download_widened(out)
+        logging.info(f"Mean neighborhood size over the whole point cloud: {block.pairs / max(grid.n, 1):.2f}")
+    parts = max(1, min(_OUTPUT_BLOCKS, n_kp // 32768))
+    job = DenseRowsDownload(n_kp, width)
+    for b in range(parts):
+        lo, hi = n_kp * b // parts, n_kp * (b + 1) // parts
+        job.push(block.rows(spfh_all, kp_dev[lo:hi].contiguous(), out_dtype=torch.float32))
+    return job.finish()
 
 
+_OUTPUT_BLOCKS = 8
 _GRIDS: dict[int, Grid] = {}
 
 

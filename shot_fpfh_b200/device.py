@@ -108,6 +108,58 @@ def download_widened(t: torch.Tensor, threads: int | None = None, blocks: int = 
     return result.numpy()
 
 
+class DenseRowsDownload:
+    """
+    Consecutive blocks of float32 device rows -> the dense float64 host array the reference API returns:
+
+        job = DenseRowsDownload(n_rows, width)
+        job.push(block)    # queued on a side stream behind the block's kernels: the copy of block b runs while the
+                           # kernels of block b + 1 do
+        arr = job.finish() # follows the copies event by event; the library's host threads widen block b while
+                           # block b + 1 is still crossing PCIe
+
+    The values are the kernels' float32 values widened exactly.
+    """
+
+    def __init__(self, n_rows: int, width: int, threads: int | None = None) -> None:
+        require_cuda()
+        self.n_rows, self.width = int(n_rows), int(width)
+        self.threads = host_threads(threads)
+        self.result = torch.empty((self.n_rows, self.width), dtype=torch.float64, pin_memory=True)
+        self.staging = torch.empty((self.n_rows, self.width), dtype=torch.float32, pin_memory=True)
+        self.side = torch.cuda.Stream()
+        self.filled = 0
+        self._blocks: list[tuple[int, int, torch.cuda.Event, torch.Tensor]] = []
+
+    def push(self, rows: torch.Tensor) -> None:
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous()
+        n = int(rows.shape[0])
+        assert rows.dim() == 2 and rows.shape[1] == self.width and self.filled + n <= self.n_rows
+        if n == 0:
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            self.staging[self.filled:self.filled + n].copy_(rows, non_blocking=True)
+            done.record(self.side)
+        self._blocks.append((self.filled, n, done, rows))  # `rows` stays alive until its copy has run
+        self.filled += n
+
+    def finish(self) -> np.ndarray:
+        assert self.filled == self.n_rows, "DenseRowsDownload.finish before every row was pushed"
+        try:
+            for lo, n, done, _ in self._blocks:
+                done.synchronize()
+                check(lib.sf_host_widen_begin(self.staging.data_ptr() + 4 * lo * self.width, n * self.width,
+                                              self.result.data_ptr() + 8 * lo * self.width, self.threads))
+        finally:
+            check(lib.sf_host_wait())  # the staging buffer is read by the pool until here
+            self._blocks = []
+        return self.result.numpy()
+
+
 class SparseRowsDownload:
     """
     Dense float32 device rows that are mostly zeros (SHOT: ~86 %) -> the dense float64 host array the reference API
