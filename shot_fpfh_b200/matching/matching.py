@@ -56,12 +56,88 @@ def nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k: int = DEFAULT_SHOR
     return ops.match_rerank(a_dev, rows_a, b_dev, rows_b, cand)
 
 
+_PIPELINE_MIN_ROWS = 65536  # scan sets at least this large cross PCIe in chunks under the shortlist GEMM
+_PIPELINE_CHUNK_ROWS = 3 * 148 * 128  # three full waves of the shortlist kernel's 128-query CTAs on 148 SMs
+
+
+def _upload_pipelined(scan: np.ndarray, ref: np.ndarray, k: int, tensor_cores: bool):
+    """
+    Host arrays in: the reference rows are copied first, then the scan rows in chunks of `_PIPELINE_CHUNK_ROWS` on a
+    side stream; the shortlist GEMM + exact re-rank of chunk c (against all the reference rows) run while chunk c + 1
+    is still crossing PCIe — at 200k x 200k x 352 the copy of the scan rows (563 MB, 10 ms) disappears under the GEMM.
+    The chunks are QUERY rows, whose results are independent: cutting the reference rows instead restarts every
+    query's top-k list per chunk, and the shortlist kernel pays ~1.5 ms per restart (measured: 4 chunks 27.3 ms against
+    21.6 ms in one piece), which ate the overlap. Each chunk is packed with its own power-of-two scale; the packed
+    reference rows are reused when the scale repeats (it does unless the chunks differ in magnitude).
+    Returns (a_dev, rows_a, b_dev, rows_b, nn, d1, d2) with device tensors.
+    """
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a_host = torch.from_numpy(np.ascontiguousarray(scan, dtype=np.float64))
+    b_host = torch.from_numpy(np.ascontiguousarray(ref, dtype=np.float64))
+    na = int(a_host.shape[0])
+    a_dev = torch.empty(a_host.shape, dtype=torch.float64, device=dev)
+    b_dev = torch.empty(b_host.shape, dtype=torch.float64, device=dev)
+    bounds = list(range(0, na, _PIPELINE_CHUNK_ROWS)) + [na]
+    cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    start = torch.cuda.Event()
+    start.record(cur)  # the destination buffers exist on the compute stream before the side stream writes them
+    arrived = []
+    with torch.cuda.stream(side):
+        side.wait_event(start)
+        b_dev.copy_(b_host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        arrived.append(ev)
+        for c in range(len(bounds) - 1):
+            a_dev[bounds[c]:bounds[c + 1]].copy_(a_host[bounds[c]:bounds[c + 1]], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            arrived.append(ev)
+    cur.wait_event(arrived[0])
+    rows_b = ops.nonempty_rows(b_dev)
+    qb = int(rows_b.shape[0])
+    b_top = b_dev.abs().max() if b_dev.numel() else b_dev.new_zeros(())
+    packed_b: dict[float, tuple[torch.Tensor, torch.Tensor]] = {}
+    rows_a_parts, nn_parts, d1_parts, d2_parts = [], [], [], []
+    for c in range(len(bounds) - 1):
+        cur.wait_event(arrived[c + 1])
+        chunk = a_dev[bounds[c]:bounds[c + 1]]
+        rows_c = ops.nonempty_rows(chunk)
+        if int(rows_c.shape[0]) == 0:
+            continue
+        if qb == 0:
+            raise ValueError("attempt to get argmin of an empty sequence")  # what NumPy raises in the reference
+        top = max(float(torch.maximum(b_top, chunk.abs().max()).item()), 1e-300)
+        scale = float(2.0 ** np.floor(np.log2(1.0 / top)))
+        if scale not in packed_b:
+            packed_b[scale] = ops.match_pack(b_dev, rows_b, scale)
+        a_packed, _ = ops.match_pack(chunk, rows_c, scale)
+        _, cand = ops.match_topk(a_packed, packed_b[scale][0], packed_b[scale][1], k, 0, tensor_cores)
+        nn, d1, d2 = ops.match_rerank(chunk, rows_c, b_dev, rows_b, cand)
+        rows_a_parts.append(rows_c + bounds[c])
+        nn_parts.append(nn)
+        d1_parts.append(d1)
+        d2_parts.append(d2)
+    if not rows_a_parts:
+        e = torch.empty(0, device=dev)
+        return (a_dev, torch.empty(0, dtype=torch.int64, device=dev), b_dev, rows_b, e.to(torch.int32), e.to(torch.float64),
+                e.to(torch.float64))
+    return a_dev, torch.cat(rows_a_parts), b_dev, rows_b, torch.cat(nn_parts), torch.cat(d1_parts), torch.cat(d2_parts)
+
+
 def _match(scan, ref, k=DEFAULT_SHORTLIST, reverse=False, tensor_cores=True):
-    a_dev, rows_a = _prepare(scan)
-    b_dev, rows_b = _prepare(ref)
-    if a_dev.shape[1] != b_dev.shape[1]:
-        raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")
-    nn, d1, d2 = nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k, tensor_cores)
+    pipelined = (
+        isinstance(scan, np.ndarray) and isinstance(ref, np.ndarray) and scan.ndim == 2 and ref.ndim == 2
+        and scan.shape[1] == ref.shape[1] and scan.shape[0] >= _PIPELINE_MIN_ROWS
+    )
+    if pipelined:
+        a_dev, rows_a, b_dev, rows_b, nn, d1, d2 = _upload_pipelined(scan, ref, k, tensor_cores)
+    else:
+        a_dev, rows_a = _prepare(scan)
+        b_dev, rows_b = _prepare(ref)
+        if a_dev.shape[1] != b_dev.shape[1]:
+            raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")
+        nn, d1, d2 = nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k, tensor_cores)
     fwd = DeviceMatch(rows_a.cpu().numpy(), rows_b.cpu().numpy(), nn.cpu().numpy().astype(np.int64), d1.cpu().numpy(),
                       d2.cpu().numpy())
     if not reverse:

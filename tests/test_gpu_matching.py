@@ -74,6 +74,41 @@ def test_distances_and_indices_bit_exact_vs_cdist(tensor_cores):
     assert np.array_equal(m.d2, second)
 
 
+def test_pipelined_upload_path_is_bit_exact_vs_cdist(monkeypatch):
+    """The chunked-upload path of `_match` (scan rows cross PCIe in chunks under the shortlist GEMM; taken from 65 536
+    scan rows up, forced here at a size cdist can check): same indices and float64 distances as cdist, with empty
+    rows, duplicates in the reference set, chunks of different magnitude and the reciprocity filter."""
+    import shot_fpfh_b200.matching.matching as mm
+    from shot_fpfh_b200.matching import match_descriptors
+
+    monkeypatch.setattr(mm, "_PIPELINE_MIN_ROWS", 1000)
+    monkeypatch.setattr(mm, "_PIPELINE_CHUNK_ROWS", 700)
+    rows = synthetic.sparse_unit_rows(3001, 352, seed=12).astype(np.float64)
+    other = synthetic.sparse_unit_rows(2503, 352, seed=13).astype(np.float64)
+    other[:400] = rows[100:500] + 1e-3 * np.random.default_rng(0).random((400, 352))
+    other[2000] = rows[7]   # a tie: the lowest index must win
+    other[100] = rows[7]
+    rows[1500:2200] *= 37.0  # a chunk with another scale
+    rows[700:1400] = 0.0     # a whole chunk of empty rows
+    rows[5] = 0.0
+    other[1300:1500] = 0.0
+    m, _ = mm._match(rows, other)
+    sa, sb, nn, dist, dmat = matching_oracle.nearest(rows, other)
+    assert np.array_equal(m.rows_a, sa) and np.array_equal(m.rows_b, sb)
+    assert np.array_equal(m.nn, nn)
+    assert np.array_equal(m.d1, dist) and np.array_equal(m.d2, np.partition(dmat, 1, axis=1)[:, 1])
+    got = match_descriptors(rows, other, None, filter_nonreciprocal=True, verbose=False, n_min_matches=10)
+    monkeypatch.setattr(mm, "_PIPELINE_MIN_ROWS", 10**9)
+    want = match_descriptors(rows, other, None, filter_nonreciprocal=True, verbose=False, n_min_matches=10)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    # an all-empty reference set raises what NumPy raises in the reference; an all-empty scan set matches nothing
+    monkeypatch.setattr(mm, "_PIPELINE_MIN_ROWS", 1000)
+    with pytest.raises(ValueError):
+        mm._match(rows, np.zeros((1500, 352)))
+    none, _ = mm._match(np.zeros((1500, 352)), other)
+    assert none.rows_a.shape == (0,) and none.nn.shape == (0,)
+
+
 def test_shortlist_kernels_agree_and_contain_exact_nn():
     """tcgen05 shortlist vs the CUDA-core shortlist vs the exhaustive float64 answer, odd sizes and widths."""
     import torch
