@@ -417,6 +417,11 @@ def bench_fpfh(args, pk):
     alg = {"grid_build": 52 * n, "radius_search": 12 * n + 12 * n + 8 * p + 12 * (n + 1), "spfh": 28 * p + 24 * n + 4 * d * n,
            "fpfh": (4 * d + 8) * p + 4 * d * n + 4 * n}
     dominant = max(stages, key=stages.get)
+    traffic = None
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_c3.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            traffic = json.load(f).get(dominant)
     grid.close()
     # end to end through the reference-shaped call: host float64 arrays in (pinned), (N, 33) float64 host array out
     from shot_fpfh_b200.descriptors import compute_fpfh_descriptor
@@ -440,6 +445,10 @@ def bench_fpfh(args, pk):
                 "api": "compute_fpfh_descriptor(keypoints_indices, cloud_points, normals, radius, n_bins=11, decorrelated=True) -> float64 (N,33)"},
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": alg[dominant] / (stages[dominant] * 1e-3) / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg[dominant] / (stages[dominant] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "traffic": traffic, "algorithmic_bytes": alg[dominant],
+                     "note": "algorithmic bytes count one SPFH-row gather per neighbour pair (SURVEY.md 8d); the 144 MB table "
+                             "is served by L1/L2, so the figure on algorithmic bytes can exceed the HBM peak: see `traffic` "
+                             "(DRAM bytes per launch, ncu) - the FPFH stage is bound by the L1 data pipe, not by HBM",
                      "per_stage": {k: {"ms": stages[k], "algorithmic_GBps": alg[k] / (stages[k] * 1e-3) / 1e9} for k in stages}},
     }
 
