@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xy
 // ---- cell keys + per-cell histogram ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     key_kernel(const double* __restrict__ xyz, int64_t n, GridView g, uint32_t* __restrict__ keys,
-               int32_t* __restrict__ vals, int32_t* __restrict__ cell_count) {
+               int32_t* __restrict__ vals, int32_t* __restrict__ cell_count, int by_slot) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   int c[3];
@@ -99,8 +99,44 @@ __global__ void __launch_bounds__(256)
   }
   const uint32_t key = (uint32_t(c[2]) * g.dims[1] + c[1]) * g.dims[0] + c[0];
   keys[i] = key;
-  vals[i] = int32_t(i);
-  atomicAdd(cell_count + key, 1);
+  // vals: the point's index (radix-sort path) or its arrival slot inside the cell (counting-sort path)
+  const int slot = atomicAdd(cell_count + key, 1);
+  vals[i] = by_slot ? slot : int32_t(i);
+}
+
+// ---- counting sort by cell, made stable --------------------------------------------------------------------------
+// The histogram of the cells is needed anyway (cell_start), and its atomicAdd hands every point a unique slot in its
+// cell: scattering to cell_start[key] + slot sorts the cloud by cell without a radix sort (three 8-bit passes over
+// key-value pairs: 60 of the 127 us of kernels in the build at 1M points). The arrival order is not reproducible, so
+// a second kernel RANKS each point inside its cell by original index — the count of cell-mates with a smaller index,
+// read from the scattered index list (7.6 mates on average at C2 / C3) — which is exactly the order of the stable
+// radix sort: the permutation, hence every result, is bit-identical to the sorted build and from run to run.
+// Cost is sum over cells of population^2 / 32-ish index reads: below the 27-cell candidate scans every use of the
+// grid performs afterwards, whatever the cloud.
+__global__ void __launch_bounds__(256)
+    place_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ slots, int64_t n,
+                 const int32_t* __restrict__ cell_start, int32_t* __restrict__ arrived) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  arrived[cell_start[keys[i]] + slots[i]] = int32_t(i);
+}
+
+__global__ void __launch_bounds__(256)
+    rank_reorder_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int64_t n,
+                        const uint32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
+                        const int32_t* __restrict__ arrived, int32_t* __restrict__ perm, double4* __restrict__ pts,
+                        double4* __restrict__ nrm, int32_t* __restrict__ inv_perm) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t key = keys[i];
+  const int b = cell_start[key], e = cell_start[key + 1];
+  int rank = 0;
+  for (int t = b; t < e; ++t) rank += __ldg(arrived + t) < int32_t(i);
+  const int s = b + rank;
+  perm[s] = int32_t(i);
+  inv_perm[i] = s;
+  pts[s] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __longlong_as_double(static_cast<long long>(i)));
+  if (normals != nullptr) nrm[s] = make_double4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], 0.0);
 }
 
 // ---- gather into cell order ------------------------------------------------------------------------------
@@ -278,25 +314,38 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
     SF_CUDA(cudaMalloc(&g->cell_count, (ncells + 1) * sizeof(int32_t)));
     g->cells_capacity = ncells + 1;
   }
-  // 3. keys + histogram, 4. radix sort by cell (stable: ascending original index inside a cell),
-  // 5. prefix over cells, 6. gather into cell order
+  // 3. keys + histogram, 4. prefix over cells, 5. sort by cell (stable: ascending original index inside a cell) and
+  // gather into cell order: counting sort + rank (see place_kernel); SF_GRID_RADIX=1 keeps the CUB radix sort of
+  // (key, index) pairs, which gives the same permutation (tests compare the two)
   SF_CUDA(cudaMemsetAsync(g->cell_count, 0, (ncells + 1) * sizeof(int32_t), stream));
   const GridView view = g->view();
   const int blocks = int((n + 255) / 256);
-  key_kernel<<<blocks, 256, 0, stream>>>(xyz, n, view, g->keys_in, g->vals_in, g->cell_count);
+  const char* radix_env = getenv("SF_GRID_RADIX");
+  const bool radix = radix_env != nullptr && radix_env[0] == '1';
+  key_kernel<<<blocks, 256, 0, stream>>>(xyz, n, view, g->keys_in, g->vals_in, g->cell_count, radix ? 0 : 1);
   int end_bit = 1;
   while ((int64_t(1) << end_bit) < ncells) ++end_bit;
   size_t sort_bytes = 0, scan_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, g->keys_in, g->keys_out, g->vals_in, g->perm, int(n), 0,
-                                  end_bit, stream);
+  if (radix)
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, g->keys_in, g->keys_out, g->vals_in, g->perm, int(n), 0,
+                                    end_bit, stream);
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, g->cell_count, g->cell_start, int(ncells + 1), stream);
   if (int rc = ensure_temp(g, std::max(sort_bytes, scan_bytes) + 256)) return rc;
   size_t bytes = g->cub_bytes;
-  SF_CUDA(cub::DeviceRadixSort::SortPairs(g->cub_temp, bytes, g->keys_in, g->keys_out, g->vals_in, g->perm, int(n), 0,
-                                          end_bit, stream));
-  bytes = g->cub_bytes;
+  if (radix) {
+    SF_CUDA(cub::DeviceRadixSort::SortPairs(g->cub_temp, bytes, g->keys_in, g->keys_out, g->vals_in, g->perm, int(n), 0,
+                                            end_bit, stream));
+    bytes = g->cub_bytes;
+  }
   SF_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_temp, bytes, g->cell_count, g->cell_start, int(ncells + 1), stream));
-  reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->perm, g->pts, g->nrm, g->inv_perm);
+  if (radix) {
+    reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->perm, g->pts, g->nrm, g->inv_perm);
+  } else {
+    int32_t* arrived = reinterpret_cast<int32_t*>(g->keys_out);
+    place_kernel<<<blocks, 256, 0, stream>>>(g->keys_in, g->vals_in, n, g->cell_start, arrived);
+    rank_reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->keys_in, g->cell_start, arrived, g->perm, g->pts,
+                                                    g->nrm, g->inv_perm);
+  }
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

@@ -181,6 +181,40 @@ def test_keypoint_selectors_against_oracle():
     assert select_keypoints_with_density_threshold(np.zeros((0, 3)), 0.1, 3).shape == (0,)
 
 
+def test_counting_sort_build_equals_radix_sort_build():
+    """The grid's counting sort + stable rank gives the permutation of the stable radix sort (ascending original index
+    inside a cell): random surface, duplicated points, one crowded cell, a large radius (few, crowded cells)."""
+    import os
+
+    import torch
+    from shot_fpfh_b200 import ops
+    from shot_fpfh_b200.device import Grid, upload
+
+    rng = np.random.default_rng(3)
+    pts, _ = synthetic.bumpy_sphere(200_000, seed=4)
+    dup = pts.copy()
+    dup[1000:3000] = dup[17]           # 2000 copies of one point
+    dup[5000:9000] = dup[5000:9000].round(2)  # many exact duplicates on a lattice
+    cases = [(pts, 5.0 * synthetic.mean_spacing(200_000)), (dup, 5.0 * synthetic.mean_spacing(200_000)),
+             (rng.random((30_000, 3)), 0.4), (np.zeros((5000, 3)), 1.0)]
+    for cloud, radius in cases:
+        p = upload(cloud)
+        perms = []
+        for radix in ("0", "1"):
+            os.environ["SF_GRID_RADIX"] = radix
+            try:
+                grid = Grid().build(p, p, radius)
+                perm, inv = ops.grid_permutation(grid)
+                offsets, nbr, _, _ = ops.radius_csr(grid, p[:2000].contiguous(), radius)
+                perms.append((perm.clone(), inv.clone(), offsets.clone(), nbr.clone()))
+                grid.close()
+            finally:
+                del os.environ["SF_GRID_RADIX"]
+        for x, y in zip(*perms):
+            assert torch.equal(x, y)
+        assert torch.equal(torch.sort(perms[0][0]).values, torch.arange(cloud.shape[0], device=p.device, dtype=torch.int32))
+
+
 def test_degenerate_clouds():
     from shot_fpfh_b200.neighbors import RadiusSearch
 
