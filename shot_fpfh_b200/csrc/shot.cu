@@ -265,20 +265,24 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     }
     int positive = 0;
     // software pipeline: the gathers of the lane's NEXT neighbour are issued before the current one is processed
+    // (the neighbour INDEX runs one round further ahead still, so that a gather never waits for its address)
     int64_t i = begin + lane;
     double4 p_next = make_double4(0, 0, 0, 0), n_next = p_next;
+    int s_after = 0;
     if (i < end) {
       const int s = __ldg(nbr + i);
       p_next = load_pt(g.pts + s);
       n_next = load_pt(g.nrm + s);
     }
+    if (i + 32 < end) s_after = __ldg(nbr + i + 32);
     __syncwarp();
     for (int64_t base = begin; base < end; base += 32, i += 32) {  // warp-uniform trip count (barriers inside)
       const double4 p = p_next, n = n_next;
       if (i + 32 < end) {
-        const int s = __ldg(nbr + i + 32);
+        const int s = s_after;
         p_next = load_pt(g.pts + s);
         n_next = load_pt(g.nrm + s);
+        if (i + 64 < end) s_after = __ldg(nbr + i + 64);
       }
       ShotDecision d;
       bool active = false;
