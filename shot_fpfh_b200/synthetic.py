@@ -32,6 +32,25 @@ def bumpy_sphere(
     return d * rho[:, None], d
 
 
+def bumpy_sphere_true_normals(directions: npt.NDArray[np.float64]) -> npt.NDArray[np.float64]:
+    """
+    Outward unit normals of the bumpy sphere itself at the points `bumpy_sphere` returns for `directions`: for a
+    star-shaped surface x = rho(d) d the normal is along rho d - (I - d d^T) grad rho. (The radial directions that the
+    benchmark uses as cheap normals make point-to-plane ICP degenerate: every cross(p, n) is perpendicular to the
+    pair's translation, so the 6x6 system is singular as soon as the residual is not exactly zero.)
+    """
+    d = directions
+    rho = 1.0 + 0.15 * np.sin(5.0 * d[:, 0]) * np.cos(3.0 * d[:, 1]) + 0.05 * np.sin(9.0 * d[:, 2])
+    grad = np.stack([
+        0.75 * np.cos(5.0 * d[:, 0]) * np.cos(3.0 * d[:, 1]),
+        -0.45 * np.sin(5.0 * d[:, 0]) * np.sin(3.0 * d[:, 1]),
+        0.45 * np.cos(9.0 * d[:, 2]),
+    ], axis=1)
+    tangential = grad - np.sum(grad * d, axis=1, keepdims=True) * d
+    n = rho[:, None] * d - tangential
+    return n / np.linalg.norm(n, axis=1, keepdims=True)
+
+
 def mean_spacing(n_points: int) -> float:
     """Mean point spacing of n points on (about) a unit sphere: sqrt(4 pi / n)."""
     return float(np.sqrt(4.0 * np.pi / n_points))
