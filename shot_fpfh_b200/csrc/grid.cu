@@ -129,14 +129,21 @@ __global__ void __launch_bounds__(256)
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint32_t key = keys[i];
+  // the point's own data first: these loads are in flight while the cell-mates are counted
+  const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+  double nx = 0.0, ny = 0.0, nz = 0.0;
+  if (normals != nullptr) {
+    nx = normals[3 * i]; ny = normals[3 * i + 1]; nz = normals[3 * i + 2];
+  }
   const int b = cell_start[key], e = cell_start[key + 1];
   int rank = 0;
+#pragma unroll 4
   for (int t = b; t < e; ++t) rank += __ldg(arrived + t) < int32_t(i);
   const int s = b + rank;
   perm[s] = int32_t(i);
   inv_perm[i] = s;
-  pts[s] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __longlong_as_double(static_cast<long long>(i)));
-  if (normals != nullptr) nrm[s] = make_double4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], 0.0);
+  pts[s] = make_double4(px, py, pz, __longlong_as_double(static_cast<long long>(i)));
+  if (normals != nullptr) nrm[s] = make_double4(nx, ny, nz, 0.0);
 }
 
 // ---- gather into cell order ------------------------------------------------------------------------------
