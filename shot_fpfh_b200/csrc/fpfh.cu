@@ -1,9 +1,17 @@
-// Kernel group P: FPFH (compute_fpfh_descriptor, fpfh.py:16-117), one warp per point.
-//   P1 spfh_kernel <- fpfh.py:38-90: Darboux-frame features (alpha, phi, theta) of every neighbour at distance > 0,
-//      binned with NumPy's histogram semantics (float64 edges from np.linspace handed in by the host), integer
-//      counts in shared memory (order-independent, hence exact), divided by the neighbourhood size INCLUDING the
-//      point itself. Rows are written in cell-sorted order so that stage 2 gathers them with good locality.
-//   P2 fpfh_kernel <- fpfh.py:97-116: spfh[i] + (sum_{j, d_j > 0} spfh[j] / d_j) / K_i on the keypoints.
+// Kernel group P: FPFH (compute_fpfh_descriptor, fpfh.py:16-117).
+//   P1 SPFH <- fpfh.py:38-90: Darboux-frame features (alpha, phi, theta) of every neighbour at distance > 0, binned
+//      with NumPy's histogram semantics (float64 edges from np.linspace handed in by the host), integer counts in
+//      shared memory (order-independent, hence exact), divided by the neighbourhood size INCLUDING the point itself.
+//      Rows are written in cell-sorted order so that stage 2 gathers them with good locality.
+//        spfh_tile_kernel  warp per tile of 32 points, pairs flattened over the lanes (rows of up to 128 bins)
+//        spfh_kernel       warp per point (wider rows; reference of the tile kernel in the tests)
+//      Both take the three bins of a pair from sf_math.cuh::fpfh_pair_bins (float32-filtered, float64 where unsure).
+//   P2 FPFH <- fpfh.py:97-116: spfh[i] + (sum_{j, d_j > 0} spfh[j] / d_j) / K_i on the keypoints.
+//        fpfh_rows4_kernel the fused drivers' padded rows: one load instruction fetches the rows of 32 / L neighbours
+//        fpfh_kernel       the piecewise sf_fpfh (caller's CSR, float64 distances) and rows wider than 128 bins
+//   Fused drivers: sf_fpfh_cloud (one GPU) and sf_fpfh_block_begin / _spfh / _rows (one block of the cell-sorted cloud
+//   per GPU, the all-gather of the SPFH rows between the last two): search_weights_kernel writes the padded neighbour
+//   lists and the float32 weights 1 / d in ONE scan of the candidate cells.
 #include <cub/cub.cuh>
 
 #include "sf_common.cuh"
@@ -159,8 +167,8 @@ __global__ void __launch_bounds__(kSpfhTileWarps * 32, 8)
 // neighbours into a PADDED list (slots sized by the candidate count, a cell_start lookup — no counting pass over
 // the candidates), the float32 weights 1/d that stage 2 needs (fpfh.py:112-114; 0 where d == 0) and the counts.
 //
-// Work unit: a TILE of 32 consecutive cell-sorted points, one warp. The points of a tile lie in one to three cells,
-// and all the points of a cell share their candidate set (the 9 runs around the cell): per distinct cell of the
+// Work unit: a TILE of 32 consecutive cell-sorted points, one warp. The points of a tile lie in a handful of cells
+// (7.6 points per occupied cell at C3: the cloud is a surface), and all the points of a cell share their candidate set (the 9 runs around the cell): per distinct cell of the
 // tile the warp stages the candidates in shared memory once (chunks of kSearchChunk), then each of the cell's
 // points in the tile scans them from there with all 32 lanes. Against one warp per point walking the runs in
 // global memory this removes the per-point run setup, the run lookup per candidate and the L1 traffic

@@ -4,9 +4,9 @@
 //
 // S2 implements the reference's actual semantics: its ten `descriptor[idx] += v`
 // statements are buffered NumPy fancy-index updates, so per statement and per bin only the neighbour with the
-// largest distance that addresses the bin contributes (even with value 0). Each warp owns a table of 1760
-// 64-bit words in shared memory, one word per (statement group, bin): (distance key << 32) | float value, updated
-// with atomicMax. The largest key wins and carries its value along; bins then sum their five tables.
+// largest distance that addresses the bin contributes (even with value 0). Each warp owns compact winner tables in
+// shared memory (sf_math.cuh: three uint32 key tables raised with the native 32-bit atomicMax, five float value
+// tables written by the lanes that still hold a slot's key after a warp barrier); bins then sum their statements.
 #include <cub/cub.cuh>
 
 #include "sf_common.cuh"
