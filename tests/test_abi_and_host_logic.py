@@ -232,3 +232,58 @@ def test_host_row_expansion_rebuilds_dense_float64_rows():
     assert lib.sf_host_expand_rows_begin(offsets.ctypes.data, cols.ctypes.data, vals.ctypes.data, 1, 5000,
                                          out.ctypes.data, 2) == SF_ERR_ARG
     assert lib.sf_host_wait() == 0
+
+
+def test_host_widening_equals_astype_float64():
+    """csrc/host_io.cpp::sf_host_widen_begin (no GPU involved): dst = double(src) exactly, any length / alignment /
+    thread count, jobs queued back to back."""
+    from shot_fpfh_b200._lib import SF_ERR_ARG, check, lib
+
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 4095, 4096, 100_003, 1_000_000):
+        src = rng.standard_normal(n + 3).astype(np.float32)
+        for shift in (0, 1, 3):  # unaligned starts on both sides
+            for threads in (1, 3, 8):
+                dst = np.full(n + 5, 7.0)
+                check(lib.sf_host_widen_begin(src[shift:].ctypes.data, n, dst[1:].ctypes.data, threads))
+                check(lib.sf_host_wait())
+                assert np.array_equal(dst[1 : 1 + n], src[shift : shift + n].astype(np.float64))
+                assert dst[0] == 7.0 and (dst[1 + n :] == 7.0).all()
+    # two jobs in flight: the second waits for the first
+    a, b = rng.standard_normal(500_000).astype(np.float32), rng.standard_normal(300_001).astype(np.float32)
+    out = np.zeros(800_001)
+    check(lib.sf_host_widen_begin(a.ctypes.data, a.size, out.ctypes.data, 4))
+    check(lib.sf_host_widen_begin(b.ctypes.data, b.size, out[a.size :].ctypes.data, 4))
+    check(lib.sf_host_wait())
+    assert np.array_equal(out, np.concatenate([a, b]).astype(np.float64))
+    assert lib.sf_host_widen_begin(None, 5, None, 2) == SF_ERR_ARG
+
+
+def test_result_buffers_follow_the_callers_pattern(monkeypatch):
+    """device.result_buffer: pageable while the caller keeps its results, page-locked (block + one spare) once it
+    is seen dropping them — checked on the allocation requests, without a GPU."""
+    import torch
+
+    from shot_fpfh_b200 import device
+
+    requests = []
+    real_empty = torch.empty
+
+    def recording_empty(*args, **kwargs):
+        requests.append(bool(kwargs.get("pin_memory", False)))
+        kwargs["pin_memory"] = False  # no CUDA here
+        return real_empty(*args, **kwargs)
+
+    monkeypatch.setattr(torch, "empty", recording_empty)
+    monkeypatch.setattr(device, "_RESULTS", {})
+    kept = [device.result_buffer((50, 8))[1] for _ in range(4)]  # a pipeline that keeps its descriptors
+    assert requests == [False] * 4
+    view = kept[0][10:20]
+    del kept
+    requests.clear()
+    d = None
+    for _ in range(6):  # a loop `d = f()`: the previous result is alive during the call
+        d = device.result_buffer((60, 8))[1]
+    # calls 1 and 2 pageable; call 3 sees a dropped result: page-locked block + spare; then the two blocks alternate
+    assert requests == [False, False, True, True, True, True, True]
+    assert view.shape == (10, 8) and d.dtype == np.float64 and d.shape == (60, 8)
