@@ -62,21 +62,22 @@ def all_gather_blocks(local: torch.Tensor, n_total: int, group=None) -> torch.Te
     return torch.cat(pieces, dim=0)
 
 
-def upload_replicated(host_rows, dtype=torch.float64, group=None) -> torch.Tensor:
+def upload_replicated(host_rows, dtype=torch.float64, group=None, to_device=None) -> torch.Tensor:
     """
     A host array that every rank holds -> the same device tensor on every rank, without every rank pushing all of it
     through PCIe: rank r uploads only block r of the rows and ONE all-gather over NVLink completes the tensor (on an
     8-GPU box the ranks share the host's memory and PCIe switches: eight full uploads of the 563 MB scan descriptors
     took 25 ms, an eighth each plus the all-gather a few).
     """
-    from .device import upload
+    if to_device is None:  # (the gloo tests pass a CPU stand-in)
+        from .device import upload as to_device
 
     rank, size = world(group)
     n = int(host_rows.shape[0])
     if size == 1 or n < size:
-        return upload(host_rows, dtype)
+        return to_device(host_rows, dtype)
     lo, hi = block_bounds(n, size, rank)
-    return all_gather_blocks(upload(host_rows[lo:hi], dtype), n, group)
+    return all_gather_blocks(to_device(host_rows[lo:hi], dtype), n, group)
 
 
 def sharded_rows(n_items: int, compute_block: Callable[[int, int], torch.Tensor], gather: bool = True, group=None):

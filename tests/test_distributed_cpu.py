@@ -131,6 +131,23 @@ def _check_fpfh_by_position(rank, size):
     assert np.array_equal(local.numpy(), full[mine.numpy()])
 
 
+def _check_upload_replicated(rank, size):
+    """An N-th of the rows per rank + one all-gather == the whole array on every rank (equal and ragged blocks)."""
+    rng = np.random.default_rng(17)
+    for n in (12, 13, 1, 601):
+        rows = rng.standard_normal((n, 5))
+        seen = []
+
+        def to_cpu(a, dtype):
+            seen.append(a.shape[0])
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+
+        got = sfd.upload_replicated(rows, torch.float64, to_device=to_cpu)
+        assert np.array_equal(got.numpy(), rows)
+        lo, hi = sfd.block_bounds(n, size, rank)
+        assert seen == ([hi - lo] if n >= size else [n])  # only this rank's block went "through PCIe"
+
+
 def _check_matching(rank, size):
     rng = np.random.default_rng(3)
     a = synthetic.sparse_unit_rows(90, 64, seed=1).astype(np.float64)
@@ -159,7 +176,8 @@ def _check_matching(rank, size):
 
 
 @pytest.mark.parametrize("size", [2, 3])
-@pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_fpfh_by_position", "_check_matching"])
+@pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_fpfh_by_position", "_check_upload_replicated",
+                                "_check_matching"])
 def test_sharded_equals_unsharded(fn, size):
     _spawn(fn, size)
 
