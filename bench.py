@@ -41,6 +41,25 @@ MIN_NB = 10
 OWN_KERNELS_PER_SHOT_STEP = 8  # bbox_init, bbox, key, reorder, candidate_count, search_moments, lrf_eigen, shot_descriptor
 
 
+_JSON_FD = None
+
+
+def _quiet_stdout() -> None:
+    """Everything any library prints to stdout during the run (NCCL's version banner under torchrun, progress bars)
+    goes to stderr; the ONE JSON line is written to the original stdout by `_emit`."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -152,7 +171,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -611,6 +630,7 @@ def bench_distributed(args, dist, rank, world):
 
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -668,7 +688,7 @@ def main():
             "clocks": res["clocks"],
             "extra": extra,
         }
-        print(json.dumps(line))
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
