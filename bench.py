@@ -144,7 +144,7 @@ def run_reference_arm(args):
         return
     pts, normals, kp, radius = make_shot_workload()
     # every step is a bounded sample; the whole run stays within ~2.5 minutes whatever K and W are
-    per_step = min(8.0, max(1.5, 150.0 / max(1, args.warmup + args.steps)))
+    per_step = min(8.0, args.cpu_seconds, max(1.5, 150.0 / max(1, args.warmup + args.steps)))
     vals, calib, info = [], None, None
     for i in range(args.warmup + args.steps):
         v, info, calib = cpu_shot_sample(pts, normals, kp, radius, per_step, calib)

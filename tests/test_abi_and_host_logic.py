@@ -287,3 +287,24 @@ def test_result_buffers_follow_the_callers_pattern(monkeypatch):
     # calls 1 and 2 pageable; call 3 sees a dropped result: page-locked block + spare; then the two blocks alternate
     assert requests == [False, False, True, True, True, True, True]
     assert view.shape == (10, 8) and d.dtype == np.float64 and d.shape == (60, 8)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm, no GPU needed): exactly one JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0", "--cpu-seconds", "1.0"], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "SHOT descriptors/sec" and line["unit"] == "descriptors/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
+    assert line["config"]["workload"].startswith("C2: SHOT single-scale, 1M-point")
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "queries" in cpu["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
