@@ -23,9 +23,10 @@ from ..device import DenseRowsDownload, Grid, upload
 def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
                 out_dtype: torch.dtype = torch.float64):
     """
-    search over every cloud point -> SPFH (cell-sorted rows) -> FPFH on the keypoints, by the fused driver
-    (sf_fpfh_cloud; the piecewise sf_radius_* / sf_spfh / sf_fpfh calls serve the multi-GPU path, where the SPFH
-    stage is sharded). Returns (fpfh, mean K).
+    search over every cloud point -> SPFH (cell-sorted rows) -> FPFH on the keypoints, by the fused driver in ONE
+    call (sf_fpfh_cloud), rows left on the device. `compute_fpfh_descriptor` and the multi-GPU driver use its block
+    form (ops.FpfhBlock: same kernels, same results, the FPFH stage callable per block of keypoints / per block of the
+    cloud). Returns (fpfh, mean K).
     """
     out, pairs = ops.fpfh_cloud(grid, radius, n_bins, decorrelated, keypoints_dev, out_dtype=out_dtype)
     return out, float(pairs) / max(grid.n, 1)
