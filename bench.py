@@ -38,7 +38,7 @@ N_POINTS = 1_000_000
 QUERY_VOXEL_IN_SPACINGS = 3.75
 RADIUS_IN_SPACINGS = 5.0
 MIN_NB = 10
-OWN_KERNELS_PER_SHOT_STEP = 8  # bbox_init, bbox, key, reorder, candidate_count, search_moments, lrf_eigen, shot_descriptor
+OWN_KERNELS_PER_SHOT_STEP = 9  # bbox_init, bbox, key, place, rank_reorder, candidate_count, search_moments, lrf_eigen, shot_descriptor
 
 
 _JSON_FD = None
