@@ -308,3 +308,33 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "queries" in cpu["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_replayed_ransac_draws_are_numpys_draws():
+    """matching/ransac.py::replay_choices == the loop of `rng.choice(n, k, replace=False, shuffle=False)` calls of the
+    reference (ransac.py:48-53): same draws, same generator state afterwards (so later calls continue the same
+    stream), with and without a buffered 32-bit half at entry, collisions (tiny populations), Lemire rejections
+    (populations of millions), and the regimes that fall back to the calls themselves."""
+    from shot_fpfh_b200.matching.ransac import replay_choices
+
+    cases = [(20000, 4, 10000), (100, 4, 5000), (6, 4, 3000), (5, 4, 100), (3_000_000, 4, 4000), (30_000_000, 4, 1500),
+             (2**31 + 7, 4, 2000), (3 * 2**30 + 1, 3, 1000), (20000, 1, 10), (40000, 7, 2000), (12000, 300, 5),
+             (9000, 300, 5), (2**33, 4, 50), (4, 4, 20), (20000, 4, 0)]
+    for seed in (72, 5):
+        for pop, size, n in cases:
+            for buffered in (False, True):
+                a, b = np.random.default_rng(seed), np.random.default_rng(seed)
+                if buffered:
+                    a.integers(0, 100, dtype=np.uint32)
+                    b.integers(0, 100, dtype=np.uint32)
+                    assert b.bit_generator.state["has_uint32"] == 1
+                want = [a.choice(pop, size, replace=False, shuffle=False) for _ in range(n)]
+                got = replay_choices(b, pop, size, n)
+                assert got.shape == (n, size) and (n == 0 or np.array_equal(np.stack(want), got)), (seed, pop, size, n)
+                assert a.bit_generator.state == b.bit_generator.state, (seed, pop, size, n, buffered)
+                assert np.array_equal(a.choice(pop, size, replace=False, shuffle=False),
+                                      b.choice(pop, size, replace=False, shuffle=False))
+    # another bit generator: the calls themselves
+    a, b = np.random.Generator(np.random.MT19937(3)), np.random.Generator(np.random.MT19937(3))
+    want = np.stack([a.choice(500, 4, replace=False, shuffle=False) for _ in range(50)])
+    assert np.array_equal(replay_choices(b, 500, 4, 50), want)
