@@ -338,3 +338,43 @@ def test_replayed_ransac_draws_are_numpys_draws():
     a, b = np.random.Generator(np.random.MT19937(3)), np.random.Generator(np.random.MT19937(3))
     want = np.stack([a.choice(500, 4, replace=False, shuffle=False) for _ in range(50)])
     assert np.array_equal(replay_choices(b, 500, 4, 50), want)
+
+
+@pytest.mark.skipif(not reference_available(), reason="the reference package is only present in the build container")
+def test_dropin_rebinds_the_names_the_pipeline_imports_and_restores_them():
+    """dropin.install(): every hot-path name `pipeline.py` imports (pipeline.py:15, :24-30) resolves to this package
+    inside the UNMODIFIED reference, the pipeline object can be built on top of them, and uninstall() puts the
+    reference's own functions back. (No compute: there is no GPU here.)"""
+    import importlib
+
+    from oracle.reference_harness import import_reference
+
+    import_reference()
+    import shot_fpfh_b200.dropin as dropin
+    from shot_fpfh_b200 import descriptors as d
+    from shot_fpfh_b200 import icp, matching as m
+
+    pipeline = importlib.import_module("shot_fpfh.pipeline")
+    originals = {name: getattr(pipeline, name) for name in (
+        "ShotMultiprocessor", "compute_fpfh_descriptor", "basic_matching", "match_descriptors",
+        "double_matching_with_rejects", "ransac_on_matches", "icp_point_to_plane")}
+    done = dropin.install()
+    try:
+        assert len(done) >= 30
+        assert pipeline.ShotMultiprocessor is d.ShotMultiprocessor
+        assert pipeline.compute_fpfh_descriptor is d.compute_fpfh_descriptor
+        assert pipeline.basic_matching is m.basic_matching and pipeline.match_descriptors is m.match_descriptors
+        assert pipeline.double_matching_with_rejects is m.double_matching_with_rejects
+        assert pipeline.ransac_on_matches is m.ransac_on_matches and pipeline.icp_point_to_plane is icp.icp_point_to_plane
+        ref_pkg = importlib.import_module("shot_fpfh")
+        assert ref_pkg.compute_normals is d.compute_normals
+        assert importlib.import_module("shot_fpfh.descriptors").ShotMultiprocessor is d.ShotMultiprocessor
+        # the reference's own orchestration object builds on top of the rebound names
+        rng = np.random.default_rng(0)
+        pts = rng.random((50, 3))
+        pipe = pipeline.RegistrationPipeline(scan=pts, scan_normals=pts, ref=pts, ref_normals=pts)
+        assert hasattr(pipe, "compute_descriptors") and hasattr(pipe, "find_descriptors_matches")
+    finally:
+        dropin.uninstall()
+    for name, fn in originals.items():
+        assert getattr(pipeline, name) is fn, name
