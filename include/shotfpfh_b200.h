@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 3
+#define SF_ABI_VERSION 4
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -130,6 +130,12 @@ int sf_shot_descriptor(sf_grid* grid, const double* queries_dev, int64_t nq, dou
 int sf_shot_single_scale(sf_grid* grid, const double* queries_dev, int64_t nq, double radius,
                          int32_t min_neighborhood_size, int32_t normalize, void* out_dev, int32_t out_is_f64,
                          double* lrf_out_dev, int64_t* pairs_host, void* stream);
+
+/* Both descriptor entry points run the float32-filtered kernel first (csrc/shot.cu::shot_fast_kernel: decisions from
+ * cell-relative float32 coordinates with proven margins) and hand the queries it cannot decide — more than 128
+ * neighbours, a decision inside its margin, two competitors closer than float32 orders — to the float64 kernel.
+ * Number of queries handed over in the last sf_shot_single_scale call that asked for `pairs_host` (measurement). */
+int sf_shot_last_deferred(int64_t* deferred);
 
 /* Measurement hook: with profiling enabled, the fused drivers (sf_shot_single_scale, sf_fpfh_cloud) record CUDA
  * events on their stream around their three stages; sf_profile_read waits for the last call and returns the

@@ -104,6 +104,22 @@ __global__ void __launch_bounds__(256)
   vals[i] = by_slot ? slot : int32_t(i);
 }
 
+// ---- float32 side copy of a cell-sorted point (sf_math.cuh "float32-filtered decisions") ---------------------------
+__device__ __forceinline__ void write_side_copy(const GridView& g, double px, double py, double pz, double nx,
+                                                double ny, double nz, bool has_normal, float4* xyzc, float4* nrm32) {
+  const double p[3] = {px, py, pz};
+  int c[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // the cell key_kernel put the point in
+    c[a] = cell_coord(p[a], g.origin[a], g.inv_cell, g.dims[a]);
+    c[a] = min(max(c[a], 0), g.dims[a] - 1);
+  }
+  float l[3];
+  shot_cell_local(p, g.origin, g.cell, c, l);
+  *xyzc = make_float4(l[0], l[1], l[2], __uint_as_float(shot_cellbits(c)));
+  if (has_normal) *nrm32 = make_float4(float(nx), float(ny), float(nz), 0.0f);
+}
+
 // ---- counting sort by cell, made stable --------------------------------------------------------------------------
 // The histogram of the cells is needed anyway (cell_start), and its atomicAdd hands every point a unique slot in its
 // cell: scattering to cell_start[key] + slot sorts the cloud by cell without a radix sort (three 8-bit passes over
@@ -125,7 +141,8 @@ __global__ void __launch_bounds__(256)
     rank_reorder_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int64_t n,
                         const uint32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
                         const int32_t* __restrict__ arrived, int32_t* __restrict__ perm, double4* __restrict__ pts,
-                        double4* __restrict__ nrm, int32_t* __restrict__ inv_perm) {
+                        double4* __restrict__ nrm, int32_t* __restrict__ inv_perm, GridView g,
+                        float4* __restrict__ xyzc, float4* __restrict__ nrm32) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint32_t key = keys[i];
@@ -144,21 +161,26 @@ __global__ void __launch_bounds__(256)
   inv_perm[i] = s;
   pts[s] = make_double4(px, py, pz, __longlong_as_double(static_cast<long long>(i)));
   if (normals != nullptr) nrm[s] = make_double4(nx, ny, nz, 0.0);
+  write_side_copy(g, px, py, pz, nx, ny, nz, normals != nullptr, xyzc + s, nrm32 + s);
 }
 
 // ---- gather into cell order ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     reorder_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int64_t n,
                    const int32_t* __restrict__ perm, double4* __restrict__ pts, double4* __restrict__ nrm,
-                   int32_t* __restrict__ inv_perm) {
+                   int32_t* __restrict__ inv_perm, GridView g, float4* __restrict__ xyzc, float4* __restrict__ nrm32) {
   const int64_t s = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (s >= n) return;
   const int32_t i = perm[s];
   inv_perm[i] = int32_t(s);
-  pts[s] = make_double4(xyz[3 * int64_t(i)], xyz[3 * int64_t(i) + 1], xyz[3 * int64_t(i) + 2],
-                        __longlong_as_double(static_cast<long long>(i)));
-  if (normals != nullptr)
-    nrm[s] = make_double4(normals[3 * int64_t(i)], normals[3 * int64_t(i) + 1], normals[3 * int64_t(i) + 2], 0.0);
+  const double px = xyz[3 * int64_t(i)], py = xyz[3 * int64_t(i) + 1], pz = xyz[3 * int64_t(i) + 2];
+  double nx = 0.0, ny = 0.0, nz = 0.0;
+  pts[s] = make_double4(px, py, pz, __longlong_as_double(static_cast<long long>(i)));
+  if (normals != nullptr) {
+    nx = normals[3 * int64_t(i)]; ny = normals[3 * int64_t(i) + 1]; nz = normals[3 * int64_t(i) + 2];
+    nrm[s] = make_double4(nx, ny, nz, 0.0);
+  }
+  write_side_copy(g, px, py, pz, nx, ny, nz, normals != nullptr, xyzc + s, nrm32 + s);
 }
 
 // ---- fixed-radius search: one warp per query ---------------------------------------------------------------
@@ -246,7 +268,7 @@ extern "C" int sf_grid_create(sf_grid** out) {
 }
 
 static void free_all(sf_grid* g) {
-  cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->perm); cudaFree(g->inv_perm);
+  cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->xyzc); cudaFree(g->nrm32); cudaFree(g->perm); cudaFree(g->inv_perm);
   cudaFree(g->cell_start); cudaFree(g->cell_count); cudaFree(g->keys_in); cudaFree(g->keys_out);
   cudaFree(g->vals_in); cudaFree(g->bbox); cudaFree(g->cub_temp);
 }
@@ -265,11 +287,13 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   SF_REQUIRE(n > 0 && n < (int64_t(1) << 31), SF_ERR_ARG, "sf_grid_build: n = %lld out of range", (long long)n);
   SF_REQUIRE(radius > 0.0 && std::isfinite(radius), SF_ERR_ARG, "sf_grid_build: radius must be positive and finite");
   if (n > g->capacity) {
-    cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->perm); cudaFree(g->inv_perm);
+    cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->xyzc); cudaFree(g->nrm32); cudaFree(g->perm); cudaFree(g->inv_perm);
     cudaFree(g->keys_in); cudaFree(g->keys_out); cudaFree(g->vals_in);
     g->capacity = 0;
     SF_CUDA(cudaMalloc(&g->pts, n * sizeof(double4)));
     SF_CUDA(cudaMalloc(&g->nrm, n * sizeof(double4)));
+    SF_CUDA(cudaMalloc(&g->xyzc, n * sizeof(float4)));
+    SF_CUDA(cudaMalloc(&g->nrm32, n * sizeof(float4)));
     SF_CUDA(cudaMalloc(&g->perm, n * sizeof(int32_t)));
     SF_CUDA(cudaMalloc(&g->inv_perm, n * sizeof(int32_t)));
     SF_CUDA(cudaMalloc(&g->keys_in, n * sizeof(uint32_t)));
@@ -346,12 +370,13 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   }
   SF_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_temp, bytes, g->cell_count, g->cell_start, int(ncells + 1), stream));
   if (radix) {
-    reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->perm, g->pts, g->nrm, g->inv_perm);
+    reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->perm, g->pts, g->nrm, g->inv_perm, view, g->xyzc,
+                                               g->nrm32);
   } else {
     int32_t* arrived = reinterpret_cast<int32_t*>(g->keys_out);
     place_kernel<<<blocks, 256, 0, stream>>>(g->keys_in, g->vals_in, n, g->cell_start, arrived);
     rank_reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->keys_in, g->cell_start, arrived, g->perm, g->pts,
-                                                    g->nrm, g->inv_perm);
+                                                    g->nrm, g->inv_perm, view, g->xyzc, g->nrm32);
   }
   SF_CUDA(cudaGetLastError());
   return SF_OK;

@@ -56,9 +56,13 @@ struct GridView {
   const double4* pts;       // cell-sorted coordinates; .w carries the original index (bit pattern of an int64)
   const double4* nrm;       // cell-sorted normals (may be null)
   const int32_t* cell_start;  // [ncells + 1], exclusive prefix of the per-cell counts
+  const float4* xyzc;       // cell-sorted float32 side copy: coordinates relative to the point's cell corner, .w = the
+                            // cell coordinates modulo 4 (sf_math.cuh::shot_cellbits) — 16 B per candidate test
+  const float4* nrm32;      // cell-sorted float32 normals (may be null)
   int64_t n;
   double origin[3];
   double inv_cell;
+  double cell;
   int dims[3];
 };
 
@@ -77,6 +81,8 @@ struct sf_grid {
   int device = 0;
   double4* pts = nullptr;
   double4* nrm = nullptr;
+  float4* xyzc = nullptr;
+  float4* nrm32 = nullptr;
   int32_t* perm = nullptr;      // sorted position -> original index
   int32_t* inv_perm = nullptr;  // original index -> sorted position
   int32_t* cell_start = nullptr;
@@ -92,12 +98,15 @@ struct sf_grid {
     v.pts = pts;
     v.nrm = has_normals ? nrm : nullptr;
     v.cell_start = cell_start;
+    v.xyzc = xyzc;
+    v.nrm32 = has_normals ? nrm32 : nullptr;
     v.n = n;
     for (int i = 0; i < 3; ++i) {
       v.origin[i] = origin[i];
       v.dims[i] = dims[i];
     }
     v.inv_cell = 1.0 / cell;
+    v.cell = cell;
     return v;
   }
 };

@@ -10,6 +10,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SF_HD __host__ __device__ __forceinline__
@@ -179,6 +180,210 @@ SF_HD ShotRecord shot_record(double X, double Y, double Z, double cosine, double
   r.v_az = a_az;
   r.v_own = (1.0f - d.a_cos) + d.own_shell + own_vol + (1.0f - a_az);
   return r;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// SHOT, float32-filtered decisions (the fast descriptor kernel, shot.cu::shot_fast_kernel).
+//
+// Every decision of shot_decide is a comparison of a quantity that is continuous in the inputs against a fixed
+// boundary, so it can be taken from a float32 evaluation whenever the float32 value keeps a proven distance from
+// the boundary; a query with any neighbour inside a margin is handed to the float64 kernel (1-3 % of the queries on
+// a surface scan, where Z clusters around 0).
+//
+// Two sources of float32 offsets c = p - q, u = 2^-24:
+//  (a) the fused driver: its search kernel has the exact float64 offset in registers and stores its float32 image
+//      in the neighbour list: each component within u |c_a| of the float64 value, so with rho = |c|
+//        rho      : 1.7 u rho (c) + 1.5 u rho (sum of squares) + 3.5 u rho (rsqrt, product)      <= 8 u rho
+//        X, Y, Z  : 1.7 u rho (c) + 1.7 u rho (axis rounded to float32) + 3 u rho (dot product)  <= 8 u rho
+//  (b) caller-provided lists: the grid's cell-relative float32 coordinates (grid.cu: lp = float((p - origin) -
+//      cell * edge), |lp| <= edge, plus the cell coordinates modulo 4): c = lp - lq + (cell_p - cell_q) * edge with
+//      cell_p - cell_q in {-1, 0, 1}, each component within 7 u edge wherever the cloud sits (roundings of lp, lq,
+//      lp - lq, edge, the fma: 5 u edge; float64 roundings of (p - origin) - cell * edge: below u edge because
+//      extent / edge < 2^25):  rho, X, Y, Z <= 24 u edge.
+//  cosine = n . z : 7 u |n|, |n|^2 <= n2;  pos = (cosine + 1) * 5.5 - 0.5  <= (44 n2 + 40) u
+// A decision is accepted when the value is farther than its bound from the boundary (the float64 reference carries
+// its own rounding, 1e-16 relative: far below). The continuous WEIGHTS follow the inputs, except where they are badly
+// conditioned: the elevation weight moves by (error of c) / rho and the azimuth weight by (error of c) / hypot(X, Y);
+// neighbours below `w_rho_min` / `w_xy_min` are left to float64 ((a): none / hypot below 1 % of rho; (b): 1 % of
+// the radius each — a per-weight error below 2e-4 in the worst case of the bounds, ~1e-5 in practice).
+// Checked on the host against shot_decide on millions of perturbed inputs (tests/test_host_math.py) and on the GPU
+// against the goldens and against the float64 kernel.
+// ----------------------------------------------------------------------------------------------------------
+constexpr float kEps32 = 5.9604645e-8f;  // 2^-24
+
+// a / b for weights (continuous in their inputs): the device's approximate division (2 ulp, no slow-path call)
+SF_HD float sf_divf(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+SF_HD float sf_rsqrtf(float x);  // (defined with the FPFH helpers below)
+
+// cell-relative float32 coordinates of p in cell c (grid.cu writes them; the kernels compute the query's)
+SF_HD void shot_cell_local(const double p[3], const double origin[3], double edge, const int c[3], float out[3]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 3; ++a) out[a] = float((p[a] - origin[a]) - double(c[a]) * edge);
+}
+SF_HD uint32_t shot_cellbits(const int c[3]) {
+  return uint32_t(c[0] & 3) | (uint32_t(c[1] & 3) << 2) | (uint32_t(c[2] & 3) << 4);
+}
+// p - q from the cell-relative coordinates; bits_p / bits_q = the cells' coordinates modulo 4 (2 bits per axis)
+SF_HD void shot_rel32(const float lp[3], uint32_t bits_p, const float lq[3], uint32_t bits_q, float edge32, float c[3]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int a = 0; a < 3; ++a) {
+    const uint32_t code = ((bits_p >> (2 * a)) - (bits_q >> (2 * a)) + 1u) & 3u;  // cell_p - cell_q + 1
+    const float shift = code == 0u ? -edge32 : (code == 2u ? edge32 : (code == 1u ? 0.0f : 2.0f * edge32));
+    c[a] = (lp[a] - lq[a]) + shift;
+  }
+}
+SF_HD float dot3f(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+
+struct ShotFastMargins {
+  float e_loc;     // bound on the error of X, Y, Z
+  float e_rho;     // bound on the error of rho
+  float w_rho_min, w_xy_min;  // weights are left to float64 below these (see above)
+  float n2;        // the cosine margin assumes |n|^2 <= n2
+};
+
+// shot_decide from float32 inputs. Returns false when any decision is within its margin of a boundary; the decision
+// is only meaningful when true is returned. cosine = n . z, not yet clipped; rho = |c| > 0.
+// d.key = rho / radius in 23-bit fixed point (taken from the mantissa of 1 + rho / radius: no conversion).
+SF_HD bool shot_decide_fast(float X, float Y, float Z, float cosine, float rho, float inv_rho, float radius,
+                            float inv_radius, const ShotFastMargins& m, ShotDecision& d) {
+  const float cosc = fminf(1.0f, fmaxf(-1.0f, cosine));
+  const float pos = fmaf(cosc + 1.0f, 0.5f * float(kShotCos), -0.5f);  // shot.py:228
+  const float e_pos = (44.0f * m.n2 + 40.0f) * kEps32;
+  // round-half-even by the float32 adder: pos in [-0.5, 10.5], 1.5 * 2^23 + pos keeps the integer in the mantissa
+  const float magic = 12582912.0f;
+  const float shifted = pos + magic;
+#if defined(__CUDA_ARCH__)
+  const int ci = __float_as_int(shifted) - 0x4B400000;
+#else
+  int ci;
+  { float t = shifted; uint32_t bits; memcpy(&bits, &t, 4); ci = int(bits) - 0x4B400000; }
+#endif
+  const float dcos = pos - (shifted - magic);
+  bool sure = (0.5f - fabsf(dcos) > e_pos) && (fabsf(dcos) > e_pos);
+  const int scos = dcos > 0.0f ? 1 : -1;
+  const float ax = fabsf(X), ay = fabsf(Y), hi = fmaxf(ax, ay);
+  sure = sure && ax > m.e_loc && ay > m.e_loc && fabsf(ax - ay) > 2.0f * m.e_loc && fabsf(Z) > m.e_loc;
+  const bool upper = Y > 0.0f, right = X > 0.0f;
+  const bool wide = ax > ay;  // the octant hugs the x axis
+  const bool second = (upper == right) ? !wide : wide;  // azimuth_octant with X, Y != 0
+  d.ti = 4 * int(upper) + 2 * int(right != upper) + int(second);
+  d.ei = Z > 0.0f;
+  const float half = 0.5f * radius;
+  const int ri = rho > half;
+  sure = sure && fabsf(rho - half) > m.e_rho && rho < radius * 1.001f && rho > m.w_rho_min && hi > m.w_xy_min;
+  d.own = shot_flat(ci, d.ti, d.ei, ri);
+  int cnb = ci + scos;
+  cnb = cnb < 0 ? cnb + kShotCos : (cnb >= kShotCos ? cnb - kShotCos : cnb);
+  d.cos_nb = shot_flat(cnb, d.ti, d.ei, ri);
+  // sign of the offset from the octant centre: the centre has the signs of (X, Y) and its larger component along
+  // the larger of |X|, |Y|, so cross(centre, (X, Y)) = sign(X) sign(Y) (m1 |Y| - m2 |X|), (m1, m2) = (cos, sin)(pi/8)
+  // when |X| > |Y|, swapped otherwise
+  const float kc = 0.92387953251128673848f, ks = 0.38268343236508978178f;
+  const float cr = wide ? fmaf(kc, ay, -ks * ax) : fmaf(ks, ay, -kc * ax);
+  sure = sure && fabsf(cr) > 2.0f * m.e_loc;
+  d.saz = ((cr > 0.0f) == (upper == right)) ? 1 : -1;
+  d.az_nb = shot_flat(ci, (d.ti + d.saz + kShotAz) & (kShotAz - 1), d.ei, ri);
+  d.a_cos = fabsf(dcos);
+  const float quarter = 0.25f * radius, three_q = 0.75f * radius, inv_half = 2.0f * inv_radius;
+  if (ri) {
+    d.own_shell = 1.0f - fabsf(rho - three_q) * inv_half;
+    d.other_shell = fmaxf(0.0f, (three_q - rho) * inv_half);
+  } else {
+    d.own_shell = 1.0f - fabsf(rho - quarter) * inv_half;
+    d.other_shell = fmaxf(0.0f, (rho - quarter) * inv_half);
+  }
+  d.fx = X;
+  d.fy = Y;
+  d.ratio = fminf(1.0f, fmaxf(-1.0f, Z * inv_rho));
+  const float one_plus = fminf(fmaf(rho, inv_radius, 1.0f), 1.99999988f);  // [1, 2): mantissa = rho / radius * 2^23
+#if defined(__CUDA_ARCH__)
+  d.key = __float_as_uint(one_plus) & 0x7FFFFFu;
+#else
+  { uint32_t bits; memcpy(&bits, &one_plus, 4); d.key = bits & 0x7FFFFFu; }
+#endif
+  return sure;
+}
+
+// The two transcendental weights without atan2f / acosf: the octant and the half-space are already decided, only
+// the angle INSIDE them is needed.
+//   azimuth  : |offset from the octant centre| in octant widths = |atan(min(|X|,|Y|) / max(|X|,|Y|)) * 4/pi - 0.5|
+//              in every octant (the angle from the nearest axis runs 0 .. pi/4 across the octant, up or down)
+//   elevation: with g = asin(|Z| / rho) * 2/pi (elevation above the tangent plane, in quarter turns):
+//              own half-space volume 1 - |0.5 - g|, other one max(0, 0.5 - g) (shot_elevation with phi = pi/2 -+ asin)
+// Polynomials: atan(t) / t in t^2 on [0, 1] (degree 7) and (asin(w) - w) / w^3 in w^2 on [0, 0.5] (degree 4, the
+// upper half through asin(w) = pi/2 - 2 asin(sqrt((1 - w) / 2))); max error 1.8e-7 / 1.6e-7 rad in float32
+// arithmetic (tests/test_host_math.py), i.e. the same 1e-7 level as atan2f / acosf on float32 inputs.
+SF_HD float shot_azimuth_fast(const ShotDecision& d) {
+  const float ax = fabsf(d.fx), ay = fabsf(d.fy);
+  const float hi = fmaxf(ax, ay), lo = fminf(ax, ay);
+  if (d.saz == 0) return 0.0f;
+  if (!(hi > 0.0f)) return 0.5f;  // on the frame's z axis: theta = atan2(0, 0) = 0 in octant 0, offset clipped to 0.5
+  const float t = sf_divf(lo, hi), s = t * t;
+  float p = -0.004668773151934147f;
+  p = fmaf(p, s, 0.02416618913412094f);
+  p = fmaf(p, s, -0.0593671016395092f);
+  p = fmaf(p, s, 0.09906096756458282f);
+  p = fmaf(p, s, -0.14016585052013397f);
+  p = fmaf(p, s, 0.19969235360622406f);
+  p = fmaf(p, s, -0.33331960439682007f);
+  p = fmaf(p, s, 0.9999998807907104f);
+  return fabsf(fmaf(p * t, 1.27323954473516268615f, -0.5f));
+}
+SF_HD void shot_elevation_fast(const ShotDecision& d, float& own_vol, float& other_vol) {
+  const float w = fabsf(d.ratio);
+  const bool big = w > 0.5f;
+  const float z = big ? (1.0f - w) * 0.5f : w * w;
+  const float r = big ? z * sf_rsqrtf(fmaxf(z, 1e-37f)) : w;
+  float p = 0.0382063128054142f;
+  p = fmaf(p, z, 0.026494354009628296f);
+  p = fmaf(p, z, 0.04501068592071533f);
+  p = fmaf(p, z, 0.07498808950185776f);
+  p = fmaf(p, z, 0.16666673123836517f);
+  const float a = fmaf(r * z, p, r);                                        // asin(r)
+  const float g = (big ? fmaf(-2.0f, a, 1.57079632679489661923f) : a) * 0.63661977236758134308f;
+  own_vol = 1.0f - fabsf(0.5f - g);
+  other_vol = fmaxf(0.0f, 0.5f - g);
+}
+
+// What a neighbour contributes, in the form the fast kernel keeps per neighbour: the three target bins, an order key
+// that is UNIQUE inside the query (23 bits of rho / radius, then the neighbour's position in the list, < 128) and
+// the five values. Two competitors whose distance parts are closer than the kernel's margin make the query
+// ambiguous for float32; it is then redone by the float64 kernel.
+struct ShotFastRecord {
+  uint32_t bins;  // own | cos_nb << 9 | az_nb << 18
+  uint32_t key;
+  float v_own, v_cos, v_az, v_rad, v_el;
+};
+constexpr int kFastIndexBits = 7;
+
+SF_HD ShotFastRecord shot_fast_record(const ShotDecision& d, uint32_t index_in_list) {
+  ShotFastRecord r;
+  r.bins = uint32_t(d.own) | (uint32_t(d.cos_nb) << 9) | (uint32_t(d.az_nb) << 18);
+  r.key = 0x80000000u | (d.key << kFastIndexBits) | index_in_list;  // never 0 (0 = nobody)
+  float own_vol, other_vol;
+  shot_elevation_fast(d, own_vol, other_vol);
+  const float a_az = shot_azimuth_fast(d);
+  r.v_own = (1.0f - d.a_cos) + d.own_shell + own_vol + (1.0f - a_az);
+  r.v_cos = d.a_cos;
+  r.v_az = a_az;
+  r.v_rad = d.other_shell;
+  r.v_el = other_vol;
+  return r;
+}
+// Two keys whose distance parts differ by at most `margin` (23-bit units) cannot be ordered by float32.
+SF_HD bool shot_keys_ambiguous(uint32_t a, uint32_t b, uint32_t margin) {
+  const uint32_t x = (a >> kFastIndexBits) & 0x7FFFFFu, y = (b >> kFastIndexBits) & 0x7FFFFFu;
+  return (x > y ? x - y : y - x) <= margin;
 }
 
 // ---- winner tables, compact form (what the kernel uses) -----------------------------------------------------------

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(128)
     lrf_eigen_kernel(int64_t nq, const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
-                     double* __restrict__ lrf) {
+                     double* __restrict__ lrf, float* __restrict__ frame32) {
+  // frame32 (optional, 9 floats per query): float32 images of the raw x, y = z cross x, z for shot_fast_kernel
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (q >= nq) return;
   if (counts ? counts[q] == 0 : offsets[q + 1] == offsets[q]) return;  // empty: the votes step writes the identity
@@ -63,6 +64,14 @@ __global__ void __launch_bounds__(128)
   eigh3(m, eval, evec);
   lrf[9 * q + 0] = evec[2][0]; lrf[9 * q + 1] = evec[2][1]; lrf[9 * q + 2] = evec[2][2];  // x: largest eigenvalue
   lrf[9 * q + 3] = evec[0][0]; lrf[9 * q + 4] = evec[0][1]; lrf[9 * q + 5] = evec[0][2];  // z: smallest eigenvalue
+  if (frame32 != nullptr) {
+    const double* x = evec[2];
+    const double* z = evec[0];
+    float* f = frame32 + 9 * q;
+    f[0] = float(x[0]); f[1] = float(x[1]); f[2] = float(x[2]);
+    f[3] = float(z[1] * x[2] - z[2] * x[1]); f[4] = float(z[2] * x[0] - z[0] * x[2]); f[5] = float(z[0] * x[1] - z[1] * x[0]);
+    f[6] = float(z[0]); f[7] = float(z[1]); f[8] = float(z[2]);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     search_moments_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius, double r2,
-                          const int64_t* __restrict__ cand_offsets, int32_t* __restrict__ nbr,
+                          const int64_t* __restrict__ cand_offsets, float4* __restrict__ nbr,
                           int32_t* __restrict__ counts, double* __restrict__ lrf,
                           unsigned long long* __restrict__ pair_counter) {
   const int lane = threadIdx.x & 31;
@@ -153,7 +162,8 @@ __global__ void __launch_bounds__(256)
   }
   for (int base = 0; base < total; base += 32) {
     const int v = base + lane;
-    bool hit = false;
+    bool hit = false, zero = false;
+    float off[3] = {0.0f, 0.0f, 0.0f};
     const int pos = pos_next;
     const double4 p = p_next;
     if (v + 32 < total) {
@@ -164,6 +174,8 @@ __global__ void __launch_bounds__(256)
       const double cx = qx - p.x, cy = qy - p.y, cz = qz - p.z;  // second moments do not see the sign
       const double d2 = rdist3(cx, cy, cz);
       hit = d2 <= r2;
+      zero = !(d2 > 0.0);
+      off[0] = float(-cx); off[1] = float(-cy); off[2] = float(-cz);
       if (hit) {
         const double w = radius - sqrt(d2);
         sw += w;
@@ -172,7 +184,12 @@ __global__ void __launch_bounds__(256)
       }
     }
     const unsigned mask = __ballot_sync(kFull, hit);
-    if (hit) nbr[out + __popc(mask & lanemask_lt())] = pos;
+    // list entry: the float32 image of the exact offset p - q (what shot_fast_kernel decides from) and the position;
+    // bit 31 flags a neighbour at distance exactly 0 (the query itself, duplicates): shot.py:213 drops those from
+    // the descriptor, and float32 cannot tell 0 from tiny
+    if (hit)
+      nbr[out + __popc(mask & lanemask_lt())] =
+          make_float4(off[0], off[1], off[2], __uint_as_float(uint32_t(pos) | (zero ? 0x80000000u : 0u)));
     out += __popc(mask);
     count += __popc(mask);
   }
@@ -213,12 +230,17 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     shot_descriptor_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius,
                            const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
                            const int32_t* __restrict__ nbr, double* __restrict__ lrf, int fuse_votes, int min_nb,
-                           int normalize, OutT* __restrict__ out) {
+                           int normalize, OutT* __restrict__ out, const int32_t* __restrict__ worklist,
+                           const int32_t* __restrict__ work_count, int nbr_stride) {
   // counts == nullptr: classic CSR, neighbours of q are nbr[offsets[q] .. offsets[q+1]). Otherwise a padded list:
   // nbr[offsets[q] .. offsets[q] + counts[q]) (the fused single-scale driver).
   // fuse_votes: lrf[9q + 0..5] holds the RAW eigenvectors (x, z) from lrf_eigen_kernel; the sign votes of
   // shot.py:40-45 run here (the second pass over the same neighbours then hits L1) and the final frame is written
   // back to lrf[9q + 0..8].
+  // worklist != nullptr: only the queries worklist[0 .. *work_count) (the ones shot_fast_kernel handed over).
+  // nbr_stride = 4: `nbr` is the fused driver's list of 16-byte entries (float32 offset, position | flag << 31), the
+  // position is word 3 of an entry and offsets / counts are in entries; the flag (neighbour at distance 0) is masked:
+  // this kernel decides that in float64 itself. nbr_stride = 1: plain int32 positions.
   extern __shared__ uint32_t table_mem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -226,7 +248,10 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
   float* vals = reinterpret_cast<float*>(keys + kKeyCount);
   const int64_t warps_total = int64_t(gridDim.x) * kShotWarpsPerBlock;
   const double inv_radius = 1.0 / radius;
-  for (int64_t q = blockIdx.x * int64_t(kShotWarpsPerBlock) + warp; q < nq; q += warps_total) {
+  const int nbr_word = nbr_stride - 1;
+  const int64_t n_items = worklist != nullptr ? int64_t(*work_count) : nq;
+  for (int64_t item = blockIdx.x * int64_t(kShotWarpsPerBlock) + warp; item < n_items; item += warps_total) {
+    const int64_t q = worklist != nullptr ? int64_t(worklist[item]) : item;
     // values are gated by their keys: only the keys are cleared (16 bytes per lane and store)
     for (int j = lane; j < kKeyCount / 4; j += 32) reinterpret_cast<uint4*>(keys)[j] = make_uint4(0u, 0u, 0u, 0u);
     const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
@@ -244,7 +269,7 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
       double x[3] = {lrf[9 * q], lrf[9 * q + 1], lrf[9 * q + 2]}, z[3] = {lrf[9 * q + 3], lrf[9 * q + 4], lrf[9 * q + 5]};
       int neg_x = 0, neg_z = 0;
       for (int64_t i = begin + lane; i < end; i += 32) {
-        const double4 p = load_pt(g.pts + __ldg(nbr + i));
+        const double4 p = load_pt(g.pts + (__ldg(nbr + i * nbr_stride + nbr_word) & 0x7fffffff));
         const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
         neg_x += (cx * x[0] + cy * x[1] + cz * x[2]) < 0.0;
         neg_z += (cx * z[0] + cy * z[1] + cz * z[2]) < 0.0;
@@ -270,11 +295,11 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
     double4 p_next = make_double4(0, 0, 0, 0), n_next = p_next;
     int s_after = 0;
     if (i < end) {
-      const int s = __ldg(nbr + i);
+      const int s = __ldg(nbr + i * nbr_stride + nbr_word) & 0x7fffffff;
       p_next = load_pt(g.pts + s);
       n_next = load_pt(g.nrm + s);
     }
-    if (i + 32 < end) s_after = __ldg(nbr + i + 32);
+    if (i + 32 < end) s_after = __ldg(nbr + (i + 32) * nbr_stride + nbr_word) & 0x7fffffff;
     __syncwarp();
     for (int64_t base = begin; base < end; base += 32, i += 32) {  // warp-uniform trip count (barriers inside)
       const double4 p = p_next, n = n_next;
@@ -282,7 +307,7 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
         const int s = s_after;
         p_next = load_pt(g.pts + s);
         n_next = load_pt(g.nrm + s);
-        if (i + 64 < end) s_after = __ldg(nbr + i + 64);
+        if (i + 64 < end) s_after = __ldg(nbr + (i + 64) * nbr_stride + nbr_word) & 0x7fffffff;
       }
       ShotDecision d;
       bool active = false;
@@ -367,6 +392,321 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
   }
 }
 
+
+// ---- S2, fast path: float32-filtered decisions -----------------------------------------------------------------------
+// One warp per query with at most 128 neighbours (four per lane, kept in registers; a slot's code is skipped when the
+// query has no neighbour for it). Round 1's kernel (above) issues ~1650 warp instructions per query, half of them
+// float64, re-gathers the neighbours for the frame's sign votes and keeps 11 KB of tables per warp (20 warps per SM).
+// Here:
+//   * in the fused driver the neighbour arrives as the float32 image of the EXACT float64 offset p - q that the search
+//     kernel had in registers (16-byte list entries: offset + position), so nothing is gathered but the float32
+//     normal and all margins are relative (8 u rho); caller-provided lists gather the grid's cell-relative float32
+//     coordinates instead. All decisions come from float32 with proven margins (sf_math.cuh::shot_decide_fast);
+//   * the sign votes need no second pass: the neighbours are projected on the RAW eigenvectors once, and flipping
+//     an axis afterwards only negates coordinates (x -> -x negates X and Y = (z cross x) . c exactly);
+//   * keys are unique inside a query (23 bits of distance + 7 bits of list position): one fire-and-forget shared
+//     atomicMax per (neighbour, statement group), and a single re-read tells every lane whether it is THE winner;
+//   * values are accumulated directly into the 352 output bins in five sub-phases (own-bin statements, radial
+//     partner, elevation partner, statement 1, statement 9), each with at most one writer per bin: a fixed order
+//     of float additions, bit-reproducible, no value tables and no assembly pass: 5.6 KB of shared memory per warp.
+// A query goes to the exact kernel above (through `worklist`) when it has more than 128 neighbours, when a decision
+// of one of its neighbours sits inside its float32 margin, or when two neighbours that compete for a bin are closer
+// in distance than float32 can order (`amb_margin`).
+constexpr int kFastSlots = 4;
+constexpr int kFastMaxK = 32 * kFastSlots;
+constexpr int kFastWarpsPerBlock = 8;
+constexpr int kFastTableWords = kKeyCount + kShotLen;  // three key tables + the output bins
+constexpr int kFastWordsPerWarp = kFastTableWords + 4;   // + the trash word losers write to (16-byte padding)
+constexpr float kFastN2 = 1.001f;                        // unit normals up to rounding
+static_assert(kFastMaxK <= (1 << kFastIndexBits), "a neighbour's list position must fit the key's index bits");
+
+struct FastParams {
+  float radius, inv_radius, edge32;
+  float e_rel;          // records: bound on the error of rho, X, Y, Z relative to rho (8 u)
+  float e_abs;          // gathered coordinates: absolute bound (24 u edge)
+  float w_min;          // gathered coordinates: weights are left to float64 below this rho / hypot(X, Y)
+  uint32_t amb_margin;  // in units of the 23-bit distance part of a key
+  int fuse_votes, write_frame, min_nb, normalize;
+};
+
+// Shared-memory accesses by 32-bit address (the kernel keeps addresses, not bins, per neighbour).
+__device__ __forceinline__ uint32_t smem_ld_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float smem_ld_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void smem_st_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void smem_red_max(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// kRecords: `list` holds the fused driver's float4 entries (float32 offset, position | zero-distance flag << 31);
+// otherwise int32 cell-sorted positions of a caller's CSR (then `frame32` is null and lrf holds the FINAL frames).
+template <typename OutT, bool kRecords, int kMinBlocks>
+__global__ void __launch_bounds__(kFastWarpsPerBlock * 32, kMinBlocks)
+    shot_fast_kernel(GridView g, const double* __restrict__ queries, int64_t nq, const int64_t* __restrict__ offsets,
+                     const int32_t* __restrict__ counts, const void* __restrict__ list, double* __restrict__ lrf,
+                     const float* __restrict__ frame32, FastParams fp, OutT* __restrict__ out,
+                     int32_t* __restrict__ worklist, int32_t* __restrict__ work_count) {
+  extern __shared__ __align__(16) uint32_t table_mem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint32_t* keys = table_mem + warp * kFastWordsPerWarp;
+  float* desc = reinterpret_cast<float*>(keys + kKeyCount);
+  const uint32_t keys_addr = uint32_t(__cvta_generic_to_shared(keys));
+  const uint32_t trash = keys_addr + uint32_t(kFastTableWords) * 4u;
+  const int64_t warps_total = int64_t(gridDim.x) * kFastWarpsPerBlock;
+  constexpr int kGroups = kShotLen / 4, kGroupRounds = (kGroups + 31) / 32;
+  for (int64_t q = blockIdx.x * int64_t(kFastWarpsPerBlock) + warp; q < nq; q += warps_total) {
+    const int64_t begin = offsets[q];
+    const int K = counts ? counts[q] : int(offsets[q + 1] - begin);
+    if (K > kFastMaxK) {  // too many for four per lane: the exact kernel takes it
+      if (lane == 0) worklist[atomicAdd(work_count, 1)] = int32_t(q);
+      continue;
+    }
+    if (K == 0) {  // shot.py:24-25 (identity frame), :306 (zero row)
+      OutT* row = out + q * kShotLen;
+#pragma unroll
+      for (int j = 0; j < kGroupRounds; ++j)
+        if (lane + 32 * j < kGroups) store_group(row + 4 * (lane + 32 * j), 0.0f, 0.0f, 0.0f, 0.0f);
+      if (fp.fuse_votes && fp.write_frame && lane < 9) lrf[9 * q + lane] = (lane % 4 == 0) ? 1.0 : 0.0;
+      continue;
+    }
+    for (int j = lane; j < kFastTableWords / 4; j += 32) reinterpret_cast<uint4*>(keys)[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0) keys[kFastTableWords] = 0xffffffffu;  // the trash word: never below a key, never equal to one
+    // ---- the frame's axes in float32 (raw eigenvectors when the votes are fused) ----
+    float ax[3], ay[3], az[3];
+    if (kRecords) {  // written by lrf_eigen_kernel: x, y = z cross x, z
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ax[a] = __ldg(frame32 + 9 * q + a);
+        ay[a] = __ldg(frame32 + 9 * q + 3 + a);
+        az[a] = __ldg(frame32 + 9 * q + 6 + a);
+      }
+    } else {  // final frame, row-major, columns [x y z]
+      const double* frame = lrf + 9 * q;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { ax[a] = float(frame[3 * a]); ay[a] = float(frame[3 * a + 1]); az[a] = float(frame[3 * a + 2]); }
+    }
+    // ---- neighbours: offsets, projection on the axes, request of the normals ----
+    float X0[kFastSlots], Y0[kFastSlots], Z0[kFastSlots], R2[kFastSlots];
+    float4 pb[kFastSlots];
+    unsigned valid = 0, zero_bits = 0;
+    bool unsure = false;  // some decision of this lane is inside its float32 margin: the exact kernel takes the query
+    if (kRecords) {
+      const float4* rec4 = static_cast<const float4*>(list) + begin;
+#pragma unroll
+      for (int s = 0; s < kFastSlots; ++s) {
+        X0[s] = Y0[s] = Z0[s] = R2[s] = 0.0f;
+        if (s * 32 < K) {  // (warp-uniform)
+          if (s * 32 + lane < K) {
+            const float4 e = __ldg(rec4 + s * 32 + lane);
+            const uint32_t w = __float_as_uint(e.w);
+            pb[s] = __ldg(g.nrm32 + (w & 0x7fffffffu));
+            const float c[3] = {e.x, e.y, e.z};
+            R2[s] = dot3f(c, c);
+            X0[s] = dot3f(c, ax);
+            Y0[s] = dot3f(c, ay);
+            Z0[s] = dot3f(c, az);
+            valid |= 1u << s;
+            zero_bits |= (w >> 31) << s;
+          }
+        }
+      }
+    } else {
+      const int32_t* nbr = static_cast<const int32_t*>(list) + begin;
+      const double* query = queries + 3 * q;
+      const double qd[3] = {__ldg(query), __ldg(query + 1), __ldg(query + 2)};
+      int cq[3];
+      float lq[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) cq[a] = cell_coord(qd[a], g.origin[a], g.inv_cell, g.dims[a]);
+      shot_cell_local(qd, g.origin, g.cell, cq, lq);
+      const uint32_t cq_bits = shot_cellbits(cq);
+#pragma unroll
+      for (int s = 0; s < kFastSlots; ++s) {
+        X0[s] = Y0[s] = Z0[s] = R2[s] = 0.0f;
+        if (s * 32 < K) {
+          if (s * 32 + lane < K) {
+            const int pos = __ldg(nbr + s * 32 + lane);
+            const float4 e = __ldg(g.xyzc + pos);
+            pb[s] = __ldg(g.nrm32 + pos);
+            const float lp[3] = {e.x, e.y, e.z};
+            float c[3];
+            shot_rel32(lp, __float_as_uint(e.w), lq, cq_bits, fp.edge32, c);
+            R2[s] = dot3f(c, c);
+            X0[s] = dot3f(c, ax);
+            Y0[s] = dot3f(c, ay);
+            Z0[s] = dot3f(c, az);
+            valid |= 1u << s;
+            if (R2[s] == 0.0f) {
+              // no flags in a caller's list: a float32 offset of exactly 0 is the query itself or a duplicate when
+              // the float64 coordinates agree exactly — anything else this close is left to the exact kernel
+              const double4 p = load_pt(g.pts + pos);
+              if (p.x == qd[0] && p.y == qd[1] && p.z == qd[2]) zero_bits |= 1u << s;
+              else unsure = true;
+            }
+          }
+        }
+      }
+    }
+    const unsigned act = valid & ~zero_bits;
+    float fsx = 1.0f, fsz = 1.0f;
+    if (fp.fuse_votes) {  // shot.py:40-45: flip when strictly more neighbours project negatively (distance 0: not negative)
+      int neg_x = 0, neg_z = 0;
+#pragma unroll
+      for (int s = 0; s < kFastSlots; ++s) {
+        if (s * 32 < K) {
+          const bool on = (act >> s) & 1u;
+          // |X0| > e <=> X0^2 > e^2 (records: e = e_rel * rho, so e^2 = e_rel^2 * rho^2)
+          const float e2 = kRecords ? fp.e_rel * fp.e_rel * R2[s] : fp.e_abs * fp.e_abs;
+          unsure = unsure || (on && !(X0[s] * X0[s] > e2 && Z0[s] * Z0[s] > e2));
+          neg_x += __popc(__ballot_sync(kFull, on && X0[s] < 0.0f));
+          neg_z += __popc(__ballot_sync(kFull, on && Z0[s] < 0.0f));
+        }
+      }
+      if (neg_x > K - neg_x) fsx = -1.0f;
+      if (neg_z > K - neg_z) fsz = -1.0f;
+    }
+    __syncwarp();  // the tables are cleared
+    // ---- decisions; one fire-and-forget shared max per (neighbour, statement group) ----
+    // Per neighbour: the shared-memory byte addresses of its three key slots, its key and its five values. The bins
+    // sit kKeyCount words above the key tables, so a value goes to (slot address of group t) + (kKeyCount - t * 352) * 4.
+    uint32_t addr[kFastSlots][3], key[kFastSlots];
+    float v_own[kFastSlots], v_cos[kFastSlots], v_az[kFastSlots], v_rad[kFastSlots], v_el[kFastSlots];
+    int positive = 0;
+#pragma unroll
+    for (int s = 0; s < kFastSlots; ++s) {
+      addr[s][0] = addr[s][1] = addr[s][2] = trash;
+      key[s] = 0u;
+      v_own[s] = v_cos[s] = v_az[s] = v_rad[s] = v_el[s] = 0.0f;
+      if (s * 32 < K) {
+        const bool on = (act >> s) & 1u;
+        if (on) {
+          const float nv[3] = {pb[s].x, pb[s].y, pb[s].z};
+          const float inv_rho = sf_rsqrtf(fmaxf(R2[s], 1e-37f)), rho = R2[s] * inv_rho;
+          ShotFastMargins m;
+          m.e_loc = kRecords ? fp.e_rel * rho : fp.e_abs;
+          m.e_rho = m.e_loc;
+          m.w_rho_min = kRecords ? 0.0f : fp.w_min;
+          m.w_xy_min = kRecords ? 0.01f * rho : fp.w_min;
+          m.n2 = kFastN2;
+          ShotDecision d;
+          // (the cosine margin assumes |n|^2 <= kFastN2: longer normals are left to the exact kernel)
+          const bool sure = shot_decide_fast(fsx * X0[s], fsx * fsz * Y0[s], fsz * Z0[s], fsz * dot3f(nv, az), rho, inv_rho,
+                                             fp.radius, fp.inv_radius, m, d) &&
+                            dot3f(nv, nv) <= kFastN2;
+          unsure = unsure || !sure;
+          if (sure) {
+            const ShotFastRecord r = shot_fast_record(d, uint32_t(s * 32 + lane));
+            key[s] = r.key;
+            v_own[s] = r.v_own; v_cos[s] = r.v_cos; v_az[s] = r.v_az; v_rad[s] = r.v_rad; v_el[s] = r.v_el;
+            addr[s][0] = keys_addr + 4u * uint32_t(kKeyOwn + d.own);
+            addr[s][1] = keys_addr + 4u * uint32_t(kKeyCos + d.cos_nb);
+            addr[s][2] = keys_addr + 4u * uint32_t(kKeyAz + d.az_nb);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) smem_red_max(addr[s][t], key[s]);
+          }
+        }
+        positive += __popc(__ballot_sync(kFull, on));
+      }
+    }
+    __syncwarp();  // the shared maxima are ordered before the reads below
+    if (__any_sync(kFull, unsure)) {
+      if (lane == 0) worklist[atomicAdd(work_count, 1)] = int32_t(q);
+      continue;
+    }
+    // ---- winners (keys are unique: equality = THE winner) and competitors float32 cannot order ----
+    // A slot that did not win (or holds no neighbour) is redirected to the warp's trash word, so that the value
+    // phases below run without branches: every lane does load - add - store, losers on the trash word.
+    bool amb = false;
+    const uint32_t amb_span = (fp.amb_margin << kFastIndexBits) | ((1u << kFastIndexBits) - 1u);
+#pragma unroll
+    for (int s = 0; s < kFastSlots; ++s) {
+      if (s * 32 < K) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t o = smem_ld_u32(addr[s][t]);  // >= key[s] (the trash word holds 0xffffffff)
+          amb = amb || (o - key[s] - 1u < amb_span && key[s] != 0u);  // a winner at most amb_span above: unordered
+          addr[s][t] = o == key[s] ? addr[s][t] + uint32_t(kKeyCount - t * kShotLen) * 4u : trash;
+        }
+      }
+    }
+    // ---- values, one writer per bin and sub-phase ----
+#pragma unroll
+    for (int s = 0; s < kFastSlots; ++s)
+      if (s * 32 < K) smem_st_f32(addr[s][0], v_own[s]);  // statements 2 + 5 + 8 + 10
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {  // radial partner (statement 3 or 4), then elevation partner (6 or 7)
+#pragma unroll
+      for (int s = 0; s < kFastSlots; ++s) {
+        if (s * 32 < K) {
+          // the own-bin winner's partner bin: its key slot is the own slot's address with bit 2 (3) flipped
+          const bool own_win = addr[s][0] != trash;
+          const uint32_t pbin = (addr[s][0] ^ (4u << t));                       // partner's VALUE slot
+          const uint32_t pk = smem_ld_u32(own_win ? pbin - uint32_t(kKeyCount) * 4u : trash);  // its own-group key
+          const uint32_t hi = max(pk, key[s]), lo = min(pk, key[s]);
+          amb = amb || (own_win && hi - lo <= amb_span);
+          const float v = t == 0 ? v_rad[s] : v_el[s];
+          const uint32_t dst = (own_win && key[s] > pk && v != 0.0f) ? pbin : trash;
+          smem_st_f32(dst, smem_ld_f32(dst) + v);
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int s = 0; s < kFastSlots; ++s)
+      if (s * 32 < K) smem_st_f32(addr[s][1], smem_ld_f32(addr[s][1]) + v_cos[s]);  // statement 1
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kFastSlots; ++s)
+      if (s * 32 < K) smem_st_f32(addr[s][2], smem_ld_f32(addr[s][2]) + v_az[s]);  // statement 9
+    __syncwarp();
+    if (__any_sync(kFull, amb)) {  // float32 cannot order two competitors: the exact kernel redoes the query
+      if (lane == 0) worklist[atomicAdd(work_count, 1)] = int32_t(q);
+      continue;
+    }
+    // ---- norm + row ----
+    float4 v[kGroupRounds];
+    float sq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kGroupRounds; ++j) {
+      v[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (lane + 32 * j < kGroups) v[j] = reinterpret_cast<const float4*>(desc)[lane + 32 * j];
+      sq = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, sq))));
+    }
+    sq = warp_sum(sq);
+    const bool keep = positive > fp.min_nb && sq > 0.0f;  // shot.py:212, :301-306
+    const float inv = keep ? (fp.normalize ? rsqrtf(sq) : 1.0f) : 0.0f;
+    OutT* row = out + q * kShotLen;
+#pragma unroll
+    for (int j = 0; j < kGroupRounds; ++j)
+      if (lane + 32 * j < kGroups)
+        store_group(row + 4 * (lane + 32 * j), v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+    if (fp.fuse_votes && fp.write_frame) {  // the final frame replaces the raw eigenvectors (every lane has read them)
+      const double* frame = lrf + 9 * q;
+      const double sx = double(fsx), sz = double(fsz);
+      const double x[3] = {sx * frame[0], sx * frame[1], sx * frame[2]}, z[3] = {sz * frame[3], sz * frame[4], sz * frame[5]};
+      const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+      __syncwarp();
+      if (lane < 3) {
+        lrf[9 * q + 3 * lane + 0] = lane == 0 ? x[0] : (lane == 1 ? x[1] : x[2]);
+        lrf[9 * q + 3 * lane + 1] = lane == 0 ? y[0] : (lane == 1 ? y[1] : y[2]);
+        lrf[9 * q + 3 * lane + 2] = lane == 0 ? z[0] : (lane == 1 ? z[1] : z[2]);
+      }
+    }
+    __syncwarp();  // all lanes have read the tables before the next query clears them
+  }
+}
+
 }  // namespace sf
 
 using namespace sf;
@@ -379,7 +719,7 @@ extern "C" int sf_shot_lrf(sf_grid* g, const double* queries, int64_t nq, double
   if (nq == 0) return SF_OK;
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
   lrf_moments_kernel<<<warp_blocks, 256, 0, stream>>>(g->view(), queries, nq, radius, offsets, nbr, lrf);
-  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, offsets, nullptr, lrf);
+  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, offsets, nullptr, lrf, nullptr);
   lrf_votes_kernel<<<warp_blocks, 256, 0, stream>>>(g->view(), queries, nq, offsets, nbr, lrf);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
@@ -412,26 +752,103 @@ extern "C" int sf_profile_read(float* ms_out) {
   return SF_OK;
 }
 
+static int64_t g_last_deferred = 0;
+
+// Queries the fast kernel handed to the exact kernel in the last sf_shot_single_scale call that asked for `pairs_host`.
+extern "C" int sf_shot_last_deferred(int64_t* deferred) {
+  SF_REQUIRE(deferred != nullptr, SF_ERR_ARG, "sf_shot_last_deferred: null output");
+  *deferred = g_last_deferred;
+  return SF_OK;
+}
+
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr && v[0] == '1';
+}
+
+// Descriptors of nq queries: shot_fast_kernel on everything, then the exact kernel on the queries the fast one handed
+// over (more than 128 neighbours, a decision inside its float32 margin, or two competitors float32 cannot order).
+// SF_SHOT_EXACT=1 sends every query to the exact kernel (the tests compare the two).
+//   records == false : `list` = int32 positions of a CSR (offsets[nq + 1]), lrf = the final frames
+//   records == true  : the fused driver's padded list of float4 entries (offsets + counts), lrf = raw eigenvectors,
+//                      frame32 = their float32 images (lrf_eigen_kernel)
+//   worklist / work_count : nq int32 + one int32 of scratch (work_count zeroed here)
 static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, double radius, const int64_t* offsets,
-                             const int32_t* counts, const int32_t* nbr, double* lrf, int fuse_votes, int min_nb,
-                             int normalize, void* out, int out_is_f64, cudaStream_t stream) {
+                             const int32_t* counts, const void* list, bool records, double* lrf, const float* frame32,
+                             int write_frame, int min_nb, int normalize, void* out, int out_is_f64, int32_t* worklist,
+                             int32_t* work_count, cudaStream_t stream) {
   const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
+  const size_t fast_smem = size_t(kFastWarpsPerBlock) * kFastWordsPerWarp * 4;
   SF_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, SF_ERR_ARG, "SHOT output rows must be 16-byte aligned");
+  SF_REQUIRE(nq < (int64_t(1) << 31), SF_ERR_ARG, "SHOT: %lld queries in one call", (long long)nq);
   static bool configured = false;
   if (!configured) {
     SF_CUDA(cudaFuncSetAttribute(shot_descriptor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     SF_CUDA(cudaFuncSetAttribute(shot_descriptor_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured = true;
   }
-  // persistent-style launch: 148 SMs x 5 resident blocks (44 KB shared memory each), capped by the work
+  const bool exact_only = env_flag("SF_SHOT_EXACT");
+  const int fuse_votes = records ? 1 : 0;
+  const GridView view = g->view();
+  if (!exact_only) {
+    FastParams fp;
+    const double u = 5.9604645e-8;  // 2^-24; the bounds below are sf_math.cuh's, rounded up
+    fp.radius = float(radius);
+    fp.inv_radius = float(1.0 / radius);
+    fp.edge32 = float(g->cell);
+    fp.e_rel = float(8.0 * u * 1.0001);
+    fp.e_abs = float(24.0 * u * g->cell * 1.0001);
+    fp.w_min = float(0.01 * radius);
+    // two keys, each within (bound on rho) / radius of the exact 23-bit distance part, + the roundings of the scaling
+    const double rho_err_units = (records ? 8.0 * u : 24.0 * u * g->cell / radius) * 8388608.0 + 1.5;
+    fp.amb_margin = uint32_t(2.0 * rho_err_units + 1.0);
+    fp.fuse_votes = fuse_votes;
+    fp.write_frame = write_frame;
+    fp.min_nb = min_nb;
+    fp.normalize = normalize;
+    SF_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), stream));
+    // persistent: 148 SMs x resident blocks of 8 warps (45 KB of tables each), capped by the work
+    const int64_t needed = (nq + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock;
+    auto launch = [&](auto kernel, auto* typed_out, int per_sm) -> cudaError_t {
+      cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem));
+      if (err != cudaSuccess) return err;
+      const unsigned blocks = unsigned(needed < 148 * per_sm ? needed : 148 * per_sm);
+      kernel<<<blocks, kFastWarpsPerBlock * 32, fast_smem, stream>>>(view, queries, nq, offsets, counts, list, lrf, frame32, fp,
+                                                                    typed_out, worklist, work_count);
+      return cudaGetLastError();
+    };
+    // SF_FAST_BLOCKS = resident blocks per SM the kernel is compiled for (2: 128 registers, 3: 80, 4: 64): tuning only
+    const char* blocks_env = getenv("SF_FAST_BLOCKS");
+    const int per_sm = blocks_env != nullptr ? atoi(blocks_env) : 3;
+    float* fo = static_cast<float*>(out);
+    double* dout = static_cast<double*>(out);
+    if (out_is_f64) {
+      if (records) SF_CUDA(launch(shot_fast_kernel<double, true, 3>, dout, 3));
+      else SF_CUDA(launch(shot_fast_kernel<double, false, 3>, dout, 3));
+    } else if (!records) {
+      SF_CUDA(launch(shot_fast_kernel<float, false, 3>, fo, 3));
+    } else if (per_sm == 2) {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 2>, fo, 2));
+    } else if (per_sm == 4) {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 4>, fo, 4));
+    } else {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 3>, fo, 3));
+    }
+  }
+  // exact kernel, persistent-style: 148 SMs x 5 resident blocks (44 KB shared memory each), capped by the work
   const int64_t blocks_needed = (nq + kShotWarpsPerBlock - 1) / kShotWarpsPerBlock;
   const unsigned blocks = unsigned(blocks_needed < 148 * 5 ? blocks_needed : 148 * 5);
+  const int32_t* wl = exact_only ? nullptr : worklist;
+  const int32_t* nbr = static_cast<const int32_t*>(list);
+  const int stride = records ? 4 : 1;
   if (out_is_f64)
     shot_descriptor_kernel<double><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
-        g->view(), queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<double*>(out));
+        view, queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<double*>(out), wl,
+        work_count, stride);
   else
     shot_descriptor_kernel<float><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
-        g->view(), queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<float*>(out));
+        view, queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<float*>(out), wl,
+        work_count, stride);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
@@ -443,8 +860,12 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_descriptor: grid built without normals");
   SF_REQUIRE(queries && offsets && lrf && out && nq >= 0, SF_ERR_ARG, "sf_shot_descriptor: bad arguments");
   if (nq == 0) return SF_OK;
-  return launch_descriptor(g, queries, nq, radius, offsets, nullptr, nbr, const_cast<double*>(lrf), 0, min_nb, normalize,
-                           out, out_is_f64, stream);
+  int32_t* worklist = nullptr;
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&worklist), size_t(nq + 1) * 4, stream));
+  const int rc = launch_descriptor(g, queries, nq, radius, offsets, nullptr, nbr, false, const_cast<double*>(lrf), nullptr, 0,
+                                   min_nb, normalize, out, out_is_f64, worklist + 1, worklist, stream);
+  cudaFreeAsync(worklist, stream);
+  return rc;
 }
 
 extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t nq, double radius, int32_t min_nb,
@@ -458,7 +879,9 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   if (pairs_host) *pairs_host = 0;
   if (nq == 0) return SF_OK;
   int64_t *cand = nullptr, *cand_offsets = nullptr;
-  int32_t *counts = nullptr, *nbr = nullptr;
+  int32_t* counts = nullptr;
+  float4* nbr = nullptr;  // padded list of 16-byte entries: float32 offset, position | zero-distance flag << 31
+  float* frame32 = nullptr;
   double* lrf = lrf_out;
   void* scan_temp = nullptr;
   size_t scan_bytes = 0;
@@ -471,31 +894,38 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   const GridView view = g->view();
   SF_CUDA(cudaMemsetAsync(cand + nq, 0, 8, stream));
   unsigned long long* pair_counter = nullptr;
+  int32_t* worklist = nullptr;  // [0] = number of queries handed to the exact kernel, then their indices
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pair_counter), 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&worklist), size_t(nq + 1) * 4, stream));
   SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
   candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(view, queries, nq, cand);
   SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, cand, cand_offsets, int(nq + 1), stream));
   int64_t total = 0;
   SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + nq, 8, cudaMemcpyDeviceToHost, stream));
   SF_CUDA(cudaStreamSynchronize(stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * 4, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * sizeof(float4), stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&frame32), size_t(nq) * 9 * sizeof(float), stream));
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
   profile_mark(0, stream);
   search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets, nbr,
                                                         counts, lrf, pair_counter);
   profile_mark(1, stream);
-  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf);
+  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf, frame32);
   profile_mark(2, stream);
-  int rc = launch_descriptor(g, queries, nq, radius, cand_offsets, counts, nbr, lrf, 1, min_nb, normalize, out, out_is_f64,
-                             stream);
+  int rc = launch_descriptor(g, queries, nq, radius, cand_offsets, counts, nbr, true, lrf, frame32, lrf_out != nullptr, min_nb,
+                             normalize, out, out_is_f64, worklist + 1, worklist, stream);
   profile_mark(3, stream);
   if (rc == SF_OK && pairs_host != nullptr) {  // neighbour pairs found (logging / algorithmic-byte accounting)
     unsigned long long pairs = 0;
+    int32_t deferred = 0;
     SF_CUDA(cudaMemcpyAsync(&pairs, pair_counter, 8, cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaMemcpyAsync(&deferred, worklist, 4, cudaMemcpyDeviceToHost, stream));
     SF_CUDA(cudaStreamSynchronize(stream));
     *pairs_host = int64_t(pairs);
+    g_last_deferred = env_flag("SF_SHOT_EXACT") ? nq : int64_t(deferred);
   }
-  void* to_free[] = {cand, cand_offsets, counts, nbr, scan_temp, pair_counter, lrf_out == nullptr ? lrf : nullptr};
+  void* to_free[] = {cand, cand_offsets, counts, nbr, frame32, scan_temp, pair_counter, worklist,
+                     lrf_out == nullptr ? lrf : nullptr};
   for (void* p : to_free)
     if (p) cudaFreeAsync(p, stream);
   return rc;

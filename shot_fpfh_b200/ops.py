@@ -174,6 +174,13 @@ def shot_single_scale(
     return out, lrf, (int(pairs.value) if want_pairs else None)
 
 
+def shot_last_deferred() -> int:
+    """Queries the float32 kernel handed to the float64 kernel in the last `shot_single_scale(want_pairs=True)`."""
+    n = ctypes.c_int64(0)
+    check(lib.sf_shot_last_deferred(ctypes.byref(n)))
+    return int(n.value)
+
+
 def profile_enable(enable: bool) -> None:
     check(lib.sf_profile_enable(int(bool(enable))))
 

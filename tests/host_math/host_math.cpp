@@ -227,4 +227,204 @@ int hm_theta_bin(double ny, double nx, const double* edges, int n) {
   return fpfh_theta_bin(ny, nx, edges, n, double(n) / (edges[n] - edges[0]));
 }
 
+// ---- the fast descriptor kernel (shot.cu::shot_fast_kernel), mirrored for one query ------------------------------
+// records != 0: the fused driver's mode — float32 images of the exact float64 offsets (what search_moments_kernel
+// stores), votes on the RAW eigenvectors (`frame` = raw x, raw z: 6 doubles). records == 0: a caller's list — the
+// grid's cell-relative float32 coordinates, `frame` = the final 3x3 frame (row-major, columns x y z).
+// Then as the kernel: float32-filtered decisions, unique keys, winners by maximum, values added in five sub-phases.
+// Returns 0 and the row when the kernel would keep the query, 1 when it would hand it to the exact kernel
+// (more than 128 neighbours, a decision inside its float32 margin, or two competitors float32 cannot order).
+// stats[0] += neighbours decided, stats[1] += neighbours whose float32 decision was unsure.
+int hm_shot_descriptor_fast(const double* point, const double* nbrs, const double* normals, int k, double radius,
+                            const double* origin, double edge, const double* frame, int records, int normalize,
+                            int min_nb, float* out352, double* frame_out9, long* stats) {
+  if (k > 128) return 1;
+  if (k == 0) {
+    for (int b = 0; b < kShotLen; ++b) out352[b] = 0.0f;
+    return 0;
+  }
+  const double inv_cell = 1.0 / edge;
+  auto cell_of = [&](const double p[3], int c[3]) {
+    for (int a = 0; a < 3; ++a) c[a] = int(floor((p[a] - origin[a]) * inv_cell));
+  };
+  const double u = 5.9604645e-8;
+  const float e_rel = float(8.0 * u * 1.0001), e_abs = float(24.0 * u * edge * 1.0001), w_min = float(0.01 * radius);
+  const float edge32 = float(edge), radius32 = float(radius), inv_radius32 = float(1.0 / radius);
+  const uint32_t amb_margin = uint32_t(2.0 * ((records ? 8.0 * u : 24.0 * u * edge / radius) * 8388608.0 + 1.5) + 1.0);
+  const int fuse_votes = records;
+  float ax[3], ay[3], az[3];
+  if (fuse_votes) {
+    const double* x = frame;
+    const double* z = frame + 3;
+    ay[0] = float(z[1] * x[2] - z[2] * x[1]);
+    ay[1] = float(z[2] * x[0] - z[0] * x[2]);
+    ay[2] = float(z[0] * x[1] - z[1] * x[0]);
+    for (int a = 0; a < 3; ++a) { ax[a] = float(x[a]); az[a] = float(z[a]); }
+  } else {
+    for (int a = 0; a < 3; ++a) { ax[a] = float(frame[3 * a]); ay[a] = float(frame[3 * a + 1]); az[a] = float(frame[3 * a + 2]); }
+  }
+  int cq[3];
+  float lq[3];
+  cell_of(point, cq);
+  shot_cell_local(point, origin, edge, cq, lq);
+  const uint32_t cq_bits = shot_cellbits(cq);
+  std::vector<float> X0(k), Y0(k), Z0(k), C0(k), R2(k), NN(k);
+  std::vector<char> zero(k, 0);
+  bool unsure = false;
+  int neg_x = 0, neg_z = 0;
+  for (int i = 0; i < k; ++i) {
+    float c[3];
+    if (records) {
+      for (int a = 0; a < 3; ++a) c[a] = float(nbrs[3 * i + a] - point[a]);
+      zero[i] = nbrs[3 * i] == point[0] && nbrs[3 * i + 1] == point[1] && nbrs[3 * i + 2] == point[2];
+    } else {
+      int cp[3];
+      float lp[3];
+      cell_of(nbrs + 3 * i, cp);
+      shot_cell_local(nbrs + 3 * i, origin, edge, cp, lp);
+      shot_rel32(lp, shot_cellbits(cp), lq, cq_bits, edge32, c);
+    }
+    R2[i] = dot3f(c, c);
+    X0[i] = dot3f(c, ax); Y0[i] = dot3f(c, ay); Z0[i] = dot3f(c, az);
+    const float nv[3] = {float(normals[3 * i]), float(normals[3 * i + 1]), float(normals[3 * i + 2])};
+    C0[i] = dot3f(nv, az);
+    NN[i] = dot3f(nv, nv);
+    if (!records && R2[i] == 0.0f) {
+      if (nbrs[3 * i] == point[0] && nbrs[3 * i + 1] == point[1] && nbrs[3 * i + 2] == point[2]) zero[i] = 1;
+      else unsure = true;
+    }
+    if (fuse_votes && !zero[i]) {
+      const float e = e_rel * sqrtf(R2[i]);
+      neg_x += X0[i] < 0.0f;
+      neg_z += Z0[i] < 0.0f;
+      unsure = unsure || !(fabsf(X0[i]) > e && fabsf(Z0[i]) > e);
+    }
+  }
+  float fsx = 1.0f, fsz = 1.0f;
+  if (fuse_votes) {
+    if (neg_x > k - neg_x) fsx = -1.0f;
+    if (neg_z > k - neg_z) fsz = -1.0f;
+  }
+  if (frame_out9 != nullptr && fuse_votes) {
+    const double sx = fsx, sz = fsz;
+    const double x[3] = {sx * frame[0], sx * frame[1], sx * frame[2]}, z[3] = {sz * frame[3], sz * frame[4], sz * frame[5]};
+    const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+    for (int a = 0; a < 3; ++a) { frame_out9[3 * a] = x[a]; frame_out9[3 * a + 1] = y[a]; frame_out9[3 * a + 2] = z[a]; }
+  }
+  std::vector<ShotFastRecord> rec(k);
+  std::vector<char> act(k, 0);
+  int positive = 0;
+  for (int i = 0; i < k; ++i) {
+    if (zero[i]) continue;
+    ++positive;
+    const float inv_rho = 1.0f / sqrtf(fmaxf(R2[i], 1e-37f)), rho = R2[i] * inv_rho;
+    ShotFastMargins m;
+    m.e_loc = records ? e_rel * rho : e_abs;
+    m.e_rho = m.e_loc;
+    m.w_rho_min = records ? 0.0f : w_min;
+    m.w_xy_min = records ? 0.01f * rho : w_min;
+    m.n2 = 1.001f;
+    ShotDecision d;
+    const bool sure = shot_decide_fast(fsx * X0[i], fsx * fsz * Y0[i], fsz * Z0[i], fsz * C0[i], rho, inv_rho, radius32,
+                                       inv_radius32, m, d) && NN[i] <= 1.001f;
+    if (stats) { stats[0] += 1; stats[1] += !sure; }
+    unsure = unsure || !sure;
+    if (!sure) continue;
+    rec[i] = shot_fast_record(d, uint32_t(i));
+    act[i] = 1;
+  }
+  if (unsure) return 1;
+  std::vector<uint32_t> keys(kKeyCount, 0u);
+  std::vector<float> desc(kShotLen, 0.0f);
+  for (int i = 0; i < k; ++i)
+    if (act[i])
+      for (int t = 0; t < 3; ++t) {
+        uint32_t& slot = keys[t * kShotLen + ((rec[i].bins >> (9 * t)) & 511u)];
+        if (rec[i].key > slot) slot = rec[i].key;
+      }
+  bool amb = false;
+  std::vector<char> win(3 * k, 0);
+  for (int i = 0; i < k; ++i)
+    if (act[i])
+      for (int t = 0; t < 3; ++t) {
+        const uint32_t o = keys[t * kShotLen + ((rec[i].bins >> (9 * t)) & 511u)];
+        if (o == rec[i].key) win[3 * i + t] = 1;
+        else amb = amb || shot_keys_ambiguous(o, rec[i].key, amb_margin);
+      }
+  for (int i = 0; i < k; ++i)
+    if (win[3 * i]) desc[rec[i].bins & 511u] = rec[i].v_own;
+  for (int t = 0; t < 2; ++t)
+    for (int i = 0; i < k; ++i)
+      if (win[3 * i]) {
+        const uint32_t partner = (rec[i].bins & 511u) ^ uint32_t(1 + t);
+        const uint32_t pk = keys[kKeyOwn + partner], key = rec[i].key;
+        amb = amb || (pk != 0u && shot_keys_ambiguous(pk, key, amb_margin));
+        const float v = t == 0 ? rec[i].v_rad : rec[i].v_el;
+        if (key > pk && v != 0.0f) desc[partner] += v;
+      }
+  for (int i = 0; i < k; ++i)
+    if (win[3 * i + 1]) desc[(rec[i].bins >> 9) & 511u] += rec[i].v_cos;
+  for (int i = 0; i < k; ++i)
+    if (win[3 * i + 2]) desc[(rec[i].bins >> 18) & 511u] += rec[i].v_az;
+  if (amb) return 1;
+  float sq = 0.0f;
+  for (int b = 0; b < kShotLen; ++b) sq += desc[b] * desc[b];
+  const bool keep = positive > min_nb && sq > 0.0f;
+  const float inv = keep ? (normalize ? 1.0f / sqrtf(sq) : 1.0f) : 0.0f;
+  for (int b = 0; b < kShotLen; ++b) out352[b] = desc[b] * inv;
+  return 0;
+}
+
+// shot_decide_fast against shot_decide on n inputs: rows of (X, Y, Z, cosine, rho) in float64 (the exact values) and
+// their float32 images with errors inside the documented bounds; relative != 0: the fused driver's margins (8 u rho),
+// else the gathered coordinates' (24 u edge, weights guarded at 1 % of the radius).
+// stats[0] = sure, stats[1] = sure but a bin / sign differs from the float64 decision (must be 0),
+// stats[2] = largest |weight difference| among the sure ones, in 1e-9 units.
+void hm_shot_decide_fast_check(long n, const double* exact5, const float* approx5, double radius, double edge,
+                               int relative, long* stats) {
+  const double u = 5.9604645e-8;
+  stats[0] = stats[1] = stats[2] = 0;
+  for (long i = 0; i < n; ++i) {
+    const double* x = exact5 + 5 * i;
+    const float* f = approx5 + 5 * i;
+    ShotDecision df;
+    ShotFastMargins m;
+    m.e_loc = m.e_rho = relative ? float(8.0 * u * 1.0001) * f[4] : float(24.0 * u * edge * 1.0001);
+    m.w_rho_min = relative ? 0.0f : float(0.01 * radius);
+    m.w_xy_min = relative ? 0.01f * f[4] : float(0.01 * radius);
+    m.n2 = 1.001f;
+    if (!shot_decide_fast(f[0], f[1], f[2], f[3], f[4], 1.0f / f[4], float(radius), float(1.0 / radius), m, df)) continue;
+    ++stats[0];
+    const ShotDecision de = shot_decide(x[0], x[1], x[2], fmin(1.0, fmax(-1.0, x[3])), x[4], radius, 1.0 / radius);
+    if (df.own != de.own || df.cos_nb != de.cos_nb || df.az_nb != de.az_nb || df.ti != de.ti || df.ei != de.ei ||
+        df.saz != de.saz)
+      ++stats[1];
+    float ov_f, ot_f, ov_e, ot_e;
+    shot_elevation_fast(df, ov_f, ot_f);
+    shot_elevation(de, ov_e, ot_e);
+    const double w = fmax(fmax(fabs(double(df.a_cos) - de.a_cos), fabs(double(df.own_shell) - de.own_shell)),
+                          fmax(fmax(fabs(double(df.other_shell) - de.other_shell), fabs(double(shot_azimuth_fast(df)) - shot_azimuth(de))),
+                               fmax(fabs(double(ov_f) - ov_e), fabs(double(ot_f) - ot_e))));
+    if (long(w * 1e9) > stats[2]) stats[2] = long(w * 1e9);
+  }
+}
+
+// the two polynomial weights against libm on float32 inputs: max |difference| over n samples
+double hm_shot_trig_check(long n, const float* fx, const float* fy, const float* ratio) {
+  double worst = 0.0;
+  for (long i = 0; i < n; ++i) {
+    ShotDecision d;
+    d.fx = fx[i]; d.fy = fy[i]; d.ratio = ratio[i];
+    d.ti = azimuth_octant(fx[i], fy[i]);
+    d.ei = ratio[i] > 0.0f;
+    d.saz = 1;
+    float a, b, c, e;
+    shot_elevation_fast(d, a, b);
+    shot_elevation(d, c, e);
+    worst = fmax(worst, fmax(fabs(double(a) - c), fabs(double(b) - e)));
+    worst = fmax(worst, fabs(double(shot_azimuth_fast(d)) - shot_azimuth(d)));
+  }
+  return worst;
+}
+
 }  // extern "C"

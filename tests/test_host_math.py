@@ -138,6 +138,140 @@ def test_shot_sparse_neighbourhood_is_zero(hm, cloud):
     assert not got.any()
 
 
+# ---- the float32-filtered fast path (shot.cu::shot_fast_kernel, sf_math.cuh::shot_decide_fast) ---------------------
+FP = ctypes.POINTER(ctypes.c_float)
+LP = ctypes.POINTER(ctypes.c_long)
+
+
+def _fast_lib(hm):
+    hm.hm_shot_descriptor_fast.argtypes = [DP, DP, DP, ctypes.c_int, ctypes.c_double, DP, ctypes.c_double, DP,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, FP, DP, LP]
+    hm.hm_shot_decide_fast_check.argtypes = [ctypes.c_long, DP, FP, ctypes.c_double, ctypes.c_double, ctypes.c_int, LP]
+    hm.hm_shot_trig_check.argtypes = [ctypes.c_long, FP, FP, FP]
+    hm.hm_shot_trig_check.restype = ctypes.c_double
+    return hm
+
+
+def test_shot_polynomial_weights_match_libm(hm):
+    """atan / asin polynomials of the fast path against atan2f / acosf of the exact path, on float32 inputs."""
+    _fast_lib(hm)
+    rng = np.random.default_rng(11)
+    n = 400_000
+    fx = rng.normal(size=n).astype(np.float32)
+    fy = rng.normal(size=n).astype(np.float32)
+    ratio = np.clip(rng.normal(scale=0.4, size=n), -1, 1).astype(np.float32)
+    ratio[:1000] = np.linspace(-1, 1, 1000, dtype=np.float32)
+    fx[:8] = [1, 1, 0, -1, -1, -1, 0, 1]
+    fy[:8] = [0, 1, 1, 1, 0, -1, -1, -1]
+    worst = hm.hm_shot_trig_check(n, fx.ctypes.data_as(FP), fy.ctypes.data_as(FP), ratio.ctypes.data_as(FP))
+    assert worst < 1e-6, worst  # two float32 evaluations, each within ~3e-7 of the exact angle
+
+
+@pytest.mark.parametrize("relative", [1, 0])
+def test_shot_float32_decisions_never_disagree_with_float64(hm, relative):
+    """
+    Whenever shot_decide_fast is sure, every bin, octant, half-space and interpolation sign equals shot_decide's on
+    the float64 values, for float32 inputs perturbed by up to the documented error bounds — `relative`: the fused
+    driver's (8 u rho on X, Y, Z, rho), else the gathered coordinates' (24 u edge); 7 u on the cosine — including
+    inputs placed on and next to every boundary.
+    """
+    _fast_lib(hm)
+    rng = np.random.default_rng(12)
+    radius, edge = 0.0177, 0.0177 * 1.001
+    n = 1_500_000
+    u = 2.0**-24
+    rho = radius * rng.uniform(0.0, 1.0, n)
+    direction = rng.normal(size=(n, 3))
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    direction[:, 2] *= rng.choice([1.0, 1e-3, 1e-6], n)  # surfaces: Z clusters around 0
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    xyz = direction * rho[:, None]
+    cosine = np.clip(rng.normal(0.8, 0.3, n), -1.2, 1.2)
+    # boundary cases: X = 0, Y = 0, |X| = |Y|, Z = 0, rho = r/2, cosine on bin centres / bin edges / the clip
+    m = 200_000
+    k = rng.integers(0, 7, m)
+    tiny = rng.choice([0.0, 1e-12, 1e-9, 1e-8, 1e-7], m) * rng.choice([-1, 1], m) * radius
+    xyz[:m][k == 0, 0] = tiny[k == 0]
+    xyz[:m][k == 1, 1] = tiny[k == 1]
+    sel = k == 2
+    xyz[:m][sel, 1] = xyz[:m][sel, 0] * rng.choice([-1, 1], sel.sum()) + tiny[sel]
+    xyz[:m][k == 3, 2] = tiny[k == 3]
+    rho = np.linalg.norm(xyz, axis=1)
+    sel = np.zeros(n, bool)
+    sel[:m] = k == 4
+    scale = (radius / 2 + np.resize(tiny, n)) / np.maximum(rho, 1e-300)
+    xyz[sel] *= scale[sel, None]
+    rho = np.linalg.norm(xyz, axis=1)
+    sel[:] = False
+    sel[:m] = k == 5
+    cosine[sel] = (rng.integers(0, 23, sel.sum()) * 0.5 + 0.5) * 2 / 11 - 1 + np.resize(tiny, n)[sel] / radius
+    sel[:] = False
+    sel[:m] = k == 6
+    cosine[sel] = rng.choice([-1.0, 1.0], sel.sum()) * (1 + np.resize(tiny, n)[sel])
+    keep = rho > 0
+    exact = np.ascontiguousarray(np.column_stack([xyz, cosine, rho])[keep])
+    n = exact.shape[0]
+    bound = (7.7 * u * exact[:, 4:5]) if relative else np.full((n, 1), 23.0 * u * edge)
+    noise = rng.uniform(-1, 1, size=(n, 5)) * np.concatenate([bound, bound, bound, np.full((n, 1), 7 * u), bound], axis=1)
+    approx = np.ascontiguousarray((exact + noise).astype(np.float32))
+    stats = (ctypes.c_long * 3)()
+    hm.hm_shot_decide_fast_check(n, _p(exact), approx.ctypes.data_as(FP), radius, edge, relative, stats)
+    print(f"float32 decisions: {stats[0]} of {n} sure, {stats[1]} disagreements, largest weight gap {stats[2] * 1e-9:.2e}")
+    assert stats[1] == 0
+    assert stats[0] > 0.3 * n  # (a third of the samples have Z squashed into the margin, a quarter a clipped cosine)
+    assert stats[2] * 1e-9 < 4e-4  # worst case of the bounds where the weights are worst conditioned (sf_math.cuh)
+
+
+@pytest.mark.parametrize("shift", [None, (4.0e5, -2.5e6, 1.0e4)])
+def test_shot_fast_kernel_mirror_matches_oracle(hm, cloud, shift):
+    """
+    The fast kernel's control flow (cell-relative float32 coordinates, votes on the raw eigenvectors, float32-filtered
+    decisions, unique keys, five value sub-phases) for 500 queries against the bit-exact oracle; queries the kernel
+    would hand to the exact kernel are counted. Second case: the cloud moved far from the origin.
+    """
+    _fast_lib(hm)
+    pts, normals, radius, tree = cloud
+    if shift is not None:
+        pts = pts + np.array(shift)
+        tree = KDTree(pts)
+    origin = pts.min(axis=0)
+    edge = radius * 1.001
+    errs, deferred, deferred2, frame_err = [], 0, 0, 0.0
+    stats = (ctypes.c_long * 2)()
+    for i in range(0, pts.shape[0], 12):
+        nb = tree.query_radius(pts[i : i + 1], radius)[0]
+        rel = pts[nb] - pts[i]
+        w = radius - np.linalg.norm(rel, axis=1)
+        _, vec = np.linalg.eigh(rel.T @ (rel * w[:, None]) / w.sum())
+        raw = np.ascontiguousarray(np.concatenate([vec[:, 2], vec[:, 0]]))
+        lrf = shot_oracle.local_reference_frame(pts[i], pts[nb], radius)
+        want = shot_oracle.shot_descriptor(pts[i], pts[nb], normals[nb], radius, lrf, True, 10)
+        got = np.zeros(352, dtype=np.float32)
+        frame = np.zeros(9)
+        rc = hm.hm_shot_descriptor_fast(
+            _p(pts[i].copy()), _p(np.ascontiguousarray(pts[nb])), _p(np.ascontiguousarray(normals[nb])), nb.shape[0],
+            radius, _p(origin.copy()), edge, _p(raw), 1, 1, 10, got.ctypes.data_as(FP), _p(frame), stats)  # fused mode
+        if rc:
+            deferred += 1
+            continue
+        frame_err = max(frame_err, np.abs(frame.reshape(3, 3) - lrf).max())
+        errs.append(float(rel_l2(got.astype(np.float64), want)))
+        # the same query from the grid's cell-relative coordinates with the final frame (sf_shot_descriptor's mode)
+        got2 = np.zeros(352, dtype=np.float32)
+        rc2 = hm.hm_shot_descriptor_fast(
+            _p(pts[i].copy()), _p(np.ascontiguousarray(pts[nb])), _p(np.ascontiguousarray(normals[nb])), nb.shape[0],
+            radius, _p(origin.copy()), edge, _p(np.ascontiguousarray(lrf)), 0, 1, 10, got2.ctypes.data_as(FP), None, None)
+        deferred2 += rc2
+        assert rc2 or float(rel_l2(got2.astype(np.float64), want)) < 1e-5
+    errs = np.array(errs)
+    print(f"fast mirror: {errs.shape[0]} rows kept, {deferred} handed over, median {np.median(errs):.2e}, max "
+          f"{errs.max():.2e}; unsure neighbours {stats[1]} of {stats[0]}; frame error {frame_err:.1e}")
+    print(f"caller-list mode: {deferred2} more handed over")
+    assert errs.shape[0] + deferred == 500 and deferred < 40 and deferred2 < 40
+    assert (errs > 1e-5).sum() == 0, f"{(errs > 1e-5).sum()} rows above 1e-5, max {errs.max():.3e}"
+    assert frame_err < 1e-12
+
+
 def test_histogram_bin_is_numpy(hm):
     rng = np.random.default_rng(4)
     for n_bins in (5, 11, 7):
