@@ -1,7 +1,7 @@
 """
 Tuning / attribution run for the C2 SHOT step on one B200 (not part of the product, not a benchmark line):
 per-stage CUDA-event times of the fused single-scale driver for each variant of the float32 descriptor kernel
-(SF_FAST_BLOCKS = resident blocks per SM it is compiled for), the number of queries it hands to the float64
+(SF_FAST_SHAPE = resident blocks per SM it is compiled for), the number of queries it hands to the float64
 kernel, and its rows against the float64 kernel's (SF_SHOT_EXACT=1).
 
     python scripts/tune_shot.py [--variants 43,33,34,42,44] [--steps 12] [--n 1000000]
@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="3,2,4")
+    ap.add_argument("--variants", default="82,73,102,63")
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune_shot.json"))
@@ -43,7 +43,7 @@ def main():
     results = {"queries": int(q), "points": int(pts.shape[0])}
 
     def run(tag, env):
-        for k in ("SF_FAST_BLOCKS", "SF_SHOT_EXACT"):
+        for k in ("SF_FAST_SHAPE", "SF_SHOT_EXACT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         out = torch.zeros((q, 352), dtype=torch.float32, device="cuda")
@@ -76,7 +76,7 @@ def main():
     exact = run("exact", {"SF_SHOT_EXACT": "1"})
     exact_norm = exact.double().norm(dim=1).clamp_min(1e-300)
     for v in args.variants.split(","):
-        got = run(f"fast_{v}", {"SF_FAST_BLOCKS": v})
+        got = run(f"fast_{v}", {"SF_FAST_SHAPE": v})
         err = (got.double() - exact.double()).norm(dim=1) / exact_norm
         zero_mismatch = int(((got.abs().sum(dim=1) == 0) != (exact.abs().sum(dim=1) == 0)).sum().item())
         results[f"fast_{v}"].update({"max_rel_l2_vs_exact": float(err.max().item()), "median_rel_l2_vs_exact": float(err.median().item()),

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
     lrf_eigen_kernel(int64_t nq, const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
                      double* __restrict__ lrf, float* __restrict__ frame32) {
-  // frame32 (optional, 9 floats per query): float32 images of the raw x, y = z cross x, z for shot_fast_kernel
+  // frame32 (optional, 12 floats per query, 9 used): float32 images of the raw x, y = z cross x, z for shot_fast_kernel
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (q >= nq) return;
   if (counts ? counts[q] == 0 : offsets[q + 1] == offsets[q]) return;  // empty: the votes step writes the identity
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128)
   if (frame32 != nullptr) {
     const double* x = evec[2];
     const double* z = evec[0];
-    float* f = frame32 + 9 * q;
+    float* f = frame32 + 12 * q;  // (kFrame32Stride: 48 bytes, one bulk copy)
     f[0] = float(x[0]); f[1] = float(x[1]); f[2] = float(x[2]);
     f[3] = float(z[1] * x[2] - z[2] * x[1]); f[4] = float(z[2] * x[0] - z[0] * x[2]); f[5] = float(z[0] * x[1] - z[1] * x[0]);
     f[6] = float(z[0]); f[7] = float(z[1]); f[8] = float(z[2]);
@@ -414,9 +414,11 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
 // in distance than float32 can order (`amb_margin`).
 constexpr int kFastSlots = 4;
 constexpr int kFastMaxK = 32 * kFastSlots;
-constexpr int kFastWarpsPerBlock = 8;
 constexpr int kFastTableWords = kKeyCount + kShotLen;  // three key tables + the output bins
-constexpr int kFastWordsPerWarp = kFastTableWords + 4;   // + the trash word losers write to (16-byte padding)
+constexpr int kFrame32Stride = 12;                          // floats per query of lrf_eigen_kernel's float32 frame (x, y, z, pad)
+// + the trash word losers write to (16-byte padding) + two staging buffers for the coming queries' inputs: 128 list
+// entries, 12 floats of frame, an mbarrier each
+constexpr int kFastWordsPerWarp = kFastTableWords + 4 + 2 * (kFastMaxK * 4 + kFrame32Stride + 4);
 constexpr float kFastN2 = 1.001f;                        // unit normals up to rounding
 static_assert(kFastMaxK <= (1 << kFastIndexBits), "a neighbour's list position must fit the key's index bits");
 
@@ -449,7 +451,7 @@ __device__ __forceinline__ void smem_red_max(uint32_t addr, uint32_t v) {
 
 // kRecords: `list` holds the fused driver's float4 entries (float32 offset, position | zero-distance flag << 31);
 // otherwise int32 cell-sorted positions of a caller's CSR (then `frame32` is null and lrf holds the FINAL frames).
-template <typename OutT, bool kRecords, int kMinBlocks>
+template <typename OutT, bool kRecords, int kFastWarpsPerBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, kMinBlocks)
     shot_fast_kernel(GridView g, const double* __restrict__ queries, int64_t nq, const int64_t* __restrict__ offsets,
                      const int32_t* __restrict__ counts, const void* __restrict__ list, double* __restrict__ lrf,
@@ -464,132 +466,178 @@ __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, kMinBlocks)
   const uint32_t trash = keys_addr + uint32_t(kFastTableWords) * 4u;
   const int64_t warps_total = int64_t(gridDim.x) * kFastWarpsPerBlock;
   constexpr int kGroups = kShotLen / 4, kGroupRounds = (kGroups + 31) / 32;
-  for (int64_t q = blockIdx.x * int64_t(kFastWarpsPerBlock) + warp; q < nq; q += warps_total) {
-    const int64_t begin = offsets[q];
-    const int K = counts ? counts[q] : int(offsets[q + 1] - begin);
-    if (K > kFastMaxK) {  // too many for four per lane: the exact kernel takes it
-      if (lane == 0) worklist[atomicAdd(work_count, 1)] = int32_t(q);
-      continue;
-    }
-    if (K == 0) {  // shot.py:24-25 (identity frame), :306 (zero row)
-      OutT* row = out + q * kShotLen;
+  const uint32_t amb_span = (fp.amb_margin << kFastIndexBits) | ((1u << kFastIndexBits) - 1u);
+
+  // Software pipeline over the warp's queries, two deep: at the top of an iteration the header (list position,
+  // neighbour count) of the query after the next is requested, and one lane asks the TMA unit for the NEXT query's list
+  // entries and frame (two bulk copies into one of the warp's two staging buffers, completion on that buffer's
+  // mbarrier): a whole iteration hides the copy (the 117 MB list comes from DRAM), and no register is carried for it.
+  constexpr int kStageBytes = kFastMaxK * 16 + kFrame32Stride * 4 + 16;  // entries, frame, mbarrier (+ padding)
+  const uint32_t stage_base = keys_addr + uint32_t(kFastTableWords + 4) * 4u;
+  const char* stage_ptr = reinterpret_cast<const char*>(keys + kFastTableWords + 4);
+  uint32_t phase_bits = 0;  // bit b: the parity buffer b's mbarrier completes next
+  if (kRecords) {
+    if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < kGroupRounds; ++j)
-        if (lane + 32 * j < kGroups) store_group(row + 4 * (lane + 32 * j), 0.0f, 0.0f, 0.0f, 0.0f);
-      if (fp.fuse_votes && fp.write_frame && lane < 9) lrf[9 * q + lane] = (lane % 4 == 0) ? 1.0 : 0.0;
-      continue;
+      for (int b = 0; b < 2; ++b)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(stage_base + b * kStageBytes + kFastMaxK * 16 + 48), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int j = lane; j < kFastTableWords / 4; j += 32) reinterpret_cast<uint4*>(keys)[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (lane == 0) keys[kFastTableWords] = 0xffffffffu;  // the trash word: never below a key, never equal to one
-    // ---- the frame's axes in float32 (raw eigenvectors when the votes are fused) ----
-    float ax[3], ay[3], az[3];
-    if (kRecords) {  // written by lrf_eigen_kernel: x, y = z cross x, z
+    __syncwarp();
+  }
+  auto header = [&](int64_t query, int64_t& first, int& count) {
+    first = 0;
+    count = 0;
+    if (query < nq) {
+      first = offsets[query];
+      count = counts ? counts[query] : int(offsets[query + 1] - first);
+    }
+  };
+  auto stage = [&](int64_t query, int64_t first, int count, int buffer) {
+    if (kRecords && count > 0 && count <= kFastMaxK && lane == 0) {
+      const uint32_t dst = stage_base + buffer * kStageBytes, bar = dst + kFastMaxK * 16 + 48;
+      const uint32_t bytes = uint32_t(count) * 16u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes + 48u) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(static_cast<const float4*>(list) + first), "r"(bytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       dst + uint32_t(kFastMaxK) * 16u),
+                   "l"(frame32 + kFrame32Stride * query), "r"(48u), "r"(bar)
+                   : "memory");
+    }
+  };
+  int64_t q = blockIdx.x * int64_t(kFastWarpsPerBlock) + warp;
+  int64_t begin, begin_next;
+  int K, K_next, buffer = 0;
+  header(q, begin, K);
+  stage(q, begin, K, 0);
+  header(q + warps_total, begin_next, K_next);
+  for (; q < nq;) {
+    const int64_t q_next = q + warps_total;
+    stage(q_next, begin_next, K_next, buffer ^ 1);  // (its header was requested an iteration ago)
+    int64_t begin_after;
+    int K_after;
+    header(q_next + warps_total, begin_after, K_after);
+    bool defer = K > kFastMaxK;  // too many for four per lane: the exact kernel takes it
+    const bool work = K > 0 && !defer;
+    uint32_t addr[kFastSlots][3], key[kFastSlots];
+    float v_own[kFastSlots], v_cos[kFastSlots], v_az[kFastSlots], v_rad[kFastSlots], v_el[kFastSlots];
+    float fsx = 1.0f, fsz = 1.0f;
+    int positive = 0;
+    if (work) {
+      for (int j = lane; j < kFastTableWords / 4; j += 32) reinterpret_cast<uint4*>(keys)[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (lane == 0) keys[kFastTableWords] = 0xffffffffu;  // the trash word: never below a key, never equal to one
+      // ---- the frame's axes in float32 (raw eigenvectors when the votes are fused) ----
+      float ax[3], ay[3], az[3];
+      const float4* stage_entries = reinterpret_cast<const float4*>(stage_ptr + buffer * kStageBytes);
+      if (kRecords) {  // staged by the TMA unit: the entries and x, y = z cross x, z of lrf_eigen_kernel
+        const float* stage_axes = reinterpret_cast<const float*>(stage_entries + kFastMaxK);
+        const uint32_t bar = stage_base + buffer * kStageBytes + kFastMaxK * 16 + 48, phase = (phase_bits >> buffer) & 1u;
+        uint32_t done;
+        do {
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t"
+              "}"
+              : "=r"(done)
+              : "r"(bar), "r"(phase)
+              : "memory");
+        } while (!done);
+        phase_bits ^= 1u << buffer;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        ax[a] = __ldg(frame32 + 9 * q + a);
-        ay[a] = __ldg(frame32 + 9 * q + 3 + a);
-        az[a] = __ldg(frame32 + 9 * q + 6 + a);
+        for (int a = 0; a < 3; ++a) { ax[a] = stage_axes[a]; ay[a] = stage_axes[3 + a]; az[a] = stage_axes[6 + a]; }
+      } else {  // final frame, row-major, columns [x y z]
+        const double* frame = lrf + 9 * q;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { ax[a] = float(frame[3 * a]); ay[a] = float(frame[3 * a + 1]); az[a] = float(frame[3 * a + 2]); }
       }
-    } else {  // final frame, row-major, columns [x y z]
-      const double* frame = lrf + 9 * q;
+      // ---- neighbours: offsets, projection on the axes, request of the normals ----
+      float X0[kFastSlots], Y0[kFastSlots], Z0[kFastSlots], R2[kFastSlots];
+      float4 pb[kFastSlots];
+      unsigned valid = 0, zero_bits = 0;
+      bool unsure = false;  // a decision of this lane is inside its float32 margin: the exact kernel takes the query
+      if (kRecords) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { ax[a] = float(frame[3 * a]); ay[a] = float(frame[3 * a + 1]); az[a] = float(frame[3 * a + 2]); }
-    }
-    // ---- neighbours: offsets, projection on the axes, request of the normals ----
-    float X0[kFastSlots], Y0[kFastSlots], Z0[kFastSlots], R2[kFastSlots];
-    float4 pb[kFastSlots];
-    unsigned valid = 0, zero_bits = 0;
-    bool unsure = false;  // some decision of this lane is inside its float32 margin: the exact kernel takes the query
-    if (kRecords) {
-      const float4* rec4 = static_cast<const float4*>(list) + begin;
-#pragma unroll
-      for (int s = 0; s < kFastSlots; ++s) {
-        X0[s] = Y0[s] = Z0[s] = R2[s] = 0.0f;
-        if (s * 32 < K) {  // (warp-uniform)
-          if (s * 32 + lane < K) {
-            const float4 e = __ldg(rec4 + s * 32 + lane);
-            const uint32_t w = __float_as_uint(e.w);
+        for (int s = 0; s < kFastSlots; ++s) {
+          X0[s] = Y0[s] = Z0[s] = R2[s] = 0.0f;
+          if (s * 32 < K) {  // (warp-uniform; inside, every lane computes: a lane past the end re-reads the last entry
+                             // and is masked out where its results would land)
+            const float4 entry = stage_entries[min(s * 32 + lane, K - 1)];
+            const uint32_t w = __float_as_uint(entry.w);
             pb[s] = __ldg(g.nrm32 + (w & 0x7fffffffu));
-            const float c[3] = {e.x, e.y, e.z};
+            const float c[3] = {entry.x, entry.y, entry.z};
             R2[s] = dot3f(c, c);
             X0[s] = dot3f(c, ax);
             Y0[s] = dot3f(c, ay);
             Z0[s] = dot3f(c, az);
-            valid |= 1u << s;
+            if (s * 32 + lane < K) valid |= 1u << s;
             zero_bits |= (w >> 31) << s;
           }
         }
-      }
-    } else {
-      const int32_t* nbr = static_cast<const int32_t*>(list) + begin;
-      const double* query = queries + 3 * q;
-      const double qd[3] = {__ldg(query), __ldg(query + 1), __ldg(query + 2)};
-      int cq[3];
-      float lq[3];
+      } else {
+        const int32_t* nbr = static_cast<const int32_t*>(list) + begin;
+        const double* query = queries + 3 * q;
+        const double qd[3] = {__ldg(query), __ldg(query + 1), __ldg(query + 2)};
+        int cq[3];
+        float lq[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) cq[a] = cell_coord(qd[a], g.origin[a], g.inv_cell, g.dims[a]);
-      shot_cell_local(qd, g.origin, g.cell, cq, lq);
-      const uint32_t cq_bits = shot_cellbits(cq);
+        for (int a = 0; a < 3; ++a) cq[a] = cell_coord(qd[a], g.origin[a], g.inv_cell, g.dims[a]);
+        shot_cell_local(qd, g.origin, g.cell, cq, lq);
+        const uint32_t cq_bits = shot_cellbits(cq);
 #pragma unroll
-      for (int s = 0; s < kFastSlots; ++s) {
-        X0[s] = Y0[s] = Z0[s] = R2[s] = 0.0f;
-        if (s * 32 < K) {
-          if (s * 32 + lane < K) {
-            const int pos = __ldg(nbr + s * 32 + lane);
-            const float4 e = __ldg(g.xyzc + pos);
-            pb[s] = __ldg(g.nrm32 + pos);
-            const float lp[3] = {e.x, e.y, e.z};
-            float c[3];
-            shot_rel32(lp, __float_as_uint(e.w), lq, cq_bits, fp.edge32, c);
-            R2[s] = dot3f(c, c);
-            X0[s] = dot3f(c, ax);
-            Y0[s] = dot3f(c, ay);
-            Z0[s] = dot3f(c, az);
-            valid |= 1u << s;
-            if (R2[s] == 0.0f) {
-              // no flags in a caller's list: a float32 offset of exactly 0 is the query itself or a duplicate when
-              // the float64 coordinates agree exactly — anything else this close is left to the exact kernel
-              const double4 p = load_pt(g.pts + pos);
-              if (p.x == qd[0] && p.y == qd[1] && p.z == qd[2]) zero_bits |= 1u << s;
-              else unsure = true;
+        for (int s = 0; s < kFastSlots; ++s) {
+          X0[s] = Y0[s] = Z0[s] = R2[s] = 0.0f;
+          if (s * 32 < K) {
+            if (s * 32 + lane < K) {
+              const int pos = __ldg(nbr + s * 32 + lane);
+              const float4 e = __ldg(g.xyzc + pos);
+              pb[s] = __ldg(g.nrm32 + pos);
+              const float lp[3] = {e.x, e.y, e.z};
+              float c[3];
+              shot_rel32(lp, __float_as_uint(e.w), lq, cq_bits, fp.edge32, c);
+              R2[s] = dot3f(c, c);
+              X0[s] = dot3f(c, ax);
+              Y0[s] = dot3f(c, ay);
+              Z0[s] = dot3f(c, az);
+              valid |= 1u << s;
+              if (R2[s] == 0.0f) {
+                // no flags in a caller's list: a float32 offset of exactly 0 is the query itself or a duplicate when
+                // the float64 coordinates agree exactly — anything else this close is left to the exact kernel
+                const double4 p = load_pt(g.pts + pos);
+                if (p.x == qd[0] && p.y == qd[1] && p.z == qd[2]) zero_bits |= 1u << s;
+                else unsure = true;
+              }
             }
           }
         }
       }
-    }
-    const unsigned act = valid & ~zero_bits;
-    float fsx = 1.0f, fsz = 1.0f;
-    if (fp.fuse_votes) {  // shot.py:40-45: flip when strictly more neighbours project negatively (distance 0: not negative)
-      int neg_x = 0, neg_z = 0;
+      const unsigned act = valid & ~zero_bits;
+      if (fp.fuse_votes) {  // shot.py:40-45: flip when strictly more neighbours project negatively (distance 0: not negative)
+        // (a projection inside its float32 margin makes the vote unsure: the decisions below test exactly that,
+        // |X| and |Z| against e_loc, on every neighbour that votes)
+        int neg_x = 0, neg_z = 0;
+#pragma unroll
+        for (int s = 0; s < kFastSlots; ++s) {
+          if (s * 32 < K) {
+            const bool on = (act >> s) & 1u;
+            neg_x += __popc(__ballot_sync(kFull, on && X0[s] < 0.0f));
+            neg_z += __popc(__ballot_sync(kFull, on && Z0[s] < 0.0f));
+          }
+        }
+        if (neg_x > K - neg_x) fsx = -1.0f;
+        if (neg_z > K - neg_z) fsz = -1.0f;
+      }
+      __syncwarp();  // the tables are cleared
+      // ---- decisions; one fire-and-forget shared max per (neighbour, statement group) ----
+      // Per neighbour: the shared-memory byte addresses of its three key slots, its key and its five values. The
+      // bins sit kKeyCount words above the key tables: a value goes to (slot of group t) + (kKeyCount - 352 t) words.
 #pragma unroll
       for (int s = 0; s < kFastSlots; ++s) {
         if (s * 32 < K) {
           const bool on = (act >> s) & 1u;
-          // |X0| > e <=> X0^2 > e^2 (records: e = e_rel * rho, so e^2 = e_rel^2 * rho^2)
-          const float e2 = kRecords ? fp.e_rel * fp.e_rel * R2[s] : fp.e_abs * fp.e_abs;
-          unsure = unsure || (on && !(X0[s] * X0[s] > e2 && Z0[s] * Z0[s] > e2));
-          neg_x += __popc(__ballot_sync(kFull, on && X0[s] < 0.0f));
-          neg_z += __popc(__ballot_sync(kFull, on && Z0[s] < 0.0f));
-        }
-      }
-      if (neg_x > K - neg_x) fsx = -1.0f;
-      if (neg_z > K - neg_z) fsz = -1.0f;
-    }
-    __syncwarp();  // the tables are cleared
-    // ---- decisions; one fire-and-forget shared max per (neighbour, statement group) ----
-    // Per neighbour: the shared-memory byte addresses of its three key slots, its key and its five values. The bins
-    // sit kKeyCount words above the key tables, so a value goes to (slot address of group t) + (kKeyCount - t * 352) * 4.
-    uint32_t addr[kFastSlots][3], key[kFastSlots];
-    float v_own[kFastSlots], v_cos[kFastSlots], v_az[kFastSlots], v_rad[kFastSlots], v_el[kFastSlots];
-    int positive = 0;
-#pragma unroll
-    for (int s = 0; s < kFastSlots; ++s) {
-      addr[s][0] = addr[s][1] = addr[s][2] = trash;
-      key[s] = 0u;
-      v_own[s] = v_cos[s] = v_az[s] = v_rad[s] = v_el[s] = 0.0f;
-      if (s * 32 < K) {
-        const bool on = (act >> s) & 1u;
-        if (on) {
           const float nv[3] = {pb[s].x, pb[s].y, pb[s].z};
           const float inv_rho = sf_rsqrtf(fmaxf(R2[s], 1e-37f)), rho = R2[s] * inv_rho;
           ShotFastMargins m;
@@ -603,107 +651,128 @@ __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, kMinBlocks)
           const bool sure = shot_decide_fast(fsx * X0[s], fsx * fsz * Y0[s], fsz * Z0[s], fsz * dot3f(nv, az), rho, inv_rho,
                                              fp.radius, fp.inv_radius, m, d) &&
                             dot3f(nv, nv) <= kFastN2;
-          unsure = unsure || !sure;
-          if (sure) {
-            const ShotFastRecord r = shot_fast_record(d, uint32_t(s * 32 + lane));
-            key[s] = r.key;
-            v_own[s] = r.v_own; v_cos[s] = r.v_cos; v_az[s] = r.v_az; v_rad[s] = r.v_rad; v_el[s] = r.v_el;
-            addr[s][0] = keys_addr + 4u * uint32_t(kKeyOwn + d.own);
-            addr[s][1] = keys_addr + 4u * uint32_t(kKeyCos + d.cos_nb);
-            addr[s][2] = keys_addr + 4u * uint32_t(kKeyAz + d.az_nb);
+          unsure = unsure || (on && !sure);
+          const bool use = on && sure;
+          const ShotFastRecord r = shot_fast_record(d, uint32_t(s * 32 + lane));
+          key[s] = use ? r.key : 0u;
+          v_own[s] = r.v_own; v_cos[s] = r.v_cos; v_az[s] = r.v_az; v_rad[s] = r.v_rad; v_el[s] = r.v_el;
+          // (an unsure decision may hold any bin: its addresses are never formed)
+          addr[s][0] = use ? keys_addr + 4u * uint32_t(kKeyOwn + d.own) : trash;
+          addr[s][1] = use ? keys_addr + 4u * uint32_t(kKeyCos + d.cos_nb) : trash;
+          addr[s][2] = use ? keys_addr + 4u * uint32_t(kKeyAz + d.az_nb) : trash;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) smem_red_max(addr[s][t], key[s]);
-          }
-        }
-        positive += __popc(__ballot_sync(kFull, on));
-      }
-    }
-    __syncwarp();  // the shared maxima are ordered before the reads below
-    if (__any_sync(kFull, unsure)) {
-      if (lane == 0) worklist[atomicAdd(work_count, 1)] = int32_t(q);
-      continue;
-    }
-    // ---- winners (keys are unique: equality = THE winner) and competitors float32 cannot order ----
-    // A slot that did not win (or holds no neighbour) is redirected to the warp's trash word, so that the value
-    // phases below run without branches: every lane does load - add - store, losers on the trash word.
-    bool amb = false;
-    const uint32_t amb_span = (fp.amb_margin << kFastIndexBits) | ((1u << kFastIndexBits) - 1u);
-#pragma unroll
-    for (int s = 0; s < kFastSlots; ++s) {
-      if (s * 32 < K) {
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t o = smem_ld_u32(addr[s][t]);  // >= key[s] (the trash word holds 0xffffffff)
-          amb = amb || (o - key[s] - 1u < amb_span && key[s] != 0u);  // a winner at most amb_span above: unordered
-          addr[s][t] = o == key[s] ? addr[s][t] + uint32_t(kKeyCount - t * kShotLen) * 4u : trash;
+          for (int t = 0; t < 3; ++t) smem_red_max(addr[s][t], key[s]);  // (0 on the trash word: no effect)
+          positive += __popc(__ballot_sync(kFull, on));
         }
       }
+      __syncwarp();  // the shared maxima are ordered before the reads below
+      defer = __any_sync(kFull, unsure);
     }
-    // ---- values, one writer per bin and sub-phase ----
-#pragma unroll
-    for (int s = 0; s < kFastSlots; ++s)
-      if (s * 32 < K) smem_st_f32(addr[s][0], v_own[s]);  // statements 2 + 5 + 8 + 10
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {  // radial partner (statement 3 or 4), then elevation partner (6 or 7)
+    if (work && !defer) {
+      // ---- winners (keys are unique: equality = THE winner) and competitors float32 cannot order ----
+      // A slot that did not win (or holds no neighbour) is redirected to the warp's trash word, so that the value
+      // phases below run without branches: every lane does load - add - store, losers on the trash word.
+      uint32_t closest = 0xffffffffu;  // smallest (winner key - own key - 1) over this lane's losing slots
 #pragma unroll
       for (int s = 0; s < kFastSlots; ++s) {
         if (s * 32 < K) {
-          // the own-bin winner's partner bin: its key slot is the own slot's address with bit 2 (3) flipped
-          const bool own_win = addr[s][0] != trash;
-          const uint32_t pbin = (addr[s][0] ^ (4u << t));                       // partner's VALUE slot
-          const uint32_t pk = smem_ld_u32(own_win ? pbin - uint32_t(kKeyCount) * 4u : trash);  // its own-group key
-          const uint32_t hi = max(pk, key[s]), lo = min(pk, key[s]);
-          amb = amb || (own_win && hi - lo <= amb_span);
-          const float v = t == 0 ? v_rad[s] : v_el[s];
-          const uint32_t dst = (own_win && key[s] > pk && v != 0.0f) ? pbin : trash;
-          smem_st_f32(dst, smem_ld_f32(dst) + v);
+          uint32_t seen[3];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) seen[t] = smem_ld_u32(addr[s][t]);  // >= key[s] (trash: 0xffffffff; no key is 0)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            closest = min(closest, seen[t] - key[s] - 1u);  // (a winner wraps to 0xffffffff)
+            addr[s][t] = seen[t] == key[s] ? addr[s][t] + uint32_t(kKeyCount - t * kShotLen) * 4u : trash;
+          }
         }
       }
+      bool amb = closest < amb_span;  // a winner at most amb_span above one of this lane's keys: unordered
+      // ---- values, one writer per bin and sub-phase (loads of a sub-phase first, then its stores) ----
+#pragma unroll
+      for (int s = 0; s < kFastSlots; ++s)
+        if (s * 32 < K) smem_st_f32(addr[s][0], v_own[s]);  // statements 2 + 5 + 8 + 10
       __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {  // radial partner (statement 3 or 4), then elevation partner (6 or 7)
+        uint32_t dst[kFastSlots], pk[kFastSlots];
+        float cur[kFastSlots];
+#pragma unroll
+        for (int s = 0; s < kFastSlots; ++s)
+          if (s * 32 < K) {
+            // the own-bin winner's partner bin: its value slot is the own value slot's address with bit 2 (3) flipped,
+            // its own-group key sits kKeyCount words below
+            dst[s] = addr[s][0] != trash ? addr[s][0] ^ (4u << t) : trash;
+            pk[s] = smem_ld_u32(dst[s] != trash ? dst[s] - uint32_t(kKeyCount) * 4u : trash);
+          }
+#pragma unroll
+        for (int s = 0; s < kFastSlots; ++s)
+          if (s * 32 < K) {
+            amb = amb || (dst[s] != trash && max(pk[s], key[s]) - min(pk[s], key[s]) <= amb_span);
+            dst[s] = key[s] > pk[s] ? dst[s] : trash;  // (pk of a non-winner: the trash word, above every key)
+            cur[s] = smem_ld_f32(dst[s]);
+          }
+#pragma unroll
+        for (int s = 0; s < kFastSlots; ++s)
+          if (s * 32 < K) smem_st_f32(dst[s], cur[s] + (t == 0 ? v_rad[s] : v_el[s]));
+        __syncwarp();
+      }
+#pragma unroll
+      for (int t = 1; t < 3; ++t) {  // statement 1, then statement 9
+        float cur[kFastSlots];
+#pragma unroll
+        for (int s = 0; s < kFastSlots; ++s)
+          if (s * 32 < K) cur[s] = smem_ld_f32(addr[s][t]);
+#pragma unroll
+        for (int s = 0; s < kFastSlots; ++s)
+          if (s * 32 < K) smem_st_f32(addr[s][t], cur[s] + (t == 1 ? v_cos[s] : v_az[s]));
+        __syncwarp();
+      }
+      defer = __any_sync(kFull, amb);  // float32 cannot order two competitors: the exact kernel redoes the query
     }
-#pragma unroll
-    for (int s = 0; s < kFastSlots; ++s)
-      if (s * 32 < K) smem_st_f32(addr[s][1], smem_ld_f32(addr[s][1]) + v_cos[s]);  // statement 1
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < kFastSlots; ++s)
-      if (s * 32 < K) smem_st_f32(addr[s][2], smem_ld_f32(addr[s][2]) + v_az[s]);  // statement 9
-    __syncwarp();
-    if (__any_sync(kFull, amb)) {  // float32 cannot order two competitors: the exact kernel redoes the query
+    if (defer) {
       if (lane == 0) worklist[atomicAdd(work_count, 1)] = int32_t(q);
-      continue;
-    }
-    // ---- norm + row ----
-    float4 v[kGroupRounds];
-    float sq = 0.0f;
+    } else {
+      // ---- norm + row (K == 0: shot.py:24-25 identity frame, :306 zero row) ----
+      float4 v[kGroupRounds];
+      float sq = 0.0f;
 #pragma unroll
-    for (int j = 0; j < kGroupRounds; ++j) {
-      v[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (lane + 32 * j < kGroups) v[j] = reinterpret_cast<const float4*>(desc)[lane + 32 * j];
-      sq = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, sq))));
-    }
-    sq = warp_sum(sq);
-    const bool keep = positive > fp.min_nb && sq > 0.0f;  // shot.py:212, :301-306
-    const float inv = keep ? (fp.normalize ? rsqrtf(sq) : 1.0f) : 0.0f;
-    OutT* row = out + q * kShotLen;
+      for (int j = 0; j < kGroupRounds; ++j) {
+        v[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (work && lane + 32 * j < kGroups) v[j] = reinterpret_cast<const float4*>(desc)[lane + 32 * j];
+        sq = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, sq))));
+      }
+      sq = warp_sum(sq);
+      const bool keep = positive > fp.min_nb && sq > 0.0f;  // shot.py:212, :301-306
+      const float inv = keep ? (fp.normalize ? rsqrtf(sq) : 1.0f) : 0.0f;
+      OutT* row = out + q * kShotLen;
 #pragma unroll
-    for (int j = 0; j < kGroupRounds; ++j)
-      if (lane + 32 * j < kGroups)
-        store_group(row + 4 * (lane + 32 * j), v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
-    if (fp.fuse_votes && fp.write_frame) {  // the final frame replaces the raw eigenvectors (every lane has read them)
-      const double* frame = lrf + 9 * q;
-      const double sx = double(fsx), sz = double(fsz);
-      const double x[3] = {sx * frame[0], sx * frame[1], sx * frame[2]}, z[3] = {sz * frame[3], sz * frame[4], sz * frame[5]};
-      const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
-      __syncwarp();
-      if (lane < 3) {
-        lrf[9 * q + 3 * lane + 0] = lane == 0 ? x[0] : (lane == 1 ? x[1] : x[2]);
-        lrf[9 * q + 3 * lane + 1] = lane == 0 ? y[0] : (lane == 1 ? y[1] : y[2]);
-        lrf[9 * q + 3 * lane + 2] = lane == 0 ? z[0] : (lane == 1 ? z[1] : z[2]);
+      for (int j = 0; j < kGroupRounds; ++j)
+        if (lane + 32 * j < kGroups)
+          store_group(row + 4 * (lane + 32 * j), v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+      if (fp.fuse_votes && fp.write_frame) {  // the final frame replaces the raw eigenvectors (every lane has read them)
+        if (!work) {
+          if (lane < 9) lrf[9 * q + lane] = (lane % 4 == 0) ? 1.0 : 0.0;
+        } else {
+          const double* frame = lrf + 9 * q;
+          const double sx = double(fsx), sz = double(fsz);
+          const double x[3] = {sx * frame[0], sx * frame[1], sx * frame[2]}, z[3] = {sz * frame[3], sz * frame[4], sz * frame[5]};
+          const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+          __syncwarp();
+          if (lane < 3) {
+            lrf[9 * q + 3 * lane + 0] = lane == 0 ? x[0] : (lane == 1 ? x[1] : x[2]);
+            lrf[9 * q + 3 * lane + 1] = lane == 0 ? y[0] : (lane == 1 ? y[1] : y[2]);
+            lrf[9 * q + 3 * lane + 2] = lane == 0 ? z[0] : (lane == 1 ? z[1] : z[2]);
+          }
+        }
       }
     }
     __syncwarp();  // all lanes have read the tables before the next query clears them
+    q = q_next;
+    begin = begin_next;
+    K = K_next;
+    begin_next = begin_after;
+    K_next = K_after;
+    buffer ^= 1;
   }
 }
 
@@ -778,7 +847,6 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
                              int write_frame, int min_nb, int normalize, void* out, int out_is_f64, int32_t* worklist,
                              int32_t* work_count, cudaStream_t stream) {
   const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
-  const size_t fast_smem = size_t(kFastWarpsPerBlock) * kFastWordsPerWarp * 4;
   SF_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, SF_ERR_ARG, "SHOT output rows must be 16-byte aligned");
   SF_REQUIRE(nq < (int64_t(1) << 31), SF_ERR_ARG, "SHOT: %lld queries in one call", (long long)nq);
   static bool configured = false;
@@ -807,32 +875,41 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
     fp.min_nb = min_nb;
     fp.normalize = normalize;
     SF_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), stream));
-    // persistent: 148 SMs x resident blocks of 8 warps (45 KB of tables each), capped by the work
-    const int64_t needed = (nq + kFastWarpsPerBlock - 1) / kFastWarpsPerBlock;
-    auto launch = [&](auto kernel, auto* typed_out, int per_sm) -> cudaError_t {
+    // persistent: 148 SMs x resident blocks (7.6 KB of tables + staging per warp), capped by the work
+    auto launch = [&](auto kernel, auto* typed_out, int warps, int per_sm) -> cudaError_t {
+      const size_t fast_smem = size_t(warps) * kFastWordsPerWarp * 4;
       cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem));
+      // (no shared-memory carveout preference: the L1 that is left serves the normals' gather — neighbouring queries
+      // run on the same SM — and forcing the maximum carveout cost 10-25 %)
       if (err != cudaSuccess) return err;
+      const int64_t needed = (nq + warps - 1) / warps;
       const unsigned blocks = unsigned(needed < 148 * per_sm ? needed : 148 * per_sm);
-      kernel<<<blocks, kFastWarpsPerBlock * 32, fast_smem, stream>>>(view, queries, nq, offsets, counts, list, lrf, frame32, fp,
-                                                                    typed_out, worklist, work_count);
+      kernel<<<blocks, warps * 32, fast_smem, stream>>>(view, queries, nq, offsets, counts, list, lrf, frame32, fp, typed_out,
+                                                        worklist, work_count);
       return cudaGetLastError();
     };
-    // SF_FAST_BLOCKS = resident blocks per SM the kernel is compiled for (2: 128 registers, 3: 80, 4: 64): tuning only
-    const char* blocks_env = getenv("SF_FAST_BLOCKS");
-    const int per_sm = blocks_env != nullptr ? atoi(blocks_env) : 3;
+    // SF_FAST_SHAPE = <warps per block><resident blocks per SM> the kernel is compiled for: tuning only
+    //   82: 126 registers, 16 warps per SM;  73: 96 registers, 21 warps;  102: 96 registers, 20 warps;
+    //   63: 112 registers, 18 warps;  83: 80 registers, 24 warps (spills)
+    const char* shape_env = getenv("SF_FAST_SHAPE");
+    const int shape = shape_env != nullptr ? atoi(shape_env) : 82;
     float* fo = static_cast<float*>(out);
     double* dout = static_cast<double*>(out);
     if (out_is_f64) {
-      if (records) SF_CUDA(launch(shot_fast_kernel<double, true, 3>, dout, 3));
-      else SF_CUDA(launch(shot_fast_kernel<double, false, 3>, dout, 3));
+      if (records) SF_CUDA(launch(shot_fast_kernel<double, true, 8, 2>, dout, 8, 2));
+      else SF_CUDA(launch(shot_fast_kernel<double, false, 8, 2>, dout, 8, 2));
     } else if (!records) {
-      SF_CUDA(launch(shot_fast_kernel<float, false, 3>, fo, 3));
-    } else if (per_sm == 2) {
-      SF_CUDA(launch(shot_fast_kernel<float, true, 2>, fo, 2));
-    } else if (per_sm == 4) {
-      SF_CUDA(launch(shot_fast_kernel<float, true, 4>, fo, 4));
+      SF_CUDA(launch(shot_fast_kernel<float, false, 8, 2>, fo, 8, 2));
+    } else if (shape == 73) {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 7, 3>, fo, 7, 3));
+    } else if (shape == 102) {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 10, 2>, fo, 10, 2));
+    } else if (shape == 63) {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 6, 3>, fo, 6, 3));
+    } else if (shape == 83) {
+      SF_CUDA(launch(shot_fast_kernel<float, true, 8, 3>, fo, 8, 3));
     } else {
-      SF_CUDA(launch(shot_fast_kernel<float, true, 3>, fo, 3));
+      SF_CUDA(launch(shot_fast_kernel<float, true, 8, 2>, fo, 8, 2));
     }
   }
   // exact kernel, persistent-style: 148 SMs x 5 resident blocks (44 KB shared memory each), capped by the work
@@ -904,7 +981,7 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + nq, 8, cudaMemcpyDeviceToHost, stream));
   SF_CUDA(cudaStreamSynchronize(stream));
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * sizeof(float4), stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&frame32), size_t(nq) * 9 * sizeof(float), stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&frame32), size_t(nq) * 12 * sizeof(float), stream));
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
   profile_mark(0, stream);
   search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets, nbr,
