@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 4
+#define SF_ABI_VERSION 5
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -53,6 +53,15 @@ int sf_grid_destroy(sf_grid* grid);
 int sf_grid_build(sf_grid* grid, const double* xyz_dev, const double* normals_dev, int64_t n, double radius,
                   void* stream);
 int sf_grid_info(const sf_grid* grid, int64_t* n, int64_t* ncells, double* cell_edge, int32_t* dims3);
+/* Calls without host synchronisation, for a caller that repeats the same work on one handle (a loop over time steps,
+ * blocks of queries, a benchmark). `mode` bit 0: sf_grid_build on the same number of points and the same radius as the
+ * handle's last synchronising build assumes that build's box (for rebuilding the SAME cloud); bit 1: sf_shot_single_scale
+ * sizes its neighbour list from its last synchronising call on this cloud instead of reading the size back. Both assumptions are CHECKED ON THE DEVICE: when one
+ * fails the kernels of these calls do nothing, and sf_grid_poll — to be called after synchronising the stream, before
+ * the results are used — reports a non-zero status (1: a point outside the assumed box, 2: neighbour list too small)
+ * and returns the handle to synchronising calls; the caller then simply repeats its calls. */
+int sf_grid_set_speculative(sf_grid* grid, int32_t mode);
+int sf_grid_poll(sf_grid* grid, int32_t* status);
 /* Copies perm[n] (cell-sorted position -> original index) and/or its inverse into caller buffers (NULL = skip). */
 int sf_grid_permutation(const sf_grid* grid, int32_t* perm_out_dev, int32_t* inv_perm_out_dev, void* stream);
 
@@ -126,7 +135,7 @@ int sf_shot_descriptor(sf_grid* grid, const double* queries_dev, int64_t nq, dou
  * Same results as sf_radius_* + sf_shot_lrf + sf_shot_descriptor, but the neighbour list stays an internal (padded)
  * temporary: ONE pass over the candidate cells finds the neighbours and accumulates the frame's moments, and the sign
  * votes run inside the descriptor kernel. lrf_out_dev (nq,3,3) and pairs_host (number of neighbour pairs found) are
- * optional. Synchronises `stream` once (to size the temporary). */
+ * optional. Synchronises `stream` once (to size the temporary) unless the handle is in speculative mode (above). */
 int sf_shot_single_scale(sf_grid* grid, const double* queries_dev, int64_t nq, double radius,
                          int32_t min_neighborhood_size, int32_t normalize, void* out_dev, int32_t out_is_f64,
                          double* lrf_out_dev, int64_t* pairs_host, void* stream);

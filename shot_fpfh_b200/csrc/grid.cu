@@ -85,6 +85,18 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xy
   }
 }
 
+// Speculative build: the box of a previous build is assumed; status = 1 when a point would fall outside its cells.
+__global__ void bbox_check_kernel(const unsigned long long* box, GridView g, int32_t* status) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  bool ok = true;
+  for (int a = 0; a < 3; ++a) {
+    const double lo = from_ordered_bits(box[a]), hi = from_ordered_bits(box[3 + a]);
+    ok = ok && isfinite(lo) && isfinite(hi);
+    ok = ok && floor((lo - g.origin[a]) * g.inv_cell) >= 0.0 && floor((hi - g.origin[a]) * g.inv_cell) <= double(g.dims[a] - 1);
+  }
+  if (!ok) *status = 1;
+}
+
 // ---- cell keys + per-cell histogram ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     key_kernel(const double* __restrict__ xyz, int64_t n, GridView g, uint32_t* __restrict__ keys,
@@ -271,12 +283,37 @@ static void free_all(sf_grid* g) {
   cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->xyzc); cudaFree(g->nrm32); cudaFree(g->perm); cudaFree(g->inv_perm);
   cudaFree(g->cell_start); cudaFree(g->cell_count); cudaFree(g->keys_in); cudaFree(g->keys_out);
   cudaFree(g->vals_in); cudaFree(g->bbox); cudaFree(g->cub_temp);
+  cudaFree(g->status_dev);
+  if (g->status_host) cudaFreeHost(g->status_host);
+  cudaFree(g->shot_cand); cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
+  cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_pairs); cudaFree(g->shot_scan_temp);
+  cudaFree(g->shot_nbr);
 }
 
 extern "C" int sf_grid_destroy(sf_grid* g) {
   if (g == nullptr) return SF_OK;
   free_all(g);
   delete g;
+  return SF_OK;
+}
+
+static int build_cells(sf_grid* g, const double* xyz, const double* normals, int64_t n, cudaStream_t stream);
+
+extern "C" int sf_grid_set_speculative(sf_grid* g, int32_t enable) {
+  SF_REQUIRE(g != nullptr, SF_ERR_ARG, "sf_grid_set_speculative: null grid");
+  g->speculative = enable;  // bit 0: sf_grid_build assumes the previous box; bit 1: sf_shot_single_scale the list size
+  return SF_OK;
+}
+
+extern "C" int sf_grid_poll(sf_grid* g, int32_t* status) {
+  SF_REQUIRE(g != nullptr && status != nullptr, SF_ERR_ARG, "sf_grid_poll: null argument");
+  *status = g->status_host != nullptr ? *g->status_host : 0;
+  if (*status != 0) {  // what was assumed does not hold: the next calls read everything back again
+    g->sized = false;
+    g->shot_entries_per_query = 0;
+    *g->status_host = 0;
+    SF_CUDA(cudaMemset(g->status_dev, 0, sizeof(int32_t)));
+  }
   return SF_OK;
 }
 
@@ -305,11 +342,24 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   g->n = n;
   g->has_normals = normals != nullptr;
 
-  // 1. bounding box (device) -> host, the only synchronisation of the build
+  if (g->status_dev == nullptr) {
+    SF_CUDA(cudaMalloc(&g->status_dev, sizeof(int32_t)));
+    SF_CUDA(cudaMemset(g->status_dev, 0, sizeof(int32_t)));
+    SF_CUDA(cudaHostAlloc(&g->status_host, sizeof(int32_t), cudaHostAllocDefault));
+    *g->status_host = 0;
+  }
+  // 1. bounding box (device) -> host, the only synchronisation of the build — skipped on a handle in speculative mode
+  //    whose last synchronising build saw the same number of points and the same radius: the box of that build is
+  //    assumed and checked on the device (sf_grid_poll tells)
   unsigned long long* box = reinterpret_cast<unsigned long long*>(g->bbox);
   bbox_init_kernel<<<1, 32, 0, stream>>>(box);
   const int bbox_blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 4));
   bbox_kernel<<<bbox_blocks, 256, 0, stream>>>(xyz, n, box);
+  const bool assume_box = (g->speculative & 1) && g->sized && n == g->sized_n && radius == g->sized_radius;
+  if (assume_box) {
+    bbox_check_kernel<<<1, 32, 0, stream>>>(box, g->view(), g->status_dev);
+    return build_cells(g, xyz, normals, n, stream);
+  }
   unsigned long long hbox[6];
   SF_CUDA(cudaMemcpyAsync(hbox, box, sizeof(hbox), cudaMemcpyDeviceToHost, stream));
   SF_CUDA(cudaStreamSynchronize(stream));
@@ -338,6 +388,16 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   }
   SF_REQUIRE(ncells <= (int64_t(1) << 26), SF_ERR_ARG, "sf_grid_build: %lld cells", (long long)ncells);
   g->ncells = ncells;
+  g->sized = true;
+  g->sized_n = n;
+  g->sized_radius = radius;
+  g->shot_entries_per_query = 0;  // another cloud: the neighbour list is sized afresh
+  return build_cells(g, xyz, normals, n, stream);
+}
+
+// Steps 3-5 of the build for the geometry held by the handle.
+static int build_cells(sf_grid* g, const double* xyz, const double* normals, int64_t n, cudaStream_t stream) {
+  const int64_t ncells = g->ncells;
   if (ncells + 1 > g->cells_capacity) {
     cudaFree(g->cell_start); cudaFree(g->cell_count);
     g->cells_capacity = 0;

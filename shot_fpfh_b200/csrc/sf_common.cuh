@@ -93,6 +93,30 @@ struct sf_grid {
   double* bbox = nullptr;  // 6 doubles, device
   void* cub_temp = nullptr;
   size_t cub_bytes = 0;
+  // ---- calls without host synchronisation (sf_grid_set_speculative, include/shotfpfh_b200.h) ----
+  // A repeated call on the same handle reuses what the previous one learned on the host (the grid's box, the size of
+  // the neighbour list) instead of reading it back; the kernels check the assumption on the device and, when it
+  // fails, raise status_dev and do nothing. The caller reads the verdict with sf_grid_poll after synchronising.
+  int speculative = 0;         // bit 0: builds, bit 1: the fused SHOT driver's list
+  bool sized = false;          // origin / dims / cell below come from a synchronising build of ...
+  int64_t sized_n = 0;         // ... this many points
+  double sized_radius = 0.0;   // ... for this radius
+  int32_t* status_dev = nullptr;   // 0 = fine; 1 = a point outside the assumed box; 2 = neighbour list too small
+  int32_t* status_host = nullptr;  // page-locked mirror, valid after the stream is synchronised
+  // scratch of sf_shot_single_scale, kept between calls
+  int64_t shot_q_capacity = 0;
+  int64_t* shot_cand = nullptr;
+  int64_t* shot_cand_offsets = nullptr;
+  int32_t* shot_counts = nullptr;
+  double* shot_lrf = nullptr;
+  float* shot_frame32 = nullptr;
+  int32_t* shot_worklist = nullptr;
+  unsigned long long* shot_pairs = nullptr;
+  void* shot_scan_temp = nullptr;
+  size_t shot_scan_bytes = 0;
+  float4* shot_nbr = nullptr;
+  int64_t shot_nbr_capacity = 0;     // entries
+  double shot_entries_per_query = 0; // from the last call that read the total back
   sf::GridView view() const {
     sf::GridView v;
     v.pts = pts;

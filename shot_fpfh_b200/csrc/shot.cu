@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(128)
     lrf_eigen_kernel(int64_t nq, const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
-                     double* __restrict__ lrf, float* __restrict__ frame32) {
+                     double* __restrict__ lrf, float* __restrict__ frame32, const int32_t* __restrict__ status = nullptr) {
+  if (status != nullptr && *status != 0) return;
   // frame32 (optional, 12 floats per query, 9 used): float32 images of the raw x, y = z cross x, z for shot_fast_kernel
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (q >= nq) return;
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(256)
     search_moments_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius, double r2,
                           const int64_t* __restrict__ cand_offsets, float4* __restrict__ nbr,
                           int32_t* __restrict__ counts, double* __restrict__ lrf,
-                          unsigned long long* __restrict__ pair_counter) {
+                          unsigned long long* __restrict__ pair_counter, const int32_t* __restrict__ status) {
+  if (status != nullptr && *status != 0) return;  // a speculative call whose assumption failed: nothing is written
   const int lane = threadIdx.x & 31;
   const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (q >= nq) return;
@@ -231,7 +233,9 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
                            const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
                            const int32_t* __restrict__ nbr, double* __restrict__ lrf, int fuse_votes, int min_nb,
                            int normalize, OutT* __restrict__ out, const int32_t* __restrict__ worklist,
-                           const int32_t* __restrict__ work_count, int nbr_stride) {
+                           const int32_t* __restrict__ work_count, int nbr_stride,
+                           const int32_t* __restrict__ status) {
+  if (status != nullptr && *status != 0) return;
   // counts == nullptr: classic CSR, neighbours of q are nbr[offsets[q] .. offsets[q+1]). Otherwise a padded list:
   // nbr[offsets[q] .. offsets[q] + counts[q]) (the fused single-scale driver).
   // fuse_votes: lrf[9q + 0..5] holds the RAW eigenvectors (x, z) from lrf_eigen_kernel; the sign votes of
@@ -456,7 +460,9 @@ __global__ void __launch_bounds__(kFastWarpsPerBlock * 32, kMinBlocks)
     shot_fast_kernel(GridView g, const double* __restrict__ queries, int64_t nq, const int64_t* __restrict__ offsets,
                      const int32_t* __restrict__ counts, const void* __restrict__ list, double* __restrict__ lrf,
                      const float* __restrict__ frame32, FastParams fp, OutT* __restrict__ out,
-                     int32_t* __restrict__ worklist, int32_t* __restrict__ work_count) {
+                     int32_t* __restrict__ worklist, int32_t* __restrict__ work_count,
+                     const int32_t* __restrict__ status) {
+  if (status != nullptr && *status != 0) return;
   extern __shared__ __align__(16) uint32_t table_mem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -845,7 +851,7 @@ static bool env_flag(const char* name) {
 static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, double radius, const int64_t* offsets,
                              const int32_t* counts, const void* list, bool records, double* lrf, const float* frame32,
                              int write_frame, int min_nb, int normalize, void* out, int out_is_f64, int32_t* worklist,
-                             int32_t* work_count, cudaStream_t stream) {
+                             int32_t* work_count, const int32_t* status, cudaStream_t stream) {
   const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
   SF_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, SF_ERR_ARG, "SHOT output rows must be 16-byte aligned");
   SF_REQUIRE(nq < (int64_t(1) << 31), SF_ERR_ARG, "SHOT: %lld queries in one call", (long long)nq);
@@ -885,7 +891,7 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
       const int64_t needed = (nq + warps - 1) / warps;
       const unsigned blocks = unsigned(needed < 148 * per_sm ? needed : 148 * per_sm);
       kernel<<<blocks, warps * 32, fast_smem, stream>>>(view, queries, nq, offsets, counts, list, lrf, frame32, fp, typed_out,
-                                                        worklist, work_count);
+                                                        worklist, work_count, status);
       return cudaGetLastError();
     };
     // SF_FAST_SHAPE = <warps per block><resident blocks per SM> the kernel is compiled for: tuning only
@@ -921,11 +927,11 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
   if (out_is_f64)
     shot_descriptor_kernel<double><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
         view, queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<double*>(out), wl,
-        work_count, stride);
+        work_count, stride, status);
   else
     shot_descriptor_kernel<float><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
         view, queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<float*>(out), wl,
-        work_count, stride);
+        work_count, stride, status);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
@@ -940,9 +946,46 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
   int32_t* worklist = nullptr;
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&worklist), size_t(nq + 1) * 4, stream));
   const int rc = launch_descriptor(g, queries, nq, radius, offsets, nullptr, nbr, false, const_cast<double*>(lrf), nullptr, 0,
-                                   min_nb, normalize, out, out_is_f64, worklist + 1, worklist, stream);
+                                   min_nb, normalize, out, out_is_f64, worklist + 1, worklist, nullptr, stream);
   cudaFreeAsync(worklist, stream);
   return rc;
+}
+
+// Scratch of the fused driver, kept by the grid handle between calls (the stream-ordered pool cost a dozen
+// allocations per call).
+static int shot_reserve_queries(sf_grid* g, int64_t nq) {
+  if (nq <= g->shot_q_capacity) return SF_OK;
+  cudaFree(g->shot_cand); cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
+  cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_scan_temp);
+  g->shot_q_capacity = 0;
+  const int64_t cap = nq + nq / 8 + 64;
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, g->shot_cand, g->shot_cand_offsets, int(cap + 1));
+  SF_CUDA(cudaMalloc(&g->shot_cand, size_t(cap + 1) * 8));
+  SF_CUDA(cudaMalloc(&g->shot_cand_offsets, size_t(cap + 1) * 8));
+  SF_CUDA(cudaMalloc(&g->shot_counts, size_t(cap) * 4));
+  SF_CUDA(cudaMalloc(&g->shot_lrf, size_t(cap) * 9 * 8));
+  SF_CUDA(cudaMalloc(&g->shot_frame32, size_t(cap) * kFrame32Stride * 4));
+  SF_CUDA(cudaMalloc(&g->shot_worklist, size_t(cap + 1) * 4));
+  SF_CUDA(cudaMalloc(&g->shot_scan_temp, scan_bytes + 16));
+  if (g->shot_pairs == nullptr) SF_CUDA(cudaMalloc(&g->shot_pairs, 8));
+  g->shot_scan_bytes = scan_bytes + 16;
+  g->shot_q_capacity = cap;
+  return SF_OK;
+}
+
+static int shot_reserve_entries(sf_grid* g, int64_t entries) {
+  if (entries <= g->shot_nbr_capacity) return SF_OK;
+  cudaFree(g->shot_nbr);
+  g->shot_nbr_capacity = 0;
+  SF_CUDA(cudaMalloc(&g->shot_nbr, size_t(entries) * sizeof(float4)));
+  g->shot_nbr_capacity = entries;
+  return SF_OK;
+}
+
+// status = 2 when the candidate total exceeds what the list can hold (speculative calls only).
+__global__ void list_capacity_kernel(const int64_t* cand_offsets, int64_t nq, int64_t capacity, int32_t* status) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && cand_offsets[nq] > capacity) *status = 2;
 }
 
 extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t nq, double radius, int32_t min_nb,
@@ -955,43 +998,49 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
              "sf_shot_single_scale: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
   if (pairs_host) *pairs_host = 0;
   if (nq == 0) return SF_OK;
-  int64_t *cand = nullptr, *cand_offsets = nullptr;
-  int32_t* counts = nullptr;
-  float4* nbr = nullptr;  // padded list of 16-byte entries: float32 offset, position | zero-distance flag << 31
-  float* frame32 = nullptr;
-  double* lrf = lrf_out;
-  void* scan_temp = nullptr;
-  size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cand, cand_offsets, int(nq + 1), stream);
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand), size_t(nq + 1) * 8, stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&cand_offsets), size_t(nq + 1) * 8, stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&counts), size_t(nq) * 4, stream));
-  SF_CUDA(scratch_alloc(&scan_temp, scan_bytes + 16, stream));
-  if (lrf == nullptr) SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&lrf), size_t(nq) * 9 * 8, stream));
+  if (int rc = shot_reserve_queries(g, nq)) return rc;
+  int64_t* cand = g->shot_cand;
+  int64_t* cand_offsets = g->shot_cand_offsets;
+  int32_t* counts = g->shot_counts;
+  float* frame32 = g->shot_frame32;
+  double* lrf = lrf_out != nullptr ? lrf_out : g->shot_lrf;
+  unsigned long long* pair_counter = g->shot_pairs;
+  int32_t* worklist = g->shot_worklist;  // [0] = number of queries handed to the exact kernel, then their indices
   const GridView view = g->view();
   SF_CUDA(cudaMemsetAsync(cand + nq, 0, 8, stream));
-  unsigned long long* pair_counter = nullptr;
-  int32_t* worklist = nullptr;  // [0] = number of queries handed to the exact kernel, then their indices
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&pair_counter), 8, stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&worklist), size_t(nq + 1) * 4, stream));
   SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
   candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(view, queries, nq, cand);
-  SF_CUDA(cub::DeviceScan::ExclusiveSum(scan_temp, scan_bytes, cand, cand_offsets, int(nq + 1), stream));
-  int64_t total = 0;
-  SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + nq, 8, cudaMemcpyDeviceToHost, stream));
-  SF_CUDA(cudaStreamSynchronize(stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&nbr), size_t(total > 0 ? total : 1) * sizeof(float4), stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&frame32), size_t(nq) * 12 * sizeof(float), stream));
+  size_t scan_bytes = g->shot_scan_bytes;
+  SF_CUDA(cub::DeviceScan::ExclusiveSum(g->shot_scan_temp, scan_bytes, cand, cand_offsets, int(nq + 1), stream));
+  // The padded list holds one 16-byte entry per CANDIDATE; its size is read back (the one synchronisation of the
+  // call) unless the handle is in speculative mode and a previous call left an estimate: then the list is sized
+  // from that estimate, the device checks it (status 2) and every kernel below returns at once when it does not fit.
+  const bool assume_size = (g->speculative & 2) && g->shot_entries_per_query > 0.0 && pairs_host == nullptr;
+  const int32_t* status = nullptr;
+  if (assume_size) {
+    if (int rc = shot_reserve_entries(g, int64_t(g->shot_entries_per_query * 1.25 * double(nq)) + 4096)) return rc;
+    list_capacity_kernel<<<1, 32, 0, stream>>>(cand_offsets, nq, g->shot_nbr_capacity, g->status_dev);
+    status = g->status_dev;
+  } else {
+    int64_t total = 0;
+    SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + nq, 8, cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaStreamSynchronize(stream));
+    if (int rc = shot_reserve_entries(g, total + total / 16 + 4096)) return rc;
+    g->shot_entries_per_query = double(total) / double(nq);
+  }
+  float4* nbr = g->shot_nbr;  // padded list of 16-byte entries: float32 offset, position | zero-distance flag << 31
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
   profile_mark(0, stream);
   search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets, nbr,
-                                                        counts, lrf, pair_counter);
+                                                        counts, lrf, pair_counter, status);
   profile_mark(1, stream);
-  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf, frame32);
+  lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf, frame32, status);
   profile_mark(2, stream);
   int rc = launch_descriptor(g, queries, nq, radius, cand_offsets, counts, nbr, true, lrf, frame32, lrf_out != nullptr, min_nb,
-                             normalize, out, out_is_f64, worklist + 1, worklist, stream);
+                             normalize, out, out_is_f64, worklist + 1, worklist, status, stream);
   profile_mark(3, stream);
+  if (g->speculative && g->status_host != nullptr)  // the verdict of the device-side checks, for sf_grid_poll
+    SF_CUDA(cudaMemcpyAsync(g->status_host, g->status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   if (rc == SF_OK && pairs_host != nullptr) {  // neighbour pairs found (logging / algorithmic-byte accounting)
     unsigned long long pairs = 0;
     int32_t deferred = 0;
@@ -1001,9 +1050,5 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
     *pairs_host = int64_t(pairs);
     g_last_deferred = env_flag("SF_SHOT_EXACT") ? nq : int64_t(deferred);
   }
-  void* to_free[] = {cand, cand_offsets, counts, nbr, frame32, scan_temp, pair_counter, worklist,
-                     lrf_out == nullptr ? lrf : nullptr};
-  for (void* p : to_free)
-    if (p) cudaFreeAsync(p, stream);
   return rc;
 }

@@ -52,7 +52,8 @@ class ShotMultiprocessor:
 
     def __enter__(self):
         require_cuda()  # fails loudly here rather than at the first kernel
-        self._grid = Grid()
+        self._grid = None
+        self._ensure_grid()
         return self
 
     def __exit__(
@@ -70,7 +71,8 @@ class ShotMultiprocessor:
     # ------------------------------------------------------------------------------------------------------
     def _ensure_grid(self) -> Grid:
         if getattr(self, "_grid", None) is None:
-            self._grid = Grid()
+            # blocks of queries after the first size their neighbour lists without a host round trip; `poll` below
+            self._grid = Grid().set_speculative(builds=False, shot_lists=True)
         return self._grid
 
     def _support(self, point_cloud, normals, subsampling_voxel_size, radius):
@@ -178,21 +180,27 @@ class ShotMultiprocessor:
         n_kp = int(np.shape(keypoints)[0])
         if n_kp == 0:
             return np.zeros((0, 352))
-        # Here the reference's `n_procs` workers are the host threads that rebuild the dense float64 rows.
-        job = SparseRowsDownload(n_kp, 352, self.n_procs)
-        try:
-            grid, _, _ = self._support(point_cloud, normals, subsampling_voxel_size, radius)
-            kp = upload(keypoints)
-            blocks = max(1, min(self._PIPELINE_MAX_BLOCKS, n_kp // self._PIPELINE_BLOCK))
-            for b in range(blocks):
-                lo, hi = block_bounds(n_kp, blocks, b)
-                desc, _ = self._single_scale_device(grid, kp[lo:hi], radius, radius, out_dtype=torch.float32)
-                job.push(desc)
-            result = job.finish()
-            self.last_d2h_bytes = job.bytes_copied  # read by bench.py
-            return result
-        finally:
-            job.abandon()
+        for attempt in range(2):
+            # Here the reference's `n_procs` workers are the host threads that rebuild the dense float64 rows.
+            job = SparseRowsDownload(n_kp, 352, self.n_procs)
+            try:
+                self._ensure_grid().set_speculative(builds=False, shot_lists=attempt == 0)
+                grid, _, _ = self._support(point_cloud, normals, subsampling_voxel_size, radius)
+                kp = upload(keypoints)
+                blocks = max(1, min(self._PIPELINE_MAX_BLOCKS, n_kp // self._PIPELINE_BLOCK))
+                for b in range(blocks):
+                    lo, hi = block_bounds(n_kp, blocks, b)
+                    desc, _ = self._single_scale_device(grid, kp[lo:hi], radius, radius, out_dtype=torch.float32)
+                    job.push(desc)
+                result = job.finish()
+                self.last_d2h_bytes = job.bytes_copied  # read by bench.py
+            finally:
+                job.abandon()
+            # blocks after the first sized their neighbour lists from the first one's (no host round trip); when a
+            # block needed more, its kernels did nothing and said so: the call is repeated with exact sizes
+            if grid.poll() == 0:
+                return result
+        raise RuntimeError("SHOT: the device-side size check failed on a synchronising call")  # cannot happen
 
     def compute_descriptor_bi_scale(
         self,

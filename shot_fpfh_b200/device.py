@@ -316,6 +316,21 @@ class Grid:
     def handle(self):
         return self._h
 
+    def set_speculative(self, builds: bool = False, shot_lists: bool = True) -> "Grid":
+        """Repeated builds of the same cloud / fused SHOT calls on this handle skip their host synchronisations (see
+        sf_grid_set_speculative in include/shotfpfh_b200.h); `poll()` after synchronising tells whether what they
+        assumed held."""
+        check(lib.sf_grid_set_speculative(self._h, int(bool(builds)) | (int(bool(shot_lists)) << 1)))
+        return self
+
+    def poll(self) -> int:
+        """0, or the reason the speculative calls since the last poll did nothing (then repeat them)."""
+        import ctypes
+
+        status = ctypes.c_int32(0)
+        check(lib.sf_grid_poll(self._h, ctypes.byref(status)))
+        return int(status.value)
+
     def info(self) -> dict:
         import ctypes
 
