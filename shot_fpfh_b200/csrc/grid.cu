@@ -85,30 +85,24 @@ __global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xy
   }
 }
 
-// Speculative build: the box of a previous build is assumed; status = 1 when a point would fall outside its cells.
-__global__ void bbox_check_kernel(const unsigned long long* box, GridView g, int32_t* status) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  bool ok = true;
-  for (int a = 0; a < 3; ++a) {
-    const double lo = from_ordered_bits(box[a]), hi = from_ordered_bits(box[3 + a]);
-    ok = ok && isfinite(lo) && isfinite(hi);
-    ok = ok && floor((lo - g.origin[a]) * g.inv_cell) >= 0.0 && floor((hi - g.origin[a]) * g.inv_cell) <= double(g.dims[a] - 1);
-  }
-  if (!ok) *status = 1;
-}
-
 // ---- cell keys + per-cell histogram ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     key_kernel(const double* __restrict__ xyz, int64_t n, GridView g, uint32_t* __restrict__ keys,
-               int32_t* __restrict__ vals, int32_t* __restrict__ cell_count, int by_slot) {
+               int32_t* __restrict__ vals, int32_t* __restrict__ cell_count, int by_slot, int32_t* __restrict__ status) {
+  // status != nullptr: a speculative build on the box of a previous one — a point outside that box (or not finite)
+  // raises the flag (sf_grid_poll); the clamp keeps the build memory-safe meanwhile
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   int c[3];
+  bool inside = true;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    c[a] = cell_coord(xyz[3 * i + a], g.origin[a], g.inv_cell, g.dims[a]);
+    const double x = xyz[3 * i + a];
+    c[a] = cell_coord(x, g.origin[a], g.inv_cell, g.dims[a]);
+    inside = inside && isfinite(x) && c[a] >= 0 && c[a] <= g.dims[a] - 1;
     c[a] = min(max(c[a], 0), g.dims[a] - 1);
   }
+  if (status != nullptr && !inside) *status = 1;
   const uint32_t key = (uint32_t(c[2]) * g.dims[1] + c[1]) * g.dims[0] + c[0];
   keys[i] = key;
   // vals: the point's index (radix-sort path) or its arrival slot inside the cell (counting-sort path)
@@ -297,7 +291,7 @@ extern "C" int sf_grid_destroy(sf_grid* g) {
   return SF_OK;
 }
 
-static int build_cells(sf_grid* g, const double* xyz, const double* normals, int64_t n, cudaStream_t stream);
+static int build_cells(sf_grid* g, const double* xyz, const double* normals, int64_t n, bool check_box, cudaStream_t stream);
 
 extern "C" int sf_grid_set_speculative(sf_grid* g, int32_t enable) {
   SF_REQUIRE(g != nullptr, SF_ERR_ARG, "sf_grid_set_speculative: null grid");
@@ -351,15 +345,12 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   // 1. bounding box (device) -> host, the only synchronisation of the build — skipped on a handle in speculative mode
   //    whose last synchronising build saw the same number of points and the same radius: the box of that build is
   //    assumed and checked on the device (sf_grid_poll tells)
+  const bool assume_box = (g->speculative & 1) && g->sized && n == g->sized_n && radius == g->sized_radius;
+  if (assume_box) return build_cells(g, xyz, normals, n, true, stream);  // (the key kernel checks every point)
   unsigned long long* box = reinterpret_cast<unsigned long long*>(g->bbox);
   bbox_init_kernel<<<1, 32, 0, stream>>>(box);
   const int bbox_blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 4));
   bbox_kernel<<<bbox_blocks, 256, 0, stream>>>(xyz, n, box);
-  const bool assume_box = (g->speculative & 1) && g->sized && n == g->sized_n && radius == g->sized_radius;
-  if (assume_box) {
-    bbox_check_kernel<<<1, 32, 0, stream>>>(box, g->view(), g->status_dev);
-    return build_cells(g, xyz, normals, n, stream);
-  }
   unsigned long long hbox[6];
   SF_CUDA(cudaMemcpyAsync(hbox, box, sizeof(hbox), cudaMemcpyDeviceToHost, stream));
   SF_CUDA(cudaStreamSynchronize(stream));
@@ -392,11 +383,11 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   g->sized_n = n;
   g->sized_radius = radius;
   g->shot_entries_per_query = 0;  // another cloud: the neighbour list is sized afresh
-  return build_cells(g, xyz, normals, n, stream);
+  return build_cells(g, xyz, normals, n, false, stream);
 }
 
 // Steps 3-5 of the build for the geometry held by the handle.
-static int build_cells(sf_grid* g, const double* xyz, const double* normals, int64_t n, cudaStream_t stream) {
+static int build_cells(sf_grid* g, const double* xyz, const double* normals, int64_t n, bool check_box, cudaStream_t stream) {
   const int64_t ncells = g->ncells;
   if (ncells + 1 > g->cells_capacity) {
     cudaFree(g->cell_start); cudaFree(g->cell_count);
@@ -413,7 +404,8 @@ static int build_cells(sf_grid* g, const double* xyz, const double* normals, int
   const int blocks = int((n + 255) / 256);
   const char* radix_env = getenv("SF_GRID_RADIX");
   const bool radix = radix_env != nullptr && radix_env[0] == '1';
-  key_kernel<<<blocks, 256, 0, stream>>>(xyz, n, view, g->keys_in, g->vals_in, g->cell_count, radix ? 0 : 1);
+  key_kernel<<<blocks, 256, 0, stream>>>(xyz, n, view, g->keys_in, g->vals_in, g->cell_count, radix ? 0 : 1,
+                                         check_box ? g->status_dev : nullptr);
   int end_bit = 1;
   while ((int64_t(1) << end_bit) < ncells) ++end_bit;
   size_t sort_bytes = 0, scan_bytes = 0;
@@ -439,6 +431,8 @@ static int build_cells(sf_grid* g, const double* xyz, const double* normals, int
                                                     g->nrm, g->inv_perm, view, g->xyzc, g->nrm32);
   }
   SF_CUDA(cudaGetLastError());
+  if (check_box)  // the verdict, for sf_grid_poll
+    SF_CUDA(cudaMemcpyAsync(g->status_host, g->status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   return SF_OK;
 }
 

@@ -227,6 +227,56 @@ def test_large_size_properties_1m():
     _check_rows(d[rows], want, "1M spot check")
 
 
+def test_calls_without_host_synchronisation_check_their_assumptions():
+    """
+    Speculative mode (sf_grid_set_speculative): a rebuilt grid assumes the previous box, the fused driver sizes its
+    neighbour list from the previous call. Same work again -> same rows, poll() == 0. A cloud outside the box ->
+    poll() == 1; denser queries than the list was sized for -> poll() == 2; in both cases the repeat is right.
+    """
+    import torch
+
+    from shot_fpfh_b200 import ops
+    from shot_fpfh_b200.device import Grid, upload
+
+    n = 40_000
+    pts, normals = synthetic.bumpy_sphere(n, seed=17)
+    # a cloud of uneven density: the upper half keeps one point in eight
+    keep = (pts[:, 2] < 0) | (np.arange(n) % 8 == 0)
+    pts, normals = pts[keep], normals[keep]
+    radius = 5.0 * synthetic.mean_spacing(n)
+    sparse_q = pts[pts[:, 2] > 0.3][:800]
+    dense_q = pts[pts[:, 2] < -0.3][:800]
+    p_dev, n_dev = upload(pts), upload(normals)
+
+    def rows(grid, queries):
+        d, _, _ = ops.shot_single_scale(grid, upload(queries), radius, 5, True, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        return d.cpu().numpy()
+
+    plain = Grid().build(p_dev, n_dev, radius)
+    want_sparse, want_dense = rows(plain, sparse_q), rows(plain, dense_q)
+    assert want_dense.any(axis=1).mean() > 0.9
+
+    spec = Grid().set_speculative(builds=True, shot_lists=True).build(p_dev, n_dev, radius)
+    assert np.array_equal(rows(spec, sparse_q), want_sparse) and spec.poll() == 0  # first calls synchronise
+    spec.build(p_dev, n_dev, radius)  # same cloud again: box assumed, list sized from the call above
+    assert np.array_equal(rows(spec, sparse_q), want_sparse) and spec.poll() == 0
+    # (2) the dense queries need a longer list than the sparse ones left an estimate for
+    got = rows(spec, dense_q)
+    assert spec.poll() == 2 and not np.array_equal(got, want_dense)
+    spec.build(p_dev, n_dev, radius)
+    assert np.array_equal(rows(spec, dense_q), want_dense) and spec.poll() == 0
+    # (1) a cloud that leaves the assumed box (same size, same radius)
+    moved = upload(pts + np.array([0.0, 0.0, 0.5]))
+    spec.build(p_dev, n_dev, radius)
+    spec.build(moved, n_dev, radius)
+    torch.cuda.synchronize()
+    assert spec.poll() == 1
+    spec.build(moved, n_dev, radius)
+    want_moved = rows(Grid().build(moved, n_dev, radius), sparse_q + np.array([0.0, 0.0, 0.5]))
+    assert np.array_equal(rows(spec, sparse_q + np.array([0.0, 0.0, 0.5])), want_moved) and spec.poll() == 0
+
+
 def test_result_transport_equals_a_dense_copy():
     """device.SparseRowsDownload (csrc/transport.cu + csrc/host_io.cpp): compact -> copy -> expand == rows.double()."""
     import torch
