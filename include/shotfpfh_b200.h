@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 5
+#define SF_ABI_VERSION 6
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -206,9 +206,11 @@ int sf_fpfh_block_rows(sf_grid* grid, int64_t first, int64_t count, const int64_
  * M — descriptor matching.  Replaces `cdist(...).argmin(axis=1)` in `basic_matching` (matching.py:162-169),
  * `match_descriptors` (matching.py:43-52) and the ratio test `double_matching_with_rejects` (matching.py:172-221).
  * ---------------------------------------------------------------------------------------------------------- */
-/* Rows with at least one non-zero entry (matching.py:43-44): ascending row ids into rows_dev[0..count). */
+/* Rows with at least one non-zero entry (matching.py:43-44): ascending row ids into rows_dev[0..count).
+ * absmax_host (optional): the largest |x| of the whole array, from the same pass (the common scale of the float16
+ * operands; NaN or infinity when the array holds one). Synchronises `stream`. */
 int sf_nonempty_rows(const double* desc_dev, int64_t n, int32_t width, int64_t* rows_dev, int64_t* count_host,
-                     void* stream);
+                     double* absmax_host, void* stream);
 /* Gathers rows `rows_dev` of a float64 matrix into the GEMM operand format: float16 (count, width_padded)
  * scaled by `scale`, plus the float32 squared norms of the ROUNDED rows. width_padded is a multiple of 64. */
 int sf_match_pack(const double* desc_dev, int32_t width, const int64_t* rows_dev, int64_t count, double scale,
@@ -224,6 +226,21 @@ int sf_match_topk(const void* a_packed_dev, int64_t qa, const void* b_packed_dev
  * target set is sharded across GPUs). */
 int sf_topk_merge(const float* score_dev, const int32_t* idx_dev, int32_t parts, int64_t qa, int32_t k,
                   float* score_out_dev, int32_t* idx_out_dev, void* stream);
+/* Certificate of the float16 shortlist (csrc/match.cu::certify_kernel): flags_dev[q] = 1 when the exact nearest
+ * (want_second: second-nearest) distance of query q from sf_match_rerank is NOT provably below the distance to every
+ * target outside its k-entry shortlist — bound from the k-th shortlist score, the float16 rounding of the operands and
+ * the float32 accumulation. score_dev: (qa, k) of sf_match_topk; a_sqnorm_dev: squared norms of the packed query rows
+ * (sf_match_pack); b_norm_max: largest norm of a packed target row; scale: the packing scale.
+ * Replaces nothing in the reference: it is what makes `cdist(...).argmin()` (matching.py:164-168) provable here. */
+int sf_match_certify(const float* score_dev, int32_t k, const float* a_sqnorm_dev, const double* d1_dev,
+                     const double* d2_dev, int64_t qa, double scale, double b_norm_max, int32_t width, int64_t qb,
+                     int32_t want_second, uint8_t* flags_dev, void* stream);
+/* Exhaustive float64 shortlist of the flagged queries which_dev[0..n_which) (positions in rows_a): the k (8 or 16)
+ * nearest targets by float64 distance, lowest index on ties, written into their rows of cand_dev (qa, k); the caller
+ * re-ranks those rows with sf_match_rerank. */
+int sf_match_exhaustive_topk(const double* a_dev, const int64_t* rows_a_dev, const int64_t* which_dev, int64_t n_which,
+                             const double* b_dev, const int64_t* rows_b_dev, int64_t qb, int32_t width, int32_t k,
+                             int32_t* cand_dev, void* stream);
 /* Exact re-rank: float64 `sqrt(sum((a-b)^2))` accumulated sequentially (what scipy's cdist computes) between each
  * query row and its k candidates; nn_dev = candidate with the smallest distance (lowest index on ties),
  * d1_dev / d2_dev = smallest and second smallest distance (d2 = +inf when k == 1 or a single candidate).

@@ -15,15 +15,32 @@ namespace sf {
 int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bnorm, int64_t qb, int width_padded,
                    int k, int index_offset, float* score, int32_t* idx, cudaStream_t stream);  // match_tc.cu
 
+// absmax (optional): bit pattern of the largest |x| of the array, raised with an integer atomicMax (non-negative
+// doubles order like their bit patterns; a NaN's pattern is above infinity's, so one NaN or infinity anywhere shows)
 __global__ void __launch_bounds__(256)
-    nonempty_kernel(const double* __restrict__ desc, int64_t n, int width, uint8_t* __restrict__ flags) {
+    nonempty_kernel(const double* __restrict__ desc, int64_t n, int width, uint8_t* __restrict__ flags,
+                    unsigned long long* __restrict__ absmax) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (row >= n) return;
   bool any = false;
-  for (int c = lane; c < width; c += 32) any |= desc[row * width + c] != 0.0;  // NaN counts as non-zero, like np.any
+  unsigned long long top = 0ull;
+  for (int c = lane; c < width; c += 32) {
+    const double v = desc[row * width + c];
+    any |= v != 0.0;  // NaN counts as non-zero, like np.any
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fabs(v)));
+    top = bits > top ? bits : top;
+  }
   any = __any_sync(kFull, any);
   if (lane == 0) flags[row] = any;
+  if (absmax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, top, o);
+      top = other > top ? other : top;
+    }
+    if (lane == 0 && top != 0ull) atomicMax(absmax, top);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -217,6 +234,103 @@ __global__ void __launch_bounds__(kRerankWarps * 32)
   }
 }
 
+// ---- certificate of the float16 shortlist ------------------------------------------------------------------------
+// The shortlist kernel ranks targets by score(b) = |b~|^2 - 2 a~.b~ on the float16-rounded, scaled rows a~ = fl16(s a),
+// b~ = fl16(s b), so |a~ - b~|^2 = score + |a~|^2, and every target OUTSIDE a query's k-entry shortlist has
+// score >= score_k. Bounds (u16 = 2^-11 relative rounding of a normal half, 2^-25 absolute below 2^-14; float32
+// accumulation of `width` products, allowed twice the rounding-to-nearest bound for the tensor core's accumulator):
+//   |a~ - b~| >= sqrt(max(0, score_k + |a~|^2 - 1e-4 (|a~| B + B^2))),   B = max |b~|
+//   s |a - b| >= |a~ - b~| - 2^-11 (1 + 2^-10) (|a~| + B) - 2 sqrt(width) 2^-25
+// A query is certified when its exact nearest (and, when asked, second-nearest) distance from the re-rank is strictly
+// below that bound on everything outside the shortlist: the re-rank then saw the true nearest neighbours. The others
+// (adversarial near-ties, rows that quantise to 0, ...) are flagged and redone exhaustively in float64.
+__global__ void __launch_bounds__(256)
+    certify_kernel(const float* __restrict__ score, int k, const float* __restrict__ a_sqnorm, const double* __restrict__ d1,
+                   const double* __restrict__ d2, int64_t qa, double scale, double b_norm_max, int width, int64_t qb,
+                   int want_second, uint8_t* __restrict__ flags) {
+  const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (q >= qa) return;
+  bool ok;
+  if (qb <= k) {
+    ok = true;  // every target is in the shortlist
+  } else {
+    const double sk = double(score[q * k + (k - 1)]), a2 = double(a_sqnorm[q]), an = sqrt(a2);
+    const double lower2 = sk + a2 - 1e-4 * (an * b_norm_max + b_norm_max * b_norm_max);
+    const double eps = 4.8828125e-4 * 1.001 * (an + b_norm_max) + 2.0 * sqrt(double(width)) * 2.98e-8;
+    const double outside = sqrt(fmax(lower2, 0.0)) - eps;  // scaled distance to anything outside the shortlist
+    const double need = want_second ? d2[q] : d1[q];
+    ok = isfinite(sk) ? (scale * need < outside) : true;  // (infinite score_k: fewer than k finite scores)
+    ok = ok && !(need != need) && !(sk != sk);
+  }
+  flags[q] = ok ? 0 : 1;
+}
+
+// Exhaustive float64 shortlist for the flagged queries: block per query, warps over the targets, lanes over the
+// columns; the k smallest squared distances (any summation order: the exact re-rank decides among them, and exact
+// ties carry identical values here) with the lowest index on ties.
+template <int K>
+__global__ void __launch_bounds__(256)
+    exhaustive_topk_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a,
+                           const int64_t* __restrict__ which, int64_t n_which, const double* __restrict__ b,
+                           const int64_t* __restrict__ rows_b, int64_t qb, int width, int32_t* __restrict__ cand) {
+  __shared__ float ws[8][K];
+  __shared__ int wi[8][K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t item = blockIdx.x;
+  if (item >= n_which) return;
+  const int64_t q = which[item];
+  const double* ra = a + (rows_a ? rows_a[q] : q) * width;
+  // float32 images only ORDER the candidates of a warp before the merge; the distances themselves are float64 below
+  double best_d[K];
+  int best_i[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) { best_d[t] = INFINITY; best_i[t] = -1; }
+  for (int64_t j = warp; j < qb; j += 8) {
+    const double* rb = b + (rows_b ? rows_b[j] : j) * width;
+    double s = 0.0;
+    for (int e = lane; e < width; e += 32) {
+      const double d = ra[e] - rb[e];
+      s = fma(d, d, s);
+    }
+    s = warp_sum(s);
+    // every lane keeps the same sorted list (ascending distance, then index)
+    if (s < best_d[K - 1] || (s == best_d[K - 1] && int(j) < best_i[K - 1]) || best_i[K - 1] < 0) {
+      if (!(s != s)) {
+        best_d[K - 1] = s; best_i[K - 1] = int(j);
+#pragma unroll
+        for (int t = K - 1; t > 0; --t) {
+          const bool swap = best_i[t - 1] < 0 || best_d[t] < best_d[t - 1] || (best_d[t] == best_d[t - 1] && best_i[t] < best_i[t - 1]);
+          if (swap) {
+            const double td = best_d[t]; best_d[t] = best_d[t - 1]; best_d[t - 1] = td;
+            const int ti = best_i[t]; best_i[t] = best_i[t - 1]; best_i[t - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+  __shared__ double wd[8][K];
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < K; ++t) { wd[warp][t] = best_d[t]; wi[warp][t] = best_i[t]; }
+  }
+  (void)ws;
+  __syncthreads();
+  if (threadIdx.x == 0) {  // merge the eight sorted lists
+    int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < K; ++t) {
+      int pick = -1;
+      for (int w = 0; w < 8; ++w) {
+        if (head[w] >= K || wi[w][head[w]] < 0) continue;
+        if (pick < 0 || wd[w][head[w]] < wd[pick][head[pick]] ||
+            (wd[w][head[w]] == wd[pick][head[pick]] && wi[w][head[w]] < wi[pick][head[pick]]))
+          pick = w;
+      }
+      cand[q * K + t] = pick >= 0 ? wi[pick][head[pick]] : -1;
+      if (pick >= 0) ++head[pick];
+    }
+  }
+}
+
 struct IsSet {
   const uint8_t* flags;
   __host__ __device__ bool operator()(int64_t i) const { return flags[i] != 0; }
@@ -227,10 +341,11 @@ struct IsSet {
 using namespace sf;
 
 extern "C" int sf_nonempty_rows(const double* desc, int64_t n, int32_t width, int64_t* rows, int64_t* count_host,
-                                void* stream_) {
+                                double* absmax_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(desc && rows && count_host && n >= 0 && width > 0, SF_ERR_ARG, "sf_nonempty_rows: bad arguments");
   *count_host = 0;
+  if (absmax_host) *absmax_host = 0.0;
   if (n == 0) return SF_OK;
   SF_REQUIRE(n < (int64_t(1) << 31), SF_ERR_ARG, "sf_nonempty_rows: too many rows");
   uint8_t* flags = nullptr;
@@ -240,11 +355,15 @@ extern "C" int sf_nonempty_rows(const double* desc, int64_t n, int32_t width, in
   cub::CountingInputIterator<int64_t> ids(0);
   cub::DeviceSelect::Flagged(nullptr, temp_bytes, ids, flags, rows, count_dev, int(n), stream);
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&flags), size_t(n), stream));
-  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&count_dev), sizeof(int64_t), stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&count_dev), 2 * sizeof(int64_t), stream));
   SF_CUDA(scratch_alloc(&temp, temp_bytes + 16, stream));
-  nonempty_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, stream>>>(desc, n, width, flags);
+  unsigned long long* absmax_dev = reinterpret_cast<unsigned long long*>(count_dev + 1);
+  SF_CUDA(cudaMemsetAsync(absmax_dev, 0, sizeof(unsigned long long), stream));
+  nonempty_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, stream>>>(desc, n, width, flags,
+                                                                     absmax_host ? absmax_dev : nullptr);
   SF_CUDA(cub::DeviceSelect::Flagged(temp, temp_bytes, ids, flags, rows, count_dev, int(n), stream));
   SF_CUDA(cudaMemcpyAsync(count_host, count_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  if (absmax_host) SF_CUDA(cudaMemcpyAsync(absmax_host, absmax_dev, sizeof(double), cudaMemcpyDeviceToHost, stream));
   SF_CUDA(cudaFreeAsync(flags, stream));
   SF_CUDA(cudaFreeAsync(count_dev, stream));
   SF_CUDA(cudaFreeAsync(temp, stream));
@@ -329,6 +448,34 @@ extern "C" int sf_topk_merge(const float* score, const int32_t* idx, int32_t par
     case 8: return launch_merge<8>(score, idx, parts, qa, score_out, idx_out, stream);
     default: return launch_merge<16>(score, idx, parts, qa, score_out, idx_out, stream);
   }
+}
+
+extern "C" int sf_match_certify(const float* score, int32_t k, const float* a_sqnorm, const double* d1, const double* d2,
+                                int64_t qa, double scale, double b_norm_max, int32_t width, int64_t qb,
+                                int32_t want_second, uint8_t* flags, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(score && a_sqnorm && d1 && d2 && flags && k >= 1, SF_ERR_ARG, "sf_match_certify: bad arguments");
+  if (qa == 0) return SF_OK;
+  certify_kernel<<<unsigned((qa + 255) / 256), 256, 0, stream>>>(score, k, a_sqnorm, d1, d2, qa, scale, b_norm_max, width, qb,
+                                                                want_second, flags);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_match_exhaustive_topk(const double* a, const int64_t* rows_a, const int64_t* which, int64_t n_which,
+                                         const double* b, const int64_t* rows_b, int64_t qb, int32_t width, int32_t k,
+                                         int32_t* cand, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(a && which && b && cand && width > 0, SF_ERR_ARG, "sf_match_exhaustive_topk: bad arguments");
+  SF_REQUIRE(k == 8 || k == 16, SF_ERR_CAPACITY, "sf_match_exhaustive_topk: k must be 8 or 16");
+  SF_REQUIRE(qb < (int64_t(1) << 31), SF_ERR_ARG, "sf_match_exhaustive_topk: too many targets");
+  if (n_which == 0) return SF_OK;
+  if (k == 8)
+    exhaustive_topk_kernel<8><<<unsigned(n_which), 256, 0, stream>>>(a, rows_a, which, n_which, b, rows_b, qb, width, cand);
+  else
+    exhaustive_topk_kernel<16><<<unsigned(n_which), 256, 0, stream>>>(a, rows_a, which, n_which, b, rows_b, qb, width, cand);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
 }
 
 extern "C" int sf_match_rerank(const double* a, const int64_t* rows_a, int64_t qa, const double* b,

@@ -790,8 +790,8 @@ extern "C" int sf_shot_lrf(sf_grid* g, const double* queries, int64_t nq, double
                            const int32_t* nbr, double* lrf, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0, SF_ERR_ARG, "sf_shot_lrf: grid not built");
-  SF_REQUIRE(queries && offsets && lrf && nq >= 0, SF_ERR_ARG, "sf_shot_lrf: bad arguments");
-  if (nq == 0) return SF_OK;
+  if (nq == 0) return SF_OK;  // (an empty query block has null pointers: zero-row tensors)
+  SF_REQUIRE(queries && offsets && lrf && nq > 0, SF_ERR_ARG, "sf_shot_lrf: bad arguments");
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
   lrf_moments_kernel<<<warp_blocks, 256, 0, stream>>>(g->view(), queries, nq, radius, offsets, nbr, lrf);
   lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, offsets, nullptr, lrf, nullptr);
@@ -941,8 +941,8 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
                                   int32_t normalize, void* out, int32_t out_is_f64, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_descriptor: grid built without normals");
-  SF_REQUIRE(queries && offsets && lrf && out && nq >= 0, SF_ERR_ARG, "sf_shot_descriptor: bad arguments");
-  if (nq == 0) return SF_OK;
+  if (nq == 0) return SF_OK;  // (an empty query block has null pointers: zero-row tensors)
+  SF_REQUIRE(queries && offsets && lrf && out && nq > 0, SF_ERR_ARG, "sf_shot_descriptor: bad arguments");
   int32_t* worklist = nullptr;
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&worklist), size_t(nq + 1) * 4, stream));
   const int rc = launch_descriptor(g, queries, nq, radius, offsets, nullptr, nbr, false, const_cast<double*>(lrf), nullptr, 0,
@@ -993,11 +993,11 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
                                     int64_t* pairs_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(g != nullptr && g->n > 0 && g->has_normals, SF_ERR_ARG, "sf_shot_single_scale: grid built without normals");
-  SF_REQUIRE(queries && out && nq >= 0, SF_ERR_ARG, "sf_shot_single_scale: bad arguments");
+  if (pairs_host) *pairs_host = 0;
+  if (nq == 0) return SF_OK;  // (an empty query block has null pointers: zero-row tensors)
+  SF_REQUIRE(queries && out && nq > 0, SF_ERR_ARG, "sf_shot_single_scale: bad arguments");
   SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
              "sf_shot_single_scale: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
-  if (pairs_host) *pairs_host = 0;
-  if (nq == 0) return SF_OK;
   if (int rc = shot_reserve_queries(g, nq)) return rc;
   int64_t* cand = g->shot_cand;
   int64_t* cand_offsets = g->shot_cand_offsets;

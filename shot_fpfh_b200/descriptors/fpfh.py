@@ -17,7 +17,7 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import DenseRowsDownload, Grid, upload
+from ..device import DenseRowsDownload, Grid, remember_device_rows, upload
 
 
 def fpfh_device(grid: Grid, keypoints_dev: torch.Tensor, radius: float, n_bins: int, decorrelated: bool,
@@ -69,10 +69,14 @@ def compute_fpfh_descriptor(
         logging.info(f"Mean neighborhood size over the whole point cloud: {block.pairs / max(grid.n, 1):.2f}")
     parts = max(1, min(_OUTPUT_BLOCKS, n_kp // 32768))
     job = DenseRowsDownload(n_kp, width)
+    pieces = []
     for b in range(parts):
         lo, hi = n_kp * b // parts, n_kp * (b + 1) // parts
-        job.push(block.rows(spfh_all, kp_dev[lo:hi].contiguous(), out_dtype=torch.float32))
-    return job.finish()
+        pieces.append(block.rows(spfh_all, kp_dev[lo:hi].contiguous(), out_dtype=torch.float32))
+        job.push(pieces[-1])
+    result = job.finish()
+    remember_device_rows(result, pieces[0] if len(pieces) == 1 else torch.cat(pieces))  # hand-off to the matcher
+    return result
 
 
 _OUTPUT_BLOCKS = 8

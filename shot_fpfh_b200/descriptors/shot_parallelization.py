@@ -21,7 +21,8 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import Grid, SparseRowsDownload, download, download_sparse_rows, require_cuda, upload
+from ..device import (Grid, SparseRowsDownload, download, download_sparse_rows, remember_device_rows, require_cuda,
+                      upload)
 from ..distributed import block_bounds
 
 
@@ -188,10 +189,12 @@ class ShotMultiprocessor:
                 grid, _, _ = self._support(point_cloud, normals, subsampling_voxel_size, radius)
                 kp = upload(keypoints)
                 blocks = max(1, min(self._PIPELINE_MAX_BLOCKS, n_kp // self._PIPELINE_BLOCK))
+                rows = torch.empty((n_kp, 352), dtype=torch.float32, device=kp.device)  # kept for the matcher (hand-off)
                 for b in range(blocks):
                     lo, hi = block_bounds(n_kp, blocks, b)
-                    desc, _ = self._single_scale_device(grid, kp[lo:hi], radius, radius, out_dtype=torch.float32)
-                    job.push(desc)
+                    ops.shot_single_scale(grid, kp[lo:hi], radius, self.min_neighborhood_size, self.normalize,
+                                          out=rows[lo:hi])
+                    job.push(rows[lo:hi])
                 result = job.finish()
                 self.last_d2h_bytes = job.bytes_copied  # read by bench.py
             finally:
@@ -199,6 +202,7 @@ class ShotMultiprocessor:
             # blocks after the first sized their neighbour lists from the first one's (no host round trip); when a
             # block needed more, its kernels did nothing and said so: the call is repeated with exact sizes
             if grid.poll() == 0:
+                remember_device_rows(result, rows)
                 return result
         raise RuntimeError("SHOT: the device-side size check failed on a synchronising call")  # cannot happen
 

@@ -290,6 +290,58 @@ def download_sparse_rows(rows: torch.Tensor, threads: int | None = None) -> np.n
         job.abandon()
 
 
+# ---- device-resident hand-off between stages ----------------------------------------------------------------------
+# The reference API returns host float64 arrays and takes them back a moment later (pipeline.py:154-174 computes the
+# descriptors, :376-399 hands them to the matcher). The float32 device rows a descriptor call produced are remembered
+# under the host array it returned (weak reference: dropped with the array); a later call that receives THAT array
+# takes the device rows instead of sending 8 bytes per element back over PCIe. The array is the caller's and may
+# have been modified since: a sample of its rows is compared with the device rows before they are trusted.
+_HANDOFF: dict[int, tuple[object, torch.Tensor]] = {}
+_HANDOFF_BUDGET_FRACTION = 0.25  # of the device's memory
+_HANDOFF_SAMPLE_ROWS = 96
+
+
+def remember_device_rows(host_array: np.ndarray, rows: torch.Tensor) -> None:
+    """`rows` (float32, device) are the values of `host_array` (float64, host) — see above."""
+    import weakref
+
+    if not (isinstance(host_array, np.ndarray) and rows.is_cuda and tuple(rows.shape) == host_array.shape):
+        return
+    budget = _HANDOFF_BUDGET_FRACTION * torch.cuda.get_device_properties(rows.device).total_memory
+    held = sum(t.numel() * t.element_size() for _, t in _HANDOFF.values())
+    for key in list(_HANDOFF):  # oldest first
+        if held + rows.numel() * rows.element_size() <= budget:
+            break
+        held -= _HANDOFF[key][1].numel() * _HANDOFF[key][1].element_size()
+        del _HANDOFF[key]
+    key = id(host_array)
+    try:
+        ref = weakref.ref(host_array, lambda _r, k=key: _HANDOFF.pop(k, None))
+    except TypeError:  # pragma: no cover
+        return
+    _HANDOFF[key] = (ref, rows)
+
+
+def device_rows_of(host_array) -> torch.Tensor | None:
+    """The device rows remembered for exactly this array object, if a sample of its rows still equals them."""
+    if not isinstance(host_array, np.ndarray):
+        return None
+    entry = _HANDOFF.get(id(host_array))
+    if entry is None or entry[0]() is not host_array:
+        return None
+    rows = entry[1]
+    if tuple(rows.shape) != host_array.shape or rows.device.index != torch.cuda.current_device():
+        return None
+    n = host_array.shape[0]
+    if n:
+        pick = np.unique(np.linspace(0, n - 1, min(n, _HANDOFF_SAMPLE_ROWS)).astype(np.int64))
+        on_device = rows[torch.from_numpy(pick).to(rows.device)].double().cpu().numpy()
+        if not np.array_equal(on_device, host_array[pick]):
+            _HANDOFF.pop(id(host_array), None)
+            return None
+    return rows
+
+
 class Grid:
     """Owner of one `sf_grid` handle (uniform grid over a cloud, see csrc/grid.cu)."""
 

@@ -22,6 +22,26 @@ import torch
 import torch.distributed as dist
 
 
+def _marker(timings: dict):
+    """mark(name): records a CUDA event under `name` when the caller asked for timings (bench.py)."""
+    events = timings.setdefault("_events", [])
+
+    def mark(name):
+        if timings.get("enabled"):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            events.append((name, ev))
+
+    return mark
+
+
+def _elapsed(timings: dict) -> None:
+    """Turns the recorded events into `timings["ms"][name]` = milliseconds since the previous mark."""
+    events = timings.pop("_events", [])
+    if timings.get("enabled") and len(events) > 1:
+        timings["ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(events[:-1], events[1:])}
+
+
 def world(group=None) -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -198,7 +218,7 @@ def sharded_fpfh_by_position(
 
 
 def fpfh(keypoints_indices, cloud_points, normals, radius, n_bins, decorrelated=False, gather=True,
-         out_dtype=torch.float32, group=None):
+         out_dtype=torch.float32, group=None, timings: dict | None = None):
     """
     FPFH rows (device tensor) of the keypoint INDICES over the ranks: every rank builds the grid of the (replicated)
     cloud and runs the fused driver on ITS block of the cell-sorted points — one scan of the candidates for the
@@ -210,27 +230,38 @@ def fpfh(keypoints_indices, cloud_points, normals, radius, n_bins, decorrelated=
     from .descriptors.fpfh import _cached_grid
     from .device import upload
 
+    t = timings if timings is not None else {}
+    mark = _marker(t)
+    mark("start")
     pts, nrm = upload_replicated(cloud_points, group=group), upload_replicated(normals, group=group)
     kp = upload(keypoints_indices, torch.int64)
+    mark("cloud_on_every_rank")
     grid = _cached_grid().build(pts, nrm, radius)  # the handle keeps its buffers between calls
     _, inv_perm = ops.grid_permutation(grid)
     positions = inv_perm[kp].long()
+    mark("grid")
     state = {}
 
     def spfh_block(first, end):
         state["block"] = ops.FpfhBlock(grid, radius, n_bins, decorrelated, first, end - first, pts.device)
-        return state["block"].spfh()
+        rows = state["block"].spfh()
+        mark("search_and_spfh_of_block")
+        return rows
 
     def fpfh_rows(spfh_all, mine):
-        return state["block"].rows(spfh_all.contiguous(), kp[mine].contiguous(), out_dtype=out_dtype)
+        mark("spfh_all_gather")
+        rows = state["block"].rows(spfh_all.contiguous(), kp[mine].contiguous(), out_dtype=out_dtype)
+        mark("fpfh_rows_of_block")
+        return rows
 
     width = 3 * n_bins if decorrelated else n_bins**3
     out = sharded_fpfh_by_position(grid.n, positions, width, spfh_block, fpfh_rows, gather, group)
     torch.cuda.synchronize()
+    _elapsed(t)
     return out
 
 
-def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None):
+def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None, timings: dict | None = None):
     """
     Exact nearest / second-nearest reference row of every non-empty scan row, the reference set sharded over the
     ranks by contiguous blocks of rows: a rank uploads ITS block of the scan rows (one all-gather over NVLink gives
@@ -242,28 +273,35 @@ def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None)
     """
     from . import ops
     from .device import upload
+    from .matching.matching import exact_nearest, largest, pack_scale
 
     ref = ref_descriptors
+    t = timings if timings is not None else {}
+    mark = _marker(t)
+    mark("start")
     a = upload_replicated(scan_descriptors, group=group)  # an N-th over PCIe per rank, the rest over NVLink
-    rows_a = ops.nonempty_rows(a)
+    mark("scan_rows_on_every_rank")
+    rows_a, a_top = ops.nonempty_rows(a, want_absmax=True)
     qa = int(rows_a.shape[0])
 
     def shard(lo, hi):
         b = upload(ref[lo:hi])  # only this rank's block crosses PCIe
-        rows_b = ops.nonempty_rows(b) if hi > lo else torch.empty(0, dtype=torch.int64, device=a.device)
-        top = torch.stack([a.abs().max() if a.numel() else a.new_zeros(()), b.abs().max() if b.numel() else a.new_zeros(())]).max()
+        rows_b, b_top = (ops.nonempty_rows(b, want_absmax=True) if hi > lo
+                         else (torch.empty(0, dtype=torch.int64, device=a.device), 0.0))
+        top = torch.tensor([largest(a_top, b_top)], dtype=torch.float64, device=a.device)
         if world(group)[1] > 1:
-            dist.all_reduce(top, op=dist.ReduceOp.MAX, group=group)
-        scale = 1.0 / max(float(top.item()), 1e-300)
+            dist.all_reduce(top, op=dist.ReduceOp.MAX, group=group)  # the same float16 scale on every rank
+        scale = pack_scale(float(top.item()))
+        mark("shard_uploaded")
         if int(rows_b.shape[0]) == 0 or qa == 0:
             inf = torch.full((qa,), float("inf"), dtype=torch.float64, device=a.device)
             return torch.full((qa,), -1, dtype=torch.int64, device=a.device), inf, inf.clone()
-        a_packed, _ = ops.match_pack(a, rows_a, scale)
-        b_packed, b_sqnorm = ops.match_pack(b, rows_b, scale)
-        _, cand = ops.match_topk(a_packed, b_packed, b_sqnorm, k, 0, True)
-        nn, d1, d2 = ops.match_rerank(a, rows_a, b, rows_b, cand)
+        nn, d1, d2, _ = exact_nearest(a, rows_a, b, rows_b, scale, k, want_second=True)
+        mark("shard_searched")
         return rows_b[nn.long()].long() + lo, d1, d2  # original reference row ids
 
     nn, d1, d2 = sharded_nearest(int(ref.shape[0]), shard, group)
+    mark("gathered_and_merged")
     torch.cuda.synchronize()
+    _elapsed(t)
     return rows_a.cpu().numpy(), nn.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()

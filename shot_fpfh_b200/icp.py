@@ -42,7 +42,10 @@ def icp_point_to_plane(
     ref_dev, normals_dev, scan_dev = upload(ref), upload(ref_normals), upload(scan)
     grid = Grid().build(ref_dev, normals_dev, float(d_max))
     subsampled = scan_dev[ops.voxel_subsample(scan_dev, float(voxel_size))].contiguous()  # icp.py:156
-    transformation_icp = transformation_init
+    # any object with .rotation / .translation (the reference's own RigidTransform under dropin, the ground truth of
+    # get_transform_from_conf_file, ...) is taken as the initial transformation
+    transformation_icp = RigidTransform(np.asarray(transformation_init.rotation, dtype=np.float64),
+                                        np.asarray(transformation_init.translation, dtype=np.float64))
     rms = 0.0
     upper = np.triu_indices(6)
     try:

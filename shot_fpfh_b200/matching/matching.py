@@ -3,10 +3,17 @@ Descriptor matching with the reference's signatures (shot_fpfh/matching/matching
 
 The reference materialises the full float64 `cdist` matrix and takes `argmin`. Here (csrc/match.cu, match_tc.cu):
 non-empty rows are compacted on the device, a tensor-core distance GEMM on float16 copies of the rows keeps a
-k-candidate shortlist per query without ever writing the matrix, and the shortlist is re-ranked with the exact
-float64 distance accumulated in SciPy's order — so the returned indices and nearest-neighbour distances are the
-reference's, provided the true nearest neighbour is among the k float16 candidates (k = 4 already
-gives 100 % on real SHOT rows; the default here is 8, and `exhaustive_check` in the tests measures it).
+k-candidate shortlist per query without ever writing the matrix, the shortlist is re-ranked with the exact float64
+distance accumulated in SciPy's order, and a CERTIFICATE decides per query whether the shortlist provably contained
+the nearest (second-nearest) neighbour: the k-th shortlist score bounds the distance to everything outside it, up to
+the float16 rounding of the operands and the float32 accumulation (csrc/match.cu::certify_kernel). Queries that are
+not certified — adversarial near-ties, rows that quantise to zero next to a large one — are redone exhaustively in
+float64, so the returned indices and distances are `cdist(...).argmin()`'s in every case; `LAST_STATS` counts them.
+
+Parity limits, stated: (1) descriptors that this package produced are float32 values widened to float64 (1e-7
+relative against the reference's float64 rows): matching is exact on the rows it is given, near-ties between the two
+versions of a row can resolve differently; (2) NaN or infinite entries raise ValueError (the reference's argmin over
+NaN distances silently returns the first NaN column).
 """
 
 from __future__ import annotations
@@ -19,9 +26,11 @@ import numpy.typing as npt
 import torch
 
 from .. import ops
-from ..device import upload
+from ..device import device_rows_of, upload
 
 DEFAULT_SHORTLIST = 8
+USE_TENSOR_CORES = True  # the tests switch it off to cross-check the two shortlist kernels
+LAST_STATS = {"queries": 0, "fallback_rows": 0, "handoff": 0}  # of the last public call (measurement)
 
 
 class DeviceMatch:
@@ -31,14 +40,68 @@ class DeviceMatch:
         self.rows_a, self.rows_b, self.nn, self.d1, self.d2 = rows_a, rows_b, nn, d1, d2
 
 
-def _prepare(desc) -> tuple[torch.Tensor, torch.Tensor]:
-    dev = upload(desc)
+def _to_device(desc) -> torch.Tensor:
+    """float64 device rows of `desc`; the float32 rows a descriptor call left on the device when `desc` is the very
+    array that call returned (device.remember_device_rows) — no PCIe transfer then."""
+    cached = device_rows_of(desc)
+    if cached is not None:
+        LAST_STATS["handoff"] += 1
+        return cached.double()
+    return upload(desc)
+
+
+def _prepare(desc) -> tuple[torch.Tensor, torch.Tensor, float]:
+    dev = _to_device(desc)
     if dev.dim() != 2:
         raise ValueError("descriptors must be a 2-D (n, width) array")
-    return dev, ops.nonempty_rows(dev)
+    rows, top = ops.nonempty_rows(dev, want_absmax=True)
+    return dev, rows, top
 
 
-def nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k: int = DEFAULT_SHORTLIST, tensor_cores: bool = True):
+def largest(*tops: float) -> float:
+    """max that keeps a NaN / inf (Python's max drops a NaN that is not first)."""
+    return float(np.max(np.asarray(tops, dtype=np.float64)))  # np.max propagates NaN
+
+
+def pack_scale(top: float) -> float:
+    """Power-of-two scale that brings the largest |entry| just below 1 (float16 operands)."""
+    if not np.isfinite(top):
+        raise ValueError("descriptors contain NaN or infinite values")
+    return float(2.0 ** np.floor(np.log2(1.0 / max(top, 1e-300))))
+
+
+def exact_nearest(a_dev, rows_a, b_dev, rows_b, scale: float, k: int = DEFAULT_SHORTLIST, want_second: bool = False,
+                  packed_b=None):
+    """
+    For every row rows_a of a: the nearest and second-nearest rows rows_b of b (positions in rows_b, float64
+    distances, lowest index on ties) — shortlist GEMM, exact re-rank, certificate, exhaustive redo of the queries
+    the certificate rejects. `want_second`: the second distance is certified too (the ratio test needs it).
+    Returns (nn int32, d1, d2, packed_b) device tensors; packed_b = (float16 rows, squared norms, largest norm) of b.
+    """
+    width = int(a_dev.shape[1])
+    # the tcgen05 kernel keeps a 128-row tile of <= 384 columns resident; wider rows (multi-scale SHOT, FPFH with
+    # n_bins >= 8) take the CUDA-core shortlist kernel, which loops over any width
+    tensor_cores = ops.padded_width(width) <= 384 and USE_TENSOR_CORES
+    a_packed, a_sqnorm = ops.match_pack(a_dev, rows_a, scale)
+    if packed_b is None:
+        b_packed, b_sqnorm = ops.match_pack(b_dev, rows_b, scale)
+        packed_b = (b_packed, b_sqnorm, float(b_sqnorm.max().sqrt().item()))
+    b_packed, b_sqnorm, b_norm_max = packed_b
+    score, cand = ops.match_topk(a_packed, b_packed, b_sqnorm, k, 0, tensor_cores)
+    nn, d1, d2 = ops.match_rerank(a_dev, rows_a, b_dev, rows_b, cand)
+    flags = ops.match_certify(score, a_sqnorm, d1, d2, scale, b_norm_max, width, int(rows_b.shape[0]), want_second)
+    which = torch.nonzero(flags).squeeze(1)
+    LAST_STATS["queries"] += int(rows_a.shape[0])
+    if int(which.shape[0]):
+        LAST_STATS["fallback_rows"] += int(which.shape[0])
+        ops.match_exhaustive_topk(a_dev, rows_a, which, b_dev, rows_b, cand)
+        nn_f, d1_f, d2_f = ops.match_rerank(a_dev, rows_a[which].contiguous(), b_dev, rows_b, cand[which].contiguous())
+        nn[which], d1[which], d2[which] = nn_f, d1_f, d2_f
+    return nn, d1, d2, packed_b
+
+
+def nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k: int = DEFAULT_SHORTLIST, want_second: bool = False,
+                             top: float | None = None):
     """
     For every non-empty row of a: the nearest and second-nearest non-empty rows of b (float64 distances, lowest
     index on ties). Returns device tensors (nn positions in rows_b, d1, d2).
@@ -49,18 +112,17 @@ def nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k: int = DEFAULT_SHOR
         return e.to(torch.int32), e.to(torch.float64), e.to(torch.float64)
     if qb == 0:
         raise ValueError("attempt to get argmin of an empty sequence")  # what NumPy raises in the reference
-    scale = 1.0 / max(float(a_dev.abs().max().item()), float(b_dev.abs().max().item()), 1e-300)
-    a_packed, _ = ops.match_pack(a_dev, rows_a, scale)
-    b_packed, b_sqnorm = ops.match_pack(b_dev, rows_b, scale)
-    _, cand = ops.match_topk(a_packed, b_packed, b_sqnorm, k, 0, tensor_cores)
-    return ops.match_rerank(a_dev, rows_a, b_dev, rows_b, cand)
+    if top is None:
+        top = largest(ops.nonempty_rows(a_dev, want_absmax=True)[1], ops.nonempty_rows(b_dev, want_absmax=True)[1])
+    nn, d1, d2, _ = exact_nearest(a_dev, rows_a, b_dev, rows_b, pack_scale(top), k, want_second)
+    return nn, d1, d2
 
 
 _PIPELINE_MIN_ROWS = 65536  # scan sets at least this large cross PCIe in chunks under the shortlist GEMM
 _PIPELINE_CHUNK_ROWS = 3 * 148 * 128  # three full waves of the shortlist kernel's 128-query CTAs on 148 SMs
 
 
-def _upload_pipelined(scan: np.ndarray, ref: np.ndarray, k: int, tensor_cores: bool):
+def _upload_pipelined(scan: np.ndarray, ref: np.ndarray, k: int, want_second: bool):
     """
     Host arrays in: the reference rows are copied first, then the scan rows in chunks of `_PIPELINE_CHUNK_ROWS` on a
     side stream; the shortlist GEMM + exact re-rank of chunk c (against all the reference rows) run while chunk c + 1
@@ -94,26 +156,20 @@ def _upload_pipelined(scan: np.ndarray, ref: np.ndarray, k: int, tensor_cores: b
             ev.record(side)
             arrived.append(ev)
     cur.wait_event(arrived[0])
-    rows_b = ops.nonempty_rows(b_dev)
+    rows_b, b_top = ops.nonempty_rows(b_dev, want_absmax=True)
     qb = int(rows_b.shape[0])
-    b_top = b_dev.abs().max() if b_dev.numel() else b_dev.new_zeros(())
-    packed_b: dict[float, tuple[torch.Tensor, torch.Tensor]] = {}
+    packed_b: dict[float, tuple] = {}
     rows_a_parts, nn_parts, d1_parts, d2_parts = [], [], [], []
     for c in range(len(bounds) - 1):
         cur.wait_event(arrived[c + 1])
         chunk = a_dev[bounds[c]:bounds[c + 1]]
-        rows_c = ops.nonempty_rows(chunk)
+        rows_c, a_top = ops.nonempty_rows(chunk, want_absmax=True)
         if int(rows_c.shape[0]) == 0:
             continue
         if qb == 0:
             raise ValueError("attempt to get argmin of an empty sequence")  # what NumPy raises in the reference
-        top = max(float(torch.maximum(b_top, chunk.abs().max()).item()), 1e-300)
-        scale = float(2.0 ** np.floor(np.log2(1.0 / top)))
-        if scale not in packed_b:
-            packed_b[scale] = ops.match_pack(b_dev, rows_b, scale)
-        a_packed, _ = ops.match_pack(chunk, rows_c, scale)
-        _, cand = ops.match_topk(a_packed, packed_b[scale][0], packed_b[scale][1], k, 0, tensor_cores)
-        nn, d1, d2 = ops.match_rerank(chunk, rows_c, b_dev, rows_b, cand)
+        scale = pack_scale(largest(a_top, b_top))
+        nn, d1, d2, packed_b[scale] = exact_nearest(chunk, rows_c, b_dev, rows_b, scale, k, want_second, packed_b.get(scale))
         rows_a_parts.append(rows_c + bounds[c])
         nn_parts.append(nn)
         d1_parts.append(d1)
@@ -125,24 +181,37 @@ def _upload_pipelined(scan: np.ndarray, ref: np.ndarray, k: int, tensor_cores: b
     return a_dev, torch.cat(rows_a_parts), b_dev, rows_b, torch.cat(nn_parts), torch.cat(d1_parts), torch.cat(d2_parts)
 
 
-def _match(scan, ref, k=DEFAULT_SHORTLIST, reverse=False, tensor_cores=True):
+def _match(scan, ref, k=DEFAULT_SHORTLIST, reverse=False, want_second=False, tensor_cores=True):
+    global USE_TENSOR_CORES
+    previous, USE_TENSOR_CORES = USE_TENSOR_CORES, bool(tensor_cores)
+    try:
+        return _match_impl(scan, ref, k, reverse, want_second)
+    finally:
+        USE_TENSOR_CORES = previous
+
+
+def _match_impl(scan, ref, k, reverse, want_second):
+    LAST_STATS.update(queries=0, fallback_rows=0, handoff=0)
     pipelined = (
         isinstance(scan, np.ndarray) and isinstance(ref, np.ndarray) and scan.ndim == 2 and ref.ndim == 2
         and scan.shape[1] == ref.shape[1] and scan.shape[0] >= _PIPELINE_MIN_ROWS
+        and device_rows_of(scan) is None  # rows that are already on the device do not cross PCIe at all
     )
     if pipelined:
-        a_dev, rows_a, b_dev, rows_b, nn, d1, d2 = _upload_pipelined(scan, ref, k, tensor_cores)
+        a_dev, rows_a, b_dev, rows_b, nn, d1, d2 = _upload_pipelined(scan, ref, k, want_second)
+        top = None
     else:
-        a_dev, rows_a = _prepare(scan)
-        b_dev, rows_b = _prepare(ref)
+        a_dev, rows_a, a_top = _prepare(scan)
+        b_dev, rows_b, b_top = _prepare(ref)
         if a_dev.shape[1] != b_dev.shape[1]:
             raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")
-        nn, d1, d2 = nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k, tensor_cores)
+        top = largest(a_top, b_top)
+        nn, d1, d2 = nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k, want_second, top)
     fwd = DeviceMatch(rows_a.cpu().numpy(), rows_b.cpu().numpy(), nn.cpu().numpy().astype(np.int64), d1.cpu().numpy(),
                       d2.cpu().numpy())
     if not reverse:
         return fwd, None
-    nn_r, _, _ = nearest_neighbors_device(b_dev, rows_b, a_dev, rows_a, k, tensor_cores)
+    nn_r, _, _ = nearest_neighbors_device(b_dev, rows_b, a_dev, rows_a, k, False, top)
     return fwd, nn_r.cpu().numpy().astype(np.int64)
 
 
@@ -242,7 +311,7 @@ def double_matching_with_rejects(
     second-nearest reference descriptors, keep the scan descriptors whose ratio d1 / d2 (1 where d2 == 0) is
     `>= threshold` — the comparison as written at matching.py:203-211 — and match them to their nearest neighbour.
     """
-    m, _ = _match(scan_descriptors, ref_descriptors)
+    m, _ = _match(scan_descriptors, ref_descriptors, want_second=True)
     d2 = np.where(np.isfinite(m.d2), m.d2, 0.0)  # a single candidate: no second neighbour -> ratio 1
     ratio = np.divide(m.d1, d2, out=np.ones_like(m.d1), where=d2 != 0)
     mask = ratio >= threshold

@@ -327,12 +327,17 @@ def fpfh(
 
 
 # ---- matching -------------------------------------------------------------------------------------------------
-def nonempty_rows(desc: torch.Tensor) -> torch.Tensor:
+def nonempty_rows(desc: torch.Tensor, want_absmax: bool = False):
+    """Ids of the rows with a non-zero entry; with `want_absmax` also the largest |x| of the array (same pass; NaN or
+    inf when the array holds one): (rows, absmax)."""
     n, width = int(desc.shape[0]), int(desc.shape[1])
     rows = torch.empty(max(n, 1), dtype=torch.int64, device=desc.device)
     count = ctypes.c_int64(0)
-    check(lib.sf_nonempty_rows(ptr(desc), n, width, ptr(rows), ctypes.byref(count), stream_ptr()))
-    return rows[: int(count.value)]
+    absmax = ctypes.c_double(0.0)
+    check(lib.sf_nonempty_rows(ptr(desc), n, width, ptr(rows), ctypes.byref(count),
+                               ctypes.byref(absmax) if want_absmax else None, stream_ptr()))
+    rows = rows[: int(count.value)]
+    return (rows, float(absmax.value)) if want_absmax else rows
 
 
 def padded_width(width: int) -> int:
@@ -369,6 +374,23 @@ def topk_merge(score: torch.Tensor, idx: torch.Tensor):
     io = torch.empty((qa, k), dtype=torch.int32, device=score.device)
     check(lib.sf_topk_merge(ptr(score.contiguous()), ptr(idx.contiguous()), parts, qa, k, ptr(so), ptr(io), stream_ptr()))
     return so, io
+
+
+def match_certify(score, a_sqnorm, d1, d2, scale: float, b_norm_max: float, width: int, qb: int, want_second: bool):
+    """uint8 (qa,) flags: 1 where the shortlist does not provably contain the nearest (second-nearest) neighbour."""
+    qa, k = int(score.shape[0]), int(score.shape[1])
+    flags = torch.empty(qa, dtype=torch.uint8, device=score.device)
+    check(lib.sf_match_certify(ptr(score.contiguous()), k, ptr(a_sqnorm), ptr(d1), ptr(d2), qa, float(scale),
+                               float(b_norm_max), int(width), int(qb), int(bool(want_second)), ptr(flags), stream_ptr()))
+    return flags
+
+
+def match_exhaustive_topk(a_desc, rows_a, which, b_desc, rows_b, cand_idx) -> None:
+    """Rewrites the rows `which` of the (qa, k) shortlist `cand_idx` with the exhaustive float64 k nearest targets."""
+    k = int(cand_idx.shape[1])
+    check(lib.sf_match_exhaustive_topk(ptr(a_desc), ptr(rows_a), ptr(which.contiguous()), int(which.shape[0]), ptr(b_desc),
+                                       ptr(rows_b), int(rows_b.shape[0]), int(a_desc.shape[1]), k, ptr(cand_idx),
+                                       stream_ptr()))
 
 
 def match_rerank(a_desc, rows_a, b_desc, rows_b, cand_idx):
