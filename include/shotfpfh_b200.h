@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 6
+#define SF_ABI_VERSION 8
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -235,6 +235,14 @@ int sf_topk_merge(const float* score_dev, const int32_t* idx_dev, int32_t parts,
 int sf_match_certify(const float* score_dev, int32_t k, const float* a_sqnorm_dev, const double* d1_dev,
                      const double* d2_dev, int64_t qa, double scale, double b_norm_max, int32_t width, int64_t qb,
                      int32_t want_second, uint8_t* flags_dev, void* stream);
+/* The exhaustive redo of all flagged queries in ONE pass over the targets (tiles of 32 target rows in shared memory):
+ * limit_dev[i] = an upper bound on the wanted distance of flagged query which_dev[i] (its exact nearest / second-nearest
+ * distance from the re-rank); every target at most that far is listed and the 16 nearest of the list (float64 distance,
+ * then index) go to cand16_dev (n_which, 16), -1 padded, for sf_match_rerank. cand16_dev[i][0] = -2 marks a query with
+ * more than 64 such near-ties: those take sf_match_exhaustive_topk. */
+int sf_match_exhaustive(const double* a_dev, const int64_t* rows_a_dev, const int64_t* which_dev, int64_t n_which,
+                        const double* limit_dev, const double* b_dev, const int64_t* rows_b_dev, int64_t qb, int32_t width,
+                        int32_t* cand16_dev, void* stream);
 /* Exhaustive float64 shortlist of the flagged queries which_dev[0..n_which) (positions in rows_a): the k (8 or 16)
  * nearest targets by float64 distance, lowest index on ties, written into their rows of cand_dev (qa, k); the caller
  * re-ranks those rows with sf_match_rerank. */
@@ -286,6 +294,10 @@ int sf_rows_compact_fill(const float* dense_dev, int64_t n_rows, int32_t width, 
  * everything started has finished and reports a malformed input. The buffers must stay valid until then. */
 int sf_host_expand_rows_begin(const int64_t* offsets_host, const uint16_t* cols_host, const float* vals_host,
                               int64_t n_rows, int32_t width, double* dst_host, int32_t threads);
+/* Host helpers of the same transport: parallel copy of pageable caller memory into a page-locked staging buffer by the
+ * pool (completed by sf_host_wait), and a huge-page hint for a freshly allocated result buffer. */
+int sf_host_copy_begin(const void* src_host, void* dst_host, int64_t bytes, int32_t threads);
+int sf_host_advise_huge(void* ptr_host, int64_t bytes);
 /* dst[i] = (double)src[i] for i in [0, n) by the same pool (started, not awaited: the float32 rows of one block are
  * widened into the float64 result the reference API returns while the next block crosses PCIe; a float32 D2H copy
  * plus this costs less than copying float64). Jobs run in the order they were started; sf_host_wait awaits all. */

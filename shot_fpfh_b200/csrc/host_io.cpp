@@ -11,6 +11,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -210,6 +213,38 @@ extern "C" int sf_host_widen_begin(const float* src, int64_t n, double* dst, int
     if (avx2) widen_avx2(src + lo, dst + lo, hi - lo);
     else for (int64_t i = lo; i < hi; ++i) dst[i] = double(src[i]);
   });
+  return SF_OK;
+}
+
+// Parallel copy of `bytes` from pageable caller memory into a page-locked staging buffer (the DMA engine then takes it
+// from there): a single memcpy runs at ~10 GB/s, the pool's threads together at the host's memory bandwidth.
+extern "C" int sf_host_copy_begin(const void* src, void* dst, int64_t bytes, int32_t threads) {
+  if (bytes < 0 || (bytes > 0 && (src == nullptr || dst == nullptr))) {
+    sf::set_error("sf_host_copy_begin: bad arguments");
+    return SF_ERR_ARG;
+  }
+  if (bytes == 0) return SF_OK;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  Pool& pool = pool_for(clamp_threads(threads));
+  const int parts = int(std::max<int64_t>(1, std::min<int64_t>(std::min(clamp_threads(threads), pool.workers()), bytes / 65536)));
+  pool.start(parts, [=](int p) {  // waits for the previous job first
+    int64_t lo, hi;
+    share(bytes, p, parts, 4096, lo, hi);
+    if (hi > lo) memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, size_t(hi - lo));
+  });
+  return SF_OK;
+}
+
+// madvise(MADV_HUGEPAGE) on a fresh result buffer: its first touch then costs one fault per 2 MB instead of per 4 KB
+// (288 MB of SHOT rows: 70 000 faults, ~20 ms, spread over the writers). A hint: ignored where THP is off.
+extern "C" int sf_host_advise_huge(void* ptr, int64_t bytes) {
+#if defined(__linux__)
+  if (ptr != nullptr && bytes > 0) {
+    const uintptr_t page = 2u << 20, lo = (reinterpret_cast<uintptr_t>(ptr) + page - 1) & ~(page - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + uintptr_t(bytes)) & ~(page - 1);
+    if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+  }
+#endif
   return SF_OK;
 }
 

@@ -331,6 +331,85 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The exhaustive redo as ONE pass over the targets for all the flagged queries together: a block stages 32 target rows
+// in shared memory (column-major: lane = target, conflict-free) and every warp runs its share of the flagged queries
+// against them in float64. Only targets at most `limit[q]` away matter — the exact nearest (second-nearest) distance
+// the re-rank already found bounds the true one from above — so they are appended to a short per-query list
+// (kExhaustiveCap entries; a query with more such near-ties is marked for the block-per-query kernel above).
+constexpr int kExhaustiveTile = 32;
+constexpr int kExhaustiveCap = 64;
+
+__global__ void __launch_bounds__(256)
+    exhaustive_tile_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a,
+                           const int64_t* __restrict__ which, int64_t n_which, const double* __restrict__ limit,
+                           const double* __restrict__ b, const int64_t* __restrict__ rows_b, int64_t qb, int width,
+                           int32_t* __restrict__ counts, double* __restrict__ list_d, int32_t* __restrict__ list_i) {
+  extern __shared__ double tile[];  // [width][kExhaustiveTile]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t first = blockIdx.x * int64_t(kExhaustiveTile);
+  for (int e = threadIdx.x; e < width * kExhaustiveTile; e += blockDim.x) {
+    const int t = e / width, c = e - t * width;  // consecutive threads read consecutive columns of a row
+    const int64_t j = first + t;
+    tile[c * kExhaustiveTile + t] = j < qb ? b[(rows_b ? rows_b[j] : j) * width + c] : 0.0;
+  }
+  __syncthreads();
+  const int64_t j = first + lane;
+  for (int64_t item = warp; item < n_which; item += 8) {
+    const int64_t q = which[item];
+    const double* ra = a + (rows_a ? rows_a[q] : q) * width;
+    double s0 = 0.0, s1 = 0.0;
+    int c = 0;
+    for (; c + 1 < width; c += 2) {
+      const double d0 = __ldg(ra + c) - tile[c * kExhaustiveTile + lane];
+      const double d1 = __ldg(ra + c + 1) - tile[(c + 1) * kExhaustiveTile + lane];
+      s0 = fma(d0, d0, s0);
+      s1 = fma(d1, d1, s1);
+    }
+    if (c < width) {
+      const double d0 = __ldg(ra + c) - tile[c * kExhaustiveTile + lane];
+      s0 = fma(d0, d0, s0);
+    }
+    const double d2 = s0 + s1, lim = limit[item];
+    if (j < qb && d2 <= lim * lim * (1.0 + 1e-12)) {
+      const int slot = atomicAdd(counts + item, 1);
+      if (slot < kExhaustiveCap) {
+        list_d[item * kExhaustiveCap + slot] = d2;
+        list_i[item * kExhaustiveCap + slot] = int32_t(j);
+      }
+    }
+  }
+}
+
+// The 16 nearest of each flagged query's list (by distance, then index), -1 padded; cand[item][0] = -2 marks a list
+// that overflowed.
+__global__ void exhaustive_select_kernel(int64_t n_which, const int32_t* __restrict__ counts,
+                                         const double* __restrict__ list_d, const int32_t* __restrict__ list_i,
+                                         int32_t* __restrict__ cand) {
+  const int64_t item = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (item >= n_which) return;
+  const int n = counts[item];
+  int32_t* out = cand + item * 16;
+  if (n > kExhaustiveCap) {
+    for (int t = 0; t < 16; ++t) out[t] = t == 0 ? -2 : -1;
+    return;
+  }
+  const double* d = list_d + item * kExhaustiveCap;
+  const int32_t* id = list_i + item * kExhaustiveCap;
+  double last_d = -1.0;
+  int last_i = -1;
+  for (int t = 0; t < 16; ++t) {  // selection in (distance, index) order: the list is short
+    int pick = -1;
+    for (int e = 0; e < n; ++e) {
+      const bool after = d[e] > last_d || (d[e] == last_d && id[e] > last_i);
+      if (!after) continue;
+      if (pick < 0 || d[e] < d[pick] || (d[e] == d[pick] && id[e] < id[pick])) pick = e;
+    }
+    out[t] = pick >= 0 ? id[pick] : -1;
+    if (pick >= 0) { last_d = d[pick]; last_i = id[pick]; }
+    else { last_d = INFINITY; }
+  }
+}
+
 struct IsSet {
   const uint8_t* flags;
   __host__ __device__ bool operator()(int64_t i) const { return flags[i] != 0; }
@@ -475,6 +554,38 @@ extern "C" int sf_match_exhaustive_topk(const double* a, const int64_t* rows_a, 
   else
     exhaustive_topk_kernel<16><<<unsigned(n_which), 256, 0, stream>>>(a, rows_a, which, n_which, b, rows_b, qb, width, cand);
   SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_match_exhaustive(const double* a, const int64_t* rows_a, const int64_t* which, int64_t n_which,
+                                   const double* limit, const double* b, const int64_t* rows_b, int64_t qb, int32_t width,
+                                   int32_t* cand16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(a && which && limit && b && cand16 && width > 0, SF_ERR_ARG, "sf_match_exhaustive: bad arguments");
+  SF_REQUIRE(qb < (int64_t(1) << 31), SF_ERR_ARG, "sf_match_exhaustive: too many targets");
+  if (n_which == 0) return SF_OK;
+  const size_t smem = size_t(width) * kExhaustiveTile * sizeof(double);
+  SF_REQUIRE(smem <= 200 * 1024, SF_ERR_CAPACITY, "sf_match_exhaustive: rows of %d columns do not fit the tile", width);
+  static bool configured = false;
+  if (!configured) {
+    SF_CUDA(cudaFuncSetAttribute(exhaustive_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  int32_t* counts = nullptr;
+  double* list_d = nullptr;
+  int32_t* list_i = nullptr;
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&counts), size_t(n_which) * 4, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&list_d), size_t(n_which) * kExhaustiveCap * 8, stream));
+  SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&list_i), size_t(n_which) * kExhaustiveCap * 4, stream));
+  SF_CUDA(cudaMemsetAsync(counts, 0, size_t(n_which) * 4, stream));
+  const unsigned tiles = unsigned((qb + kExhaustiveTile - 1) / kExhaustiveTile);
+  exhaustive_tile_kernel<<<tiles, 256, smem, stream>>>(a, rows_a, which, n_which, limit, b, rows_b, qb, width, counts, list_d,
+                                                       list_i);
+  exhaustive_select_kernel<<<unsigned((n_which + 127) / 128), 128, 0, stream>>>(n_which, counts, list_d, list_i, cand16);
+  SF_CUDA(cudaGetLastError());
+  cudaFreeAsync(counts, stream);
+  cudaFreeAsync(list_d, stream);
+  cudaFreeAsync(list_i, stream);
   return SF_OK;
 }
 

@@ -5,6 +5,8 @@ Everything here fails loudly when no CUDA device is present — there is no CPU 
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -37,7 +39,19 @@ def upload(a, dtype=torch.float64) -> torch.Tensor:
         return a.to(device=dev, dtype=dtype).contiguous()
     np_dtype = {torch.float64: np.float64, torch.float32: np.float32, torch.int64: np.int64, torch.int32: np.int32}[dtype]
     host = np.ascontiguousarray(a, dtype=np_dtype)
-    return torch.from_numpy(host).to(dev, non_blocking=True)
+    source = torch.from_numpy(host)
+    if host.nbytes >= _STAGED_UPLOAD_BYTES and not source.is_pinned() and not os.environ.get("SF_NO_STAGED_UPLOAD"):
+        # Pageable memory: the driver would stage the copy itself, synchronously and on one thread (50 MB of cloud:
+        # 9 ms). The library's host threads copy it into a page-locked block of PyTorch's caching host allocator (the
+        # allocator keeps the block until the copy queued below has run), and the DMA engine takes it from there.
+        staging = torch.empty(host.shape, dtype=dtype, pin_memory=True)
+        check(lib.sf_host_copy_begin(host.ctypes.data, staging.data_ptr(), host.nbytes, host_threads()))
+        check(lib.sf_host_wait())
+        return staging.to(dev, non_blocking=True)
+    return source.to(dev, non_blocking=True)
+
+
+_STAGED_UPLOAD_BYTES = 4 << 20
 
 
 def download(t: torch.Tensor) -> np.ndarray:
@@ -73,45 +87,41 @@ def host_threads(requested: int | None = None) -> int:
 
 
 # ---- host result buffers ------------------------------------------------------------------------------------------
-# The dense float64 arrays the reference API returns are WRITTEN BY HOST THREADS (never by DMA), so they need not be
-# page-locked; what matters is what a fresh 288 MB buffer costs. Measured: a page-locked block from PyTorch's caching
-# host allocator is free when the cache holds one — a caller that drops each result before or right after the next call
-# (a benchmark loop) — but ~200 ms of cudaHostAlloc when it does not: a caller that KEEPS its results (the registration
-# pipeline holds the scan's descriptors while the reference cloud's are computed; 226 ms per SHOT call at 1M points for
-# 4 ms of work). A fresh pageable array costs ~20 ms of page faults spread over the pool's threads either way.
-# Policy, per result shape: pageable until the caller has been seen to drop a result of this shape; from then on
-# page-locked, creating (once) the block in use plus one spare, since `d = f()` in a loop keeps the previous result
-# alive during the call. Steady state is reached at the fourth call of a loop.
-class _ShapeHistory:
-    def __init__(self) -> None:
-        self.alive: list[tuple[object, bool]] = []  # (weak reference to the buffer's owner, page-locked?)
-        self.released = 0
-        self.pinned_created = 0
+# The dense float64 arrays the reference API returns are WRITTEN BY HOST THREADS (never by DMA), so they are plain
+# NumPy memory. What a fresh 288 MB buffer costs is its first touch (70 000 page faults, ~20 ms), so a buffer the caller
+# has dropped is handed out again instead. Measured on the B200 hosts (same box, alternating runs): the pool's threads
+# fill memory from cudaHostAlloc in 3.4 ms per call at C2, pageable memory in 4.4-5.7 ms (bimodal), pageable memory
+# page-locked in place (cudaHostRegister) in 5.6-5.8 ms, huge-page-advised memory in 7.0 ms; but cudaHostAlloc costs
+# ~100-200 ms per buffer. So: a FRESH buffer is pageable (a pipeline that keeps its results never pays the page-locked
+# allocation), and the first time a dropped buffer would be handed out again — a caller that loops — it is replaced,
+# once, by a cudaHostAlloc block that is then recycled.
+# The pool owns the base arrays; the caller gets a VIEW, so the base's reference count tells when every reference to
+# a result (views and slices included) is gone.
+_RESULT_POOL: list[list] = []  # [base array, from cudaHostAlloc?]
+_RESULT_POOL_BYTES = 4 << 30
 
 
-_RESULTS: dict[tuple, _ShapeHistory] = {}
-
-
-def result_buffer(shape) -> tuple[torch.Tensor, np.ndarray]:
-    """(float64 host tensor of `shape`, the ndarray over it that the API returns). Return THAT ndarray (or views of
-    it): its lifetime is what tells later calls whether the buffer was released."""
-    import weakref
+def result_buffer(shape) -> tuple[np.ndarray, np.ndarray]:
+    """(float64 base array of `shape`, the view of it that the API returns — return THAT view or views of it)."""
+    import sys
 
     shape = tuple(int(x) for x in shape)
-    h = _RESULTS.setdefault(shape, _ShapeHistory())
-    still = [(r, p) for r, p in h.alive if r() is not None]
-    h.released += len(h.alive) - len(still)
-    h.alive = still
-    free_pinned = h.pinned_created - sum(1 for _, p in h.alive if p)
-    pinned = free_pinned > 0 or h.released > 0
-    out = torch.empty(shape, dtype=torch.float64, pin_memory=pinned)
-    if pinned and free_pinned <= 0:  # invest: this block and a spare for the `d = f()` loop
-        spare = torch.empty(shape, dtype=torch.float64, pin_memory=True)  # while `out` holds the first block
-        del spare  # back to the caching allocator as a free block
-        h.pinned_created += 2
-    arr = out.numpy()
-    h.alive.append((weakref.ref(arr.base), pinned))  # the tensor object the ndarray (and its views) keep alive
-    return out, arr
+    count = int(np.prod(shape)) if shape else 1
+    entry = None
+    for i in range(len(_RESULT_POOL)):
+        # references: the pool's entry and getrefcount's argument -> 2 when no caller holds a view of it any more
+        if _RESULT_POOL[i][0].size == count and sys.getrefcount(_RESULT_POOL[i][0]) == 2:
+            entry = _RESULT_POOL.pop(i)
+            if not entry[1] and entry[0].nbytes >= (8 << 20) and torch.cuda.is_available():
+                entry = [torch.empty(count, dtype=torch.float64, pin_memory=True).numpy(), True]
+            break
+    if entry is None:
+        entry = [np.empty(count, dtype=np.float64), False]
+    _RESULT_POOL.append(entry)
+    held = sum(e[0].nbytes for e in _RESULT_POOL)
+    while held > _RESULT_POOL_BYTES and len(_RESULT_POOL) > 1:  # the pool forgets its oldest arrays (their views live on)
+        held -= _RESULT_POOL.pop(0)[0].nbytes
+    return entry[0], entry[0].reshape(shape)
 
 
 def download_widened(t: torch.Tensor, threads: int | None = None, blocks: int = 8) -> np.ndarray:
@@ -144,7 +154,7 @@ def download_widened(t: torch.Tensor, threads: int | None = None, blocks: int = 
         for b in range(blocks):
             events[b].synchronize()
             check(lib.sf_host_widen_begin(staging.data_ptr() + 4 * bounds[b], bounds[b + 1] - bounds[b],
-                                          result.data_ptr() + 8 * bounds[b], n_threads))
+                                          result.ctypes.data + 8 * bounds[b], n_threads))
     finally:
         check(lib.sf_host_wait())  # the staging buffer is read by the pool until here
     return result_arr
@@ -195,7 +205,7 @@ class DenseRowsDownload:
             for lo, n, done, _ in self._blocks:
                 done.synchronize()
                 check(lib.sf_host_widen_begin(self.staging.data_ptr() + 4 * lo * self.width, n * self.width,
-                                              self.result.data_ptr() + 8 * lo * self.width, self.threads))
+                                              self.result.ctypes.data + 8 * lo * self.width, self.threads))
         finally:
             check(lib.sf_host_wait())  # the staging buffer is read by the pool until here
             self._blocks = []
@@ -255,7 +265,7 @@ class SparseRowsDownload:
         self._keep += [h_offsets, h_cols, h_vals]  # read by the host threads until finish()
         self._pending = True
         check(lib.sf_host_expand_rows_begin(h_offsets.data_ptr(), h_cols.data_ptr(), h_vals.data_ptr(), n, self.width,
-                                            self.result.data_ptr() + 8 * self.filled * self.width, self.threads))
+                                            self.result.ctypes.data + 8 * self.filled * self.width, self.threads))
         self.filled += n
 
     def finish(self) -> np.ndarray:

@@ -94,10 +94,24 @@ def exact_nearest(a_dev, rows_a, b_dev, rows_b, scale: float, k: int = DEFAULT_S
     LAST_STATS["queries"] += int(rows_a.shape[0])
     if int(which.shape[0]):
         LAST_STATS["fallback_rows"] += int(which.shape[0])
-        ops.match_exhaustive_topk(a_dev, rows_a, which, b_dev, rows_b, cand)
-        nn_f, d1_f, d2_f = ops.match_rerank(a_dev, rows_a[which].contiguous(), b_dev, rows_b, cand[which].contiguous())
-        nn[which], d1[which], d2[which] = nn_f, d1_f, d2_f
+        # (within the current SECOND distance: the redo then returns both neighbours exactly)
+        nn[which], d1[which], d2[which] = exhaustive_redo(a_dev, rows_a, which, b_dev, rows_b, d2[which])
     return nn, d1, d2, packed_b
+
+
+def exhaustive_redo(a_dev, rows_a, which, b_dev, rows_b, limit):
+    """Exact (nn, d1, d2) of the flagged queries `which`: one float64 pass over all the targets lists every target within
+    `limit` (the exact distance the re-rank found: an upper bound on the true one), the re-rank decides among the 16
+    nearest of the list; the rare query with more than 64 such near-ties gets a full float64 scan of its own."""
+    finite = torch.isfinite(limit)
+    limit = torch.where(finite, limit, torch.full_like(limit, 1e300))  # (fewer than two candidates so far: everything)
+    cand16 = ops.match_exhaustive(a_dev, rows_a, which, limit, b_dev, rows_b)
+    crowded = torch.nonzero(cand16[:, 0] == -2).squeeze(1)
+    if int(crowded.shape[0]):
+        full = torch.full((int(rows_a.shape[0]), 16), -1, dtype=torch.int32, device=a_dev.device)
+        ops.match_exhaustive_topk(a_dev, rows_a, which[crowded].contiguous(), b_dev, rows_b, full)
+        cand16[crowded] = full[which[crowded]]
+    return ops.match_rerank(a_dev, rows_a[which].contiguous(), b_dev, rows_b, cand16)
 
 
 def nearest_neighbors_device(a_dev, rows_a, b_dev, rows_b, k: int = DEFAULT_SHORTLIST, want_second: bool = False,

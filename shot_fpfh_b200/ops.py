@@ -385,6 +385,16 @@ def match_certify(score, a_sqnorm, d1, d2, scale: float, b_norm_max: float, widt
     return flags
 
 
+def match_exhaustive(a_desc, rows_a, which, limit, b_desc, rows_b) -> torch.Tensor:
+    """(n_which, 16) int32 shortlist of the flagged queries `which`: every target within `limit` (float64 per flagged
+    query), the 16 nearest of them; row[0] == -2 where more than 64 targets qualified (see sf_match_exhaustive)."""
+    n = int(which.shape[0])
+    cand = torch.empty((n, 16), dtype=torch.int32, device=a_desc.device)
+    check(lib.sf_match_exhaustive(ptr(a_desc), ptr(rows_a), ptr(which.contiguous()), n, ptr(limit.contiguous()), ptr(b_desc),
+                                  ptr(rows_b), int(rows_b.shape[0]), int(a_desc.shape[1]), ptr(cand), stream_ptr()))
+    return cand
+
+
 def match_exhaustive_topk(a_desc, rows_a, which, b_desc, rows_b, cand_idx) -> None:
     """Rewrites the rows `which` of the (qa, k) shortlist `cand_idx` with the exhaustive float64 k nearest targets."""
     k = int(cand_idx.shape[1])

@@ -259,34 +259,29 @@ def test_host_widening_equals_astype_float64():
     assert lib.sf_host_widen_begin(None, 5, None, 2) == SF_ERR_ARG
 
 
-def test_result_buffers_follow_the_callers_pattern(monkeypatch):
-    """device.result_buffer: pageable while the caller keeps its results, page-locked (block + one spare) once it
-    is seen dropping them — checked on the allocation requests, without a GPU."""
-    import torch
-
+def test_result_buffers_are_recycled_only_when_the_caller_dropped_them(monkeypatch):
+    """device.result_buffer: a buffer goes out again only when no reference to the previous result (views and slices
+    included) is left; results the caller keeps are never touched."""
     from shot_fpfh_b200 import device
 
-    requests = []
-    real_empty = torch.empty
-
-    def recording_empty(*args, **kwargs):
-        requests.append(bool(kwargs.get("pin_memory", False)))
-        kwargs["pin_memory"] = False  # no CUDA here
-        return real_empty(*args, **kwargs)
-
-    monkeypatch.setattr(torch, "empty", recording_empty)
-    monkeypatch.setattr(device, "_RESULTS", {})
+    monkeypatch.setattr(device, "_RESULT_POOL", [])
     kept = [device.result_buffer((50, 8))[1] for _ in range(4)]  # a pipeline that keeps its descriptors
-    assert requests == [False] * 4
+    for i, k in enumerate(kept):
+        k[...] = i
+    assert len({k.ctypes.data for k in kept}) == 4
     view = kept[0][10:20]
+    first = kept[1].ctypes.data
     del kept
-    requests.clear()
-    d = None
-    for _ in range(6):  # a loop `d = f()`: the previous result is alive during the call
-        d = device.result_buffer((60, 8))[1]
-    # calls 1 and 2 pageable; call 3 sees a dropped result: page-locked block + spare; then the two blocks alternate
-    assert requests == [False, False, True, True, True, True, True]
-    assert view.shape == (10, 8) and d.dtype == np.float64 and d.shape == (60, 8)
+    d = device.result_buffer((50, 8))[1]  # one of the three dropped buffers comes back ...
+    d[...] = 9.0
+    assert np.all(view == 0)  # ... never the one a slice still points into
+    addresses = {d.ctypes.data}
+    for _ in range(6):  # a loop `d = f()`: the previous result is alive during the call -> buffers alternate
+        d = device.result_buffer((50, 8))[1]
+        d[...] = 7.0
+        addresses.add(d.ctypes.data)
+    assert np.all(view == 0)
+    assert len(addresses) <= 3 and first in addresses and d.dtype == np.float64 and d.shape == (50, 8)
 
 
 def test_bench_reference_arm_prints_one_contract_line():
@@ -305,7 +300,9 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
     assert line["config"]["workload"].startswith("C2: SHOT single-scale, 1M-point")
     cpu = line["cpu_baseline"]
-    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and "queries" in cpu["sample"]
+    # the unmodified reference from baseline/_ref when it is installed, else the oracle port
+    assert cpu["kind"] in ("reference", "port") and cpu["cores"] >= 1 and cpu["value"] == line["value"]
+    assert "queries" in cpu["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
 
