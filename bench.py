@@ -608,6 +608,11 @@ def bench_fpfh(args, pk):
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg[dominant] / (stages[dominant] * 1e-3) / 1e9 / pk["hbm_gbs"],
                      "traffic": traffic, "algorithmic_bytes": alg[dominant],
                      "dram_frac": (traffic / (stages[dominant] * 1e-3) / 1e9 / pk["hbm_gbs"]) if traffic else None,
+                     # the roof that bounds this stage: the SMs' L1 data pipes (148 x 128 B per clock at 1965 MHz);
+                     # ncu (profiles/r01_fpfh_fused_metrics.txt): L1 data pipe 65 % busy — wavefronts, not bytes, fill it
+                     "l1": {"peak_GBps": 148 * 128 * 1.965, "achieved_GBps": alg[dominant] / (stages[dominant] * 1e-3) / 1e9,
+                            "frac": alg[dominant] / (stages[dominant] * 1e-3) / 1e9 / (148 * 128 * 1.965),
+                            "ncu_l1_data_pipe_busy": 0.65},
                      "note": "algorithmic bytes count one SPFH-row gather per neighbour pair (SURVEY.md 8d); the 144 MB table "
                              "is served by L1/L2, so the figure on algorithmic bytes can exceed the HBM peak: see `traffic` "
                              "(DRAM bytes per launch, ncu) - the FPFH stage is bound by the L1 data pipe, not by HBM",
