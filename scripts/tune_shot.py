@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variants", default="82,73,102,63")
+    ap.add_argument("--envs", default="", help="further variants, each a +-joined list of NAME=VALUE, separated by commas")
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune_shot.json"))
@@ -43,7 +44,7 @@ def main():
     results = {"queries": int(q), "points": int(pts.shape[0])}
 
     def run(tag, env):
-        for k in ("SF_FAST_SHAPE", "SF_SHOT_EXACT"):
+        for k in [k for k in os.environ if k.startswith("SF_")]:
             os.environ.pop(k, None)
         os.environ.update(env)
         out = torch.zeros((q, 352), dtype=torch.float32, device="cuda")
@@ -76,8 +77,10 @@ def main():
 
     exact = run("exact", {"SF_SHOT_EXACT": "1"})
     exact_norm = exact.double().norm(dim=1).clamp_min(1e-300)
-    for v in args.variants.split(","):
-        got = run(f"fast_{v}", {"SF_FAST_SHAPE": v})
+    variants = [(v, {"SF_FAST_SHAPE": v}) for v in args.variants.split(",") if v]
+    variants += [(e, dict(kv.split("=") for kv in e.split("+"))) for e in args.envs.split(",") if e]
+    for v, env in variants:
+        got = run(f"fast_{v}", env)
         err = (got.double() - exact.double()).norm(dim=1) / exact_norm
         zero_mismatch = int(((got.abs().sum(dim=1) == 0) != (exact.abs().sum(dim=1) == 0)).sum().item())
         results[f"fast_{v}"].update({"max_rel_l2_vs_exact": float(err.max().item()), "median_rel_l2_vs_exact": float(err.median().item()),

@@ -137,33 +137,40 @@ __device__ __forceinline__ void write_side_copy(const GridView& g, double px, do
 // grid performs afterwards, whatever the cloud.
 __global__ void __launch_bounds__(256)
     place_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ slots, int64_t n,
-                 const int32_t* __restrict__ cell_start, int32_t* __restrict__ arrived) {
-  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i >= n) return;
-  arrived[cell_start[keys[i]] + slots[i]] = int32_t(i);
-}
-
-__global__ void __launch_bounds__(256)
-    rank_reorder_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int64_t n,
-                        const uint32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
-                        const int32_t* __restrict__ arrived, int32_t* __restrict__ perm, double4* __restrict__ pts,
-                        double4* __restrict__ nrm, int32_t* __restrict__ inv_perm, GridView g,
-                        float4* __restrict__ xyzc, float4* __restrict__ nrm32) {
+                 const int32_t* __restrict__ cell_start, int2* __restrict__ arrived) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint32_t key = keys[i];
+  arrived[cell_start[key] + slots[i]] = make_int2(int32_t(i), int32_t(key));  // (one 8-byte store: one sector)
+}
+
+// One thread per SLOT of the cell-sorted order (round 2; the first version ran one thread per point in input order:
+// 32 lanes walked 32 different cells, 30 M sector look-ups for 1M points, 89 us, LSU-bound). A warp now covers 32
+// neighbouring slots = about four cells: the cell bounds, the walk over the cell-mates and every store of the sorted
+// arrays (a permutation inside the cell) touch the same few lines, and only the point's own coordinates and normal
+// are gathered from input order.
+__global__ void __launch_bounds__(256)
+    rank_reorder_kernel(const double* __restrict__ xyz, const double* __restrict__ normals, int64_t n,
+                        const int32_t* __restrict__ cell_start, const int2* __restrict__ arrived,
+                        int32_t* __restrict__ perm, double4* __restrict__ pts, double4* __restrict__ nrm,
+                        int32_t* __restrict__ inv_perm, GridView g, float4* __restrict__ xyzc,
+                        float4* __restrict__ nrm32) {
+  const int64_t t0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t0 >= n) return;
+  const int2 mine = arrived[t0];
+  const int64_t i = mine.x;
   // the point's own data first: these loads are in flight while the cell-mates are counted
-  const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+  const double px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
   double nx = 0.0, ny = 0.0, nz = 0.0;
   if (normals != nullptr) {
-    nx = normals[3 * i]; ny = normals[3 * i + 1]; nz = normals[3 * i + 2];
+    nx = __ldg(normals + 3 * i); ny = __ldg(normals + 3 * i + 1); nz = __ldg(normals + 3 * i + 2);
   }
-  const int b = cell_start[key], e = cell_start[key + 1];
+  const int b = cell_start[mine.y], e = cell_start[mine.y + 1];
   int rank = 0;
 #pragma unroll 4
-  for (int t = b; t < e; ++t) rank += __ldg(arrived + t) < int32_t(i);
+  for (int t = b; t < e; ++t) rank += arrived[t].x < mine.x;
   const int s = b + rank;
-  perm[s] = int32_t(i);
+  perm[s] = mine.x;
   inv_perm[i] = s;
   pts[s] = make_double4(px, py, pz, __longlong_as_double(static_cast<long long>(i)));
   if (normals != nullptr) nrm[s] = make_double4(nx, ny, nz, 0.0);
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(256)
     const double4 p = load_pt(g.pts + self_first + q);
     qx = p.x; qy = p.y; qz = p.z;
   }
-  const Runs runs = build_runs(g, qx, qy, qz, lane);
+  const Runs runs = build_runs(g, qx, qy, qz, lane, r2);  // (cells out of reach dropped)
   const int total = runs.pref[9];
   int64_t out = kFill ? offsets[q] : 0;
   int count = 0;
@@ -280,6 +287,7 @@ static void free_all(sf_grid* g) {
   cudaFree(g->status_dev);
   if (g->status_host) cudaFreeHost(g->status_host);
   cudaFree(g->shot_cand); cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
+  cudaFree(g->shot_runs);
   cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_pairs); cudaFree(g->shot_scan_temp);
   cudaFree(g->shot_nbr);
 }
@@ -328,7 +336,7 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
     SF_CUDA(cudaMalloc(&g->perm, n * sizeof(int32_t)));
     SF_CUDA(cudaMalloc(&g->inv_perm, n * sizeof(int32_t)));
     SF_CUDA(cudaMalloc(&g->keys_in, n * sizeof(uint32_t)));
-    SF_CUDA(cudaMalloc(&g->keys_out, n * sizeof(uint32_t)));
+    SF_CUDA(cudaMalloc(&g->keys_out, 2 * n * sizeof(uint32_t)));  // (radix: n keys; counting sort: n int2)
     SF_CUDA(cudaMalloc(&g->vals_in, n * sizeof(int32_t)));
     g->capacity = n;
   }
@@ -425,10 +433,10 @@ static int build_cells(sf_grid* g, const double* xyz, const double* normals, int
     reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->perm, g->pts, g->nrm, g->inv_perm, view, g->xyzc,
                                                g->nrm32);
   } else {
-    int32_t* arrived = reinterpret_cast<int32_t*>(g->keys_out);
+    int2* arrived = reinterpret_cast<int2*>(g->keys_out);  // (index, cell) per slot of the arrival order
     place_kernel<<<blocks, 256, 0, stream>>>(g->keys_in, g->vals_in, n, g->cell_start, arrived);
-    rank_reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->keys_in, g->cell_start, arrived, g->perm, g->pts,
-                                                    g->nrm, g->inv_perm, view, g->xyzc, g->nrm32);
+    rank_reorder_kernel<<<blocks, 256, 0, stream>>>(xyz, normals, n, g->cell_start, arrived, g->perm, g->pts, g->nrm,
+                                                    g->inv_perm, view, g->xyzc, g->nrm32);
   }
   SF_CUDA(cudaGetLastError());
   if (check_box)  // the verdict, for sf_grid_poll

@@ -108,6 +108,7 @@ struct sf_grid {
   int64_t* shot_cand = nullptr;
   int64_t* shot_cand_offsets = nullptr;
   int32_t* shot_counts = nullptr;
+  int4* shot_runs = nullptr;         // 5 x int4 per query: start[9], pref[1..9] of its culled runs (candidate_count_kernel)
   double* shot_lrf = nullptr;
   float* shot_frame32 = nullptr;
   int32_t* shot_worklist = nullptr;
@@ -181,9 +182,11 @@ __device__ __forceinline__ int cell_coord(double q, double origin, double inv_ce
   return int(c);
 }
 
-// The runs around cell (cx, cy, cz) — coordinates may lie outside the grid (queries off the cloud).
-__device__ __forceinline__ Runs build_runs_cell(const GridView& g, int cx, int cy, int cz, int lane) {
-  int s = 0, len = 0;
+// Lane j < 9 owns run j of the cell (cx, cy, cz) — coordinates may lie outside the grid (queries off the cloud):
+// its start in the cell-sorted array and its length (0 for the other lanes and for rows outside the grid).
+__device__ __forceinline__ void run_of_lane(const GridView& g, int cx, int cy, int cz, int lane, int& s, int& len) {
+  s = 0;
+  len = 0;
   if (lane < 9) {
     const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
@@ -193,6 +196,10 @@ __device__ __forceinline__ Runs build_runs_cell(const GridView& g, int cx, int c
       len = __ldg(g.cell_start + base + x1 + 1) - s;
     }
   }
+}
+
+// The table of runs from the (start, length) lanes 0..8 hold.
+__device__ __forceinline__ Runs runs_from_lanes(int s, int len, int lane) {
   int incl = len;
 #pragma unroll
   for (int o = 1; o < 16; o <<= 1) {
@@ -209,10 +216,73 @@ __device__ __forceinline__ Runs build_runs_cell(const GridView& g, int cx, int c
   return r;
 }
 
+// The runs around cell (cx, cy, cz).
+__device__ __forceinline__ Runs build_runs_cell(const GridView& g, int cx, int cy, int cz, int lane) {
+  int s, len;
+  run_of_lane(g, cx, cy, cz, lane, s, len);
+  return runs_from_lanes(s, len, lane);
+}
+
 __device__ __forceinline__ Runs build_runs(const GridView& g, double qx, double qy, double qz, int lane) {
   return build_runs_cell(g, cell_coord(qx, g.origin[0], g.inv_cell, g.dims[0]),
                          cell_coord(qy, g.origin[1], g.inv_cell, g.dims[1]),
                          cell_coord(qz, g.origin[2], g.inv_cell, g.dims[2]), lane);
+}
+
+// ---- culled candidate set of a fixed-radius query ---------------------------------------------------------------
+// A neighbouring cell whose nearest face lies farther than the radius from the query cannot hold a neighbour: with a
+// cell edge just above the radius that removes about half of the 8 corner cells and a fifth of the 12 edge cells (a
+// quarter of the candidates the exact test then rejects one by one). The gaps are LOWER bounds of the distance from the
+// query to the faces of its own cell (shrunk by more than the rounding of cell_coord on either side of a face), so a
+// cell is dropped only when every point that key_kernel can have put in it is out of reach.
+struct CellGaps {
+  int c[3];
+  double lo[3], hi[3];
+};
+
+__device__ __forceinline__ CellGaps cell_gaps(const GridView& g, double qx, double qy, double qz) {
+  const double q[3] = {qx, qy, qz};
+  CellGaps r;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    r.c[a] = cell_coord(q[a], g.origin[a], g.inv_cell, g.dims[a]);
+    const double face = g.origin[a] + double(r.c[a]) * g.cell;
+    const double slack = 1e-9 * g.cell + 1e-14 * (fabs(q[a]) + fabs(g.origin[a]) + double(g.dims[a]) * g.cell);
+    r.lo[a] = fmax(0.0, (q[a] - face) - slack);
+    r.hi[a] = fmax(0.0, ((face + g.cell) - q[a]) - slack);
+  }
+  return r;
+}
+
+// Run j (0..8: row cy + j % 3 - 1, slab cz + j / 3 - 1) of the query's neighbourhood without the cells out of reach.
+__device__ __forceinline__ void culled_run(const GridView& g, const CellGaps& cg, int j, double r2, int& s, int& len) {
+  s = 0;
+  len = 0;
+  const int dy = j % 3 - 1, dz = j / 3 - 1;
+  const int yy = cg.c[1] + dy, zz = cg.c[2] + dz;
+  const double gy = dy < 0 ? cg.lo[1] : (dy > 0 ? cg.hi[1] : 0.0);
+  const double gz = dz < 0 ? cg.lo[2] : (dz > 0 ? cg.hi[2] : 0.0);
+  const double reach = r2 * (1.0 + 1e-9);
+  const double yz2 = gy * gy + gz * gz;
+  if (yz2 > reach) return;
+  int x0 = cg.c[0] - 1, x1 = cg.c[0] + 1;
+  if (yz2 + cg.lo[0] * cg.lo[0] > reach) x0 = cg.c[0];
+  if (yz2 + cg.hi[0] * cg.hi[0] > reach) x1 = cg.c[0];
+  x0 = max(x0, 0);
+  x1 = min(x1, g.dims[0] - 1);
+  if (yy >= 0 && yy < g.dims[1] && zz >= 0 && zz < g.dims[2] && x0 <= x1) {
+    const int64_t base = (int64_t(zz) * g.dims[1] + yy) * g.dims[0];
+    s = __ldg(g.cell_start + base + x0);
+    len = __ldg(g.cell_start + base + x1 + 1) - s;
+  }
+}
+
+// The runs of a query that looks for neighbours within sqrt(r2) (r2 must not exceed the square of the cell edge).
+__device__ __forceinline__ Runs build_runs(const GridView& g, double qx, double qy, double qz, int lane, double r2) {
+  const CellGaps cg = cell_gaps(g, qx, qy, qz);
+  int s = 0, len = 0;
+  if (lane < 9) culled_run(g, cg, lane, r2, s, len);
+  return runs_from_lanes(s, len, lane);
 }
 
 // Position in the cell-sorted array of virtual candidate v (0 <= v < pref[9]).

@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(256)
   sw = warp_sum(sw);
 #pragma unroll
   for (int k = 0; k < 6; ++k) m[k] = warp_sum(m[k]);
-  if (lane < 6) {
+  if (lane < 7) {  // raw sums, the sum of the weights at [6]: lrf_eigen_kernel divides
     double v = m[0];
 #pragma unroll
     for (int k = 1; k < 6; ++k) v = lane == k ? m[k] : v;
-    lrf[9 * q + lane] = end > begin ? v / sw : 0.0;
+    lrf[9 * q + lane] = lane == 6 ? sw : v;
   }
 }
 
@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(128)
   if (q >= nq) return;
   if (counts ? counts[q] == 0 : offsets[q + 1] == offsets[q]) return;  // empty: the votes step writes the identity
   double m[6];
+  const double sw = lrf[9 * q + 6];  // weighted covariance = sums / sum of the weights (shot.py:31-34)
 #pragma unroll
-  for (int k = 0; k < 6; ++k) m[k] = lrf[9 * q + k];
+  for (int k = 0; k < 6; ++k) m[k] = lrf[9 * q + k] / sw;
   double eval[3], evec[3][3];
   eigh3(m, eval, evec);
   lrf[9 * q + 0] = evec[2][0]; lrf[9 * q + 1] = evec[2][1]; lrf[9 * q + 2] = evec[2][2];  // x: largest eigenvalue
@@ -118,38 +119,54 @@ __global__ void __launch_bounds__(256)
 // [cand_offsets[q], cand_offsets[q+1]) sized by its candidate count (a cell_start lookup, no distance test), the
 // one scan writes the hits there, counts them and accumulates the frame's weighted moments while the points are
 // in registers. The votes then run inside the descriptor kernel.
+// One THREAD per query works out the query's cell, the gaps to its faces and its nine culled runs — the part of the
+// search every lane of a warp would otherwise repeat (a third of search_moments_kernel's instructions in its first
+// form) — and leaves them as a table of five int4: start[0..8], pref[1..9] (running totals), two unused words.
 __global__ void __launch_bounds__(256)
-    candidate_count_kernel(GridView g, const double* __restrict__ queries, int64_t nq, int64_t* __restrict__ cand) {
+    candidate_count_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double r2,
+                           int64_t* __restrict__ cand, int4* __restrict__ runs_table) {
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (q >= nq) return;
-  const int cx = cell_coord(queries[3 * q], g.origin[0], g.inv_cell, g.dims[0]);
-  const int cy = cell_coord(queries[3 * q + 1], g.origin[1], g.inv_cell, g.dims[1]);
-  const int cz = cell_coord(queries[3 * q + 2], g.origin[2], g.inv_cell, g.dims[2]);
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+  const CellGaps cg = cell_gaps(g, queries[3 * q], queries[3 * q + 1], queries[3 * q + 2]);
+  int start[9], pref[9];
   int total = 0;
-  if (x0 <= x1) {
-    for (int dz = -1; dz <= 1; ++dz)
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = cy + dy, zz = cz + dz;
-        if (yy < 0 || yy >= g.dims[1] || zz < 0 || zz >= g.dims[2]) continue;
-        const int64_t base = (int64_t(zz) * g.dims[1] + yy) * g.dims[0];
-        total += __ldg(g.cell_start + base + x1 + 1) - __ldg(g.cell_start + base + x0);
-      }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    int len;
+    culled_run(g, cg, j, r2, start[j], len);
+    total += len;
+    pref[j] = total;
   }
   cand[q] = total;
+  int4* t = runs_table + 5 * q;
+  t[0] = make_int4(start[0], start[1], start[2], start[3]);
+  t[1] = make_int4(start[4], start[5], start[6], start[7]);
+  t[2] = make_int4(start[8], pref[0], pref[1], pref[2]);
+  t[3] = make_int4(pref[3], pref[4], pref[5], pref[6]);
+  t[4] = make_int4(pref[7], pref[8], 0, 0);
 }
 
 __global__ void __launch_bounds__(256)
     search_moments_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double radius, double r2,
-                          const int64_t* __restrict__ cand_offsets, float4* __restrict__ nbr,
-                          int32_t* __restrict__ counts, double* __restrict__ lrf,
+                          const int64_t* __restrict__ cand_offsets, const int4* __restrict__ runs_table,
+                          float4* __restrict__ nbr, int32_t* __restrict__ counts, double* __restrict__ lrf,
                           unsigned long long* __restrict__ pair_counter, const int32_t* __restrict__ status) {
   if (status != nullptr && *status != 0) return;  // a speculative call whose assumption failed: nothing is written
   const int lane = threadIdx.x & 31;
   const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (q >= nq) return;
   const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
-  const Runs runs = build_runs(g, qx, qy, qz, lane);
+  Runs runs;  // (candidate_count_kernel's table: five broadcast loads, cells out of reach already dropped)
+  {
+    const int4* t = runs_table + 5 * q;
+    const int4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4);
+    runs.start[0] = t0.x; runs.start[1] = t0.y; runs.start[2] = t0.z; runs.start[3] = t0.w;
+    runs.start[4] = t1.x; runs.start[5] = t1.y; runs.start[6] = t1.z; runs.start[7] = t1.w;
+    runs.start[8] = t2.x;
+    runs.pref[0] = 0; runs.pref[1] = t2.y; runs.pref[2] = t2.z; runs.pref[3] = t2.w;
+    runs.pref[4] = t3.x; runs.pref[5] = t3.y; runs.pref[6] = t3.z; runs.pref[7] = t3.w;
+    runs.pref[8] = t4.x; runs.pref[9] = t4.y;
+  }
   const int total = runs.pref[9];
   int64_t out = cand_offsets[q];
   int count = 0;
@@ -179,7 +196,12 @@ __global__ void __launch_bounds__(256)
       zero = !(d2 > 0.0);
       off[0] = float(-cx); off[1] = float(-cy); off[2] = float(-cz);
       if (hit) {
-        const double w = radius - sqrt(d2);
+        // (distance 0 — the query itself — would send the whole warp through sqrt's slow path once per query: the
+        // argument is replaced for that lane, behind a barrier the compiler cannot fold the select through)
+        double arg = zero ? 1.0 : d2;
+        asm volatile("" : "+d"(arg));
+        const double root = sqrt(arg);
+        const double w = radius - (zero ? 0.0 : root);
         sw += w;
         m[0] += w * cx * cx; m[1] += w * cx * cy; m[2] += w * cx * cz;
         m[3] += w * cy * cy; m[4] += w * cy * cz; m[5] += w * cz * cz;
@@ -195,14 +217,25 @@ __global__ void __launch_bounds__(256)
     out += __popc(mask);
     count += __popc(mask);
   }
-  sw = warp_sum(sw);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) m[k] = warp_sum(m[k]);
-  if (lane < 6) {
-    double v = m[0];
-#pragma unroll
-    for (int k = 1; k < 6; ++k) v = lane == k ? m[k] : v;
-    lrf[9 * q + lane] = count > 0 ? v / sw : 0.0;
+  // transposing butterfly over (sw, m0..m5, 0): after the exchange at distance 16 a lane carries four of the eight sums,
+  // then two, then one (9 double-word exchanges instead of 35); the lanes whose bits 4..2 spell k end with value k
+  {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    double a0 = h16 ? m[3] : sw, a1 = h16 ? m[4] : m[0], a2 = h16 ? m[5] : m[1], a3 = h16 ? 0.0 : m[2];
+    a0 += __shfl_xor_sync(kFull, h16 ? sw : m[3], 16);
+    a1 += __shfl_xor_sync(kFull, h16 ? m[0] : m[4], 16);
+    a2 += __shfl_xor_sync(kFull, h16 ? m[1] : m[5], 16);
+    a3 += __shfl_xor_sync(kFull, h16 ? m[2] : 0.0, 16);
+    double b0 = h8 ? a2 : a0, b1 = h8 ? a3 : a1;
+    b0 += __shfl_xor_sync(kFull, h8 ? a0 : a2, 8);
+    b1 += __shfl_xor_sync(kFull, h8 ? a1 : a3, 8);
+    double c0 = h4 ? b1 : b0;
+    c0 += __shfl_xor_sync(kFull, h4 ? b0 : b1, 4);
+    c0 += __shfl_xor_sync(kFull, c0, 2);
+    c0 += __shfl_xor_sync(kFull, c0, 1);
+    const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // 0: sw, 1..6: m0..m5
+    // raw sums: m0..m5 at [0..5], the sum of the weights at [6] (lrf_eigen_kernel divides)
+    if ((lane & 3) == 0 && k <= 6) lrf[9 * q + (k == 0 ? 6 : k - 1)] = c0;
   }
   if (lane == 0) {
     counts[q] = count;
@@ -956,7 +989,7 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
 static int shot_reserve_queries(sf_grid* g, int64_t nq) {
   if (nq <= g->shot_q_capacity) return SF_OK;
   cudaFree(g->shot_cand); cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
-  cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_scan_temp);
+  cudaFree(g->shot_runs); cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_scan_temp);
   g->shot_q_capacity = 0;
   const int64_t cap = nq + nq / 8 + 64;
   size_t scan_bytes = 0;
@@ -964,6 +997,7 @@ static int shot_reserve_queries(sf_grid* g, int64_t nq) {
   SF_CUDA(cudaMalloc(&g->shot_cand, size_t(cap + 1) * 8));
   SF_CUDA(cudaMalloc(&g->shot_cand_offsets, size_t(cap + 1) * 8));
   SF_CUDA(cudaMalloc(&g->shot_counts, size_t(cap) * 4));
+  SF_CUDA(cudaMalloc(&g->shot_runs, size_t(cap) * 5 * sizeof(int4)));
   SF_CUDA(cudaMalloc(&g->shot_lrf, size_t(cap) * 9 * 8));
   SF_CUDA(cudaMalloc(&g->shot_frame32, size_t(cap) * kFrame32Stride * 4));
   SF_CUDA(cudaMalloc(&g->shot_worklist, size_t(cap + 1) * 4));
@@ -1009,7 +1043,8 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   const GridView view = g->view();
   SF_CUDA(cudaMemsetAsync(cand + nq, 0, 8, stream));
   SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
-  candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(view, queries, nq, cand);
+  candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(view, queries, nq, radius * radius, cand,
+                                                                         g->shot_runs);
   size_t scan_bytes = g->shot_scan_bytes;
   SF_CUDA(cub::DeviceScan::ExclusiveSum(g->shot_scan_temp, scan_bytes, cand, cand_offsets, int(nq + 1), stream));
   // The padded list holds one 16-byte entry per CANDIDATE; its size is read back (the one synchronisation of the
@@ -1031,8 +1066,8 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   float4* nbr = g->shot_nbr;  // padded list of 16-byte entries: float32 offset, position | zero-distance flag << 31
   const unsigned warp_blocks = unsigned((nq * 32 + 255) / 256);
   profile_mark(0, stream);
-  search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets, nbr,
-                                                        counts, lrf, pair_counter, status);
+  search_moments_kernel<<<warp_blocks, 256, 0, stream>>>(view, queries, nq, radius, radius * radius, cand_offsets,
+                                                        g->shot_runs, nbr, counts, lrf, pair_counter, status);
   profile_mark(1, stream);
   lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf, frame32, status);
   profile_mark(2, stream);
