@@ -286,9 +286,9 @@ static void free_all(sf_grid* g) {
   cudaFree(g->vals_in); cudaFree(g->bbox); cudaFree(g->cub_temp);
   cudaFree(g->status_dev);
   if (g->status_host) cudaFreeHost(g->status_host);
-  cudaFree(g->shot_cand); cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
+  cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
   cudaFree(g->shot_runs);
-  cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_pairs); cudaFree(g->shot_scan_temp);
+  cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_pairs);
   cudaFree(g->shot_nbr);
 }
 

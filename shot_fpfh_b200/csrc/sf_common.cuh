@@ -105,7 +105,6 @@ struct sf_grid {
   int32_t* status_host = nullptr;  // page-locked mirror, valid after the stream is synchronised
   // scratch of sf_shot_single_scale, kept between calls
   int64_t shot_q_capacity = 0;
-  int64_t* shot_cand = nullptr;
   int64_t* shot_cand_offsets = nullptr;
   int32_t* shot_counts = nullptr;
   int4* shot_runs = nullptr;         // 5 x int4 per query: start[9], pref[1..9] of its culled runs (candidate_count_kernel)
@@ -113,8 +112,6 @@ struct sf_grid {
   float* shot_frame32 = nullptr;
   int32_t* shot_worklist = nullptr;
   unsigned long long* shot_pairs = nullptr;
-  void* shot_scan_temp = nullptr;
-  size_t shot_scan_bytes = 0;
   float4* shot_nbr = nullptr;
   int64_t shot_nbr_capacity = 0;     // entries
   double shot_entries_per_query = 0; // from the last call that read the total back

@@ -122,28 +122,58 @@ __global__ void __launch_bounds__(256)
 // One THREAD per query works out the query's cell, the gaps to its faces and its nine culled runs — the part of the
 // search every lane of a warp would otherwise repeat (a third of search_moments_kernel's instructions in its first
 // form) — and leaves them as a table of five int4: start[0..8], pref[1..9] (running totals), two unused words.
+// The query's slots in the padded list are handed out here as well: a block adds up its queries' candidate counts and
+// takes its share of the list with ONE atomicAdd on a cursor (round 2; a device-wide prefix sum did this before: two
+// more kernels and their launch gaps, 25 us of a 0.57 ms step). Where a query's slots lie is internal — the order of
+// the neighbours inside them is what results depend on — so the arrival order of the blocks does not matter.
+// status (speculative calls): raised to 2 when the list, sized from a previous call, cannot hold the candidates.
 __global__ void __launch_bounds__(256)
     candidate_count_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double r2,
-                           int64_t* __restrict__ cand, int4* __restrict__ runs_table) {
+                           int64_t* __restrict__ cand_offsets, int4* __restrict__ runs_table,
+                           unsigned long long* __restrict__ cursor, int64_t capacity, int32_t* __restrict__ status) {
+  __shared__ int warp_total[8];
+  __shared__ unsigned long long block_base;
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (q >= nq) return;
-  const CellGaps cg = cell_gaps(g, queries[3 * q], queries[3 * q + 1], queries[3 * q + 2]);
-  int start[9], pref[9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int total = 0;
+  if (q < nq) {
+    const CellGaps cg = cell_gaps(g, queries[3 * q], queries[3 * q + 1], queries[3 * q + 2]);
+    int start[9], pref[9];
 #pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    int len;
-    culled_run(g, cg, j, r2, start[j], len);
-    total += len;
-    pref[j] = total;
+    for (int j = 0; j < 9; ++j) {
+      int len;
+      culled_run(g, cg, j, r2, start[j], len);
+      total += len;
+      pref[j] = total;
+    }
+    int4* t = runs_table + 5 * q;
+    t[0] = make_int4(start[0], start[1], start[2], start[3]);
+    t[1] = make_int4(start[4], start[5], start[6], start[7]);
+    t[2] = make_int4(start[8], pref[0], pref[1], pref[2]);
+    t[3] = make_int4(pref[3], pref[4], pref[5], pref[6]);
+    t[4] = make_int4(pref[7], pref[8], 0, 0);
   }
-  cand[q] = total;
-  int4* t = runs_table + 5 * q;
-  t[0] = make_int4(start[0], start[1], start[2], start[3]);
-  t[1] = make_int4(start[4], start[5], start[6], start[7]);
-  t[2] = make_int4(start[8], pref[0], pref[1], pref[2]);
-  t[3] = make_int4(pref[3], pref[4], pref[5], pref[6]);
-  t[4] = make_int4(pref[7], pref[8], 0, 0);
+  int incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_total[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int t = warp_total[w];
+      warp_total[w] = run;
+      run += t;
+    }
+    block_base = atomicAdd(cursor, static_cast<unsigned long long>(run));
+    if (status != nullptr && int64_t(block_base) + run > capacity) *status = 2;
+  }
+  __syncthreads();
+  if (q < nq) cand_offsets[q] = int64_t(block_base) + warp_total[warp] + (incl - total);
 }
 
 __global__ void __launch_bounds__(256)
@@ -988,22 +1018,17 @@ extern "C" int sf_shot_descriptor(sf_grid* g, const double* queries, int64_t nq,
 // allocations per call).
 static int shot_reserve_queries(sf_grid* g, int64_t nq) {
   if (nq <= g->shot_q_capacity) return SF_OK;
-  cudaFree(g->shot_cand); cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
-  cudaFree(g->shot_runs); cudaFree(g->shot_frame32); cudaFree(g->shot_worklist); cudaFree(g->shot_scan_temp);
+  cudaFree(g->shot_cand_offsets); cudaFree(g->shot_counts); cudaFree(g->shot_lrf);
+  cudaFree(g->shot_runs); cudaFree(g->shot_frame32); cudaFree(g->shot_worklist);
   g->shot_q_capacity = 0;
   const int64_t cap = nq + nq / 8 + 64;
-  size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, g->shot_cand, g->shot_cand_offsets, int(cap + 1));
-  SF_CUDA(cudaMalloc(&g->shot_cand, size_t(cap + 1) * 8));
   SF_CUDA(cudaMalloc(&g->shot_cand_offsets, size_t(cap + 1) * 8));
   SF_CUDA(cudaMalloc(&g->shot_counts, size_t(cap) * 4));
   SF_CUDA(cudaMalloc(&g->shot_runs, size_t(cap) * 5 * sizeof(int4)));
   SF_CUDA(cudaMalloc(&g->shot_lrf, size_t(cap) * 9 * 8));
   SF_CUDA(cudaMalloc(&g->shot_frame32, size_t(cap) * kFrame32Stride * 4));
   SF_CUDA(cudaMalloc(&g->shot_worklist, size_t(cap + 1) * 4));
-  SF_CUDA(cudaMalloc(&g->shot_scan_temp, scan_bytes + 16));
-  if (g->shot_pairs == nullptr) SF_CUDA(cudaMalloc(&g->shot_pairs, 8));
-  g->shot_scan_bytes = scan_bytes + 16;
+  if (g->shot_pairs == nullptr) SF_CUDA(cudaMalloc(&g->shot_pairs, 16));
   g->shot_q_capacity = cap;
   return SF_OK;
 }
@@ -1017,11 +1042,6 @@ static int shot_reserve_entries(sf_grid* g, int64_t entries) {
   return SF_OK;
 }
 
-// status = 2 when the candidate total exceeds what the list can hold (speculative calls only).
-__global__ void list_capacity_kernel(const int64_t* cand_offsets, int64_t nq, int64_t capacity, int32_t* status) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && cand_offsets[nq] > capacity) *status = 2;
-}
-
 extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t nq, double radius, int32_t min_nb,
                                     int32_t normalize, void* out, int32_t out_is_f64, double* lrf_out,
                                     int64_t* pairs_host, void* stream_) {
@@ -1033,20 +1053,14 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   SF_REQUIRE(radius > 0.0 && radius * 1.0005 <= g->cell, SF_ERR_ARG,
              "sf_shot_single_scale: radius %g exceeds the cell edge %g the grid was built for", radius, g->cell);
   if (int rc = shot_reserve_queries(g, nq)) return rc;
-  int64_t* cand = g->shot_cand;
   int64_t* cand_offsets = g->shot_cand_offsets;
   int32_t* counts = g->shot_counts;
   float* frame32 = g->shot_frame32;
   double* lrf = lrf_out != nullptr ? lrf_out : g->shot_lrf;
-  unsigned long long* pair_counter = g->shot_pairs;
+  unsigned long long* pair_counter = g->shot_pairs;  // [0] neighbour pairs found, [1] cursor of the padded list
   int32_t* worklist = g->shot_worklist;  // [0] = number of queries handed to the exact kernel, then their indices
   const GridView view = g->view();
-  SF_CUDA(cudaMemsetAsync(cand + nq, 0, 8, stream));
-  SF_CUDA(cudaMemsetAsync(pair_counter, 0, 8, stream));
-  candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(view, queries, nq, radius * radius, cand,
-                                                                         g->shot_runs);
-  size_t scan_bytes = g->shot_scan_bytes;
-  SF_CUDA(cub::DeviceScan::ExclusiveSum(g->shot_scan_temp, scan_bytes, cand, cand_offsets, int(nq + 1), stream));
+  SF_CUDA(cudaMemsetAsync(pair_counter, 0, 16, stream));
   // The padded list holds one 16-byte entry per CANDIDATE; its size is read back (the one synchronisation of the
   // call) unless the handle is in speculative mode and a previous call left an estimate: then the list is sized
   // from that estimate, the device checks it (status 2) and every kernel below returns at once when it does not fit.
@@ -1054,11 +1068,14 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   const int32_t* status = nullptr;
   if (assume_size) {
     if (int rc = shot_reserve_entries(g, int64_t(g->shot_entries_per_query * 1.25 * double(nq)) + 4096)) return rc;
-    list_capacity_kernel<<<1, 32, 0, stream>>>(cand_offsets, nq, g->shot_nbr_capacity, g->status_dev);
     status = g->status_dev;
-  } else {
+  }
+  candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(
+      view, queries, nq, radius * radius, cand_offsets, g->shot_runs, pair_counter + 1,
+      assume_size ? g->shot_nbr_capacity : INT64_MAX, assume_size ? g->status_dev : nullptr);
+  if (!assume_size) {
     int64_t total = 0;
-    SF_CUDA(cudaMemcpyAsync(&total, cand_offsets + nq, 8, cudaMemcpyDeviceToHost, stream));
+    SF_CUDA(cudaMemcpyAsync(&total, pair_counter + 1, 8, cudaMemcpyDeviceToHost, stream));
     SF_CUDA(cudaStreamSynchronize(stream));
     if (int rc = shot_reserve_entries(g, total + total / 16 + 4096)) return rc;
     g->shot_entries_per_query = double(total) / double(nq);
