@@ -50,26 +50,65 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void __launch_bounds__(128)
+// The solver's branches are data-dependent (QL or QR iteration, two to four sweeps, the 2x2 ending): with one query
+// per thread in query order only 12 of a warp's 32 threads were active per instruction. The problems of a block are
+// therefore regrouped between the two halves of the decomposition: every thread reduces ITS query to tridiagonal form,
+// the block sorts the 128 tridiagonal problems by the direction dsteqr is about to take (through shared memory), and
+// every thread finishes the problem it picked up and writes the axes of that problem's query.
+constexpr int kEigenThreads = 128;
+
+__global__ void __launch_bounds__(kEigenThreads)
     lrf_eigen_kernel(int64_t nq, const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
                      double* __restrict__ lrf, float* __restrict__ frame32, const int32_t* __restrict__ status = nullptr) {
+  __shared__ double rec[8][kEigenThreads];  // d[3], e[2], tau, v2, scale of the problem in each slot
+  __shared__ int32_t owner[kEigenThreads];  // its query (offset inside the block), -1 = empty slot
+  __shared__ int32_t warp_count[2][kEigenThreads / 32];
   if (status != nullptr && *status != 0) return;
   // frame32 (optional, 12 floats per query, 9 used): float32 images of the raw x, y = z cross x, z for shot_fast_kernel
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (q >= nq) return;
-  if (counts ? counts[q] == 0 : offsets[q + 1] == offsets[q]) return;  // empty: the votes step writes the identity
-  double m[6];
-  const double sw = lrf[9 * q + 6];  // weighted covariance = sums / sum of the weights (shot.py:31-34)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // empty neighbourhoods take no part: the votes step writes the identity
+  const bool live = q < nq && !(counts ? counts[q] == 0 : offsets[q + 1] == offsets[q]);
+  Tridiagonal3 t;
+  bool up = false;
+  if (live) {
+    double m[6];
+    const double sw = lrf[9 * q + 6];  // weighted covariance = sums / sum of the weights (shot.py:31-34)
 #pragma unroll
-  for (int k = 0; k < 6; ++k) m[k] = lrf[9 * q + k] / sw;
+    for (int k = 0; k < 6; ++k) m[k] = lrf[9 * q + k] / sw;
+    eigh3_tridiagonal(m, t);
+    up = eigh3_bottom_up(t);
+  }
+  owner[threadIdx.x] = -1;
+  const unsigned down_mask = __ballot_sync(kFull, live && !up), up_mask = __ballot_sync(kFull, live && up);
+  if (lane == 0) {
+    warp_count[0][warp] = __popc(down_mask);
+    warp_count[1][warp] = __popc(up_mask);
+  }
+  __syncthreads();
+  if (live) {  // top-down problems fill the slots from the front, bottom-up ones from the back
+    int before = __popc((up ? up_mask : down_mask) & lanemask_lt());
+    for (int w = 0; w < warp; ++w) before += warp_count[up ? 1 : 0][w];
+    const int slot = up ? kEigenThreads - 1 - before : before;
+    rec[0][slot] = t.d[0]; rec[1][slot] = t.d[1]; rec[2][slot] = t.d[2]; rec[3][slot] = t.e[0]; rec[4][slot] = t.e[1];
+    rec[5][slot] = t.tau; rec[6][slot] = t.v2; rec[7][slot] = t.scale;
+    owner[slot] = threadIdx.x;
+  }
+  __syncthreads();
+  const int mine = owner[threadIdx.x];
+  if (mine < 0) return;
+  t.d[0] = rec[0][threadIdx.x]; t.d[1] = rec[1][threadIdx.x]; t.d[2] = rec[2][threadIdx.x];
+  t.e[0] = rec[3][threadIdx.x]; t.e[1] = rec[4][threadIdx.x];
+  t.tau = rec[5][threadIdx.x]; t.v2 = rec[6][threadIdx.x]; t.scale = rec[7][threadIdx.x];
+  const int64_t qo = blockIdx.x * int64_t(blockDim.x) + mine;
   double eval[3], evec[3][3];
-  eigh3(m, eval, evec);
-  lrf[9 * q + 0] = evec[2][0]; lrf[9 * q + 1] = evec[2][1]; lrf[9 * q + 2] = evec[2][2];  // x: largest eigenvalue
-  lrf[9 * q + 3] = evec[0][0]; lrf[9 * q + 4] = evec[0][1]; lrf[9 * q + 5] = evec[0][2];  // z: smallest eigenvalue
+  eigh3_finish(t, eval, evec);
+  lrf[9 * qo + 0] = evec[2][0]; lrf[9 * qo + 1] = evec[2][1]; lrf[9 * qo + 2] = evec[2][2];  // x: largest eigenvalue
+  lrf[9 * qo + 3] = evec[0][0]; lrf[9 * qo + 4] = evec[0][1]; lrf[9 * qo + 5] = evec[0][2];  // z: smallest eigenvalue
   if (frame32 != nullptr) {
     const double* x = evec[2];
     const double* z = evec[0];
-    float* f = frame32 + 12 * q;  // (kFrame32Stride: 48 bytes, one bulk copy)
+    float* f = frame32 + 12 * qo;  // (kFrame32Stride: 48 bytes, one bulk copy)
     f[0] = float(x[0]); f[1] = float(x[1]); f[2] = float(x[2]);
     f[3] = float(z[1] * x[2] - z[2] * x[1]); f[4] = float(z[2] * x[0] - z[0] * x[2]); f[5] = float(z[0] * x[1] - z[1] * x[0]);
     f[6] = float(z[0]); f[7] = float(z[1]); f[8] = float(z[2]);

@@ -23,6 +23,20 @@ void hm_eigh3(const double* m, double* eval, double* evec9) {
   }
 }
 
+// The statically-indexed dsteqr3 (what the kernels run) against the loop-for-loop transcription of LAPACK's dsteqr, on n
+// tridiagonal problems (d3, e2 per problem): the number of problems on which any of the 14 outputs differs in any BIT.
+long hm_dsteqr3_static_vs_generic(const double* d3, const double* e2, long n) {
+  long differ = 0;
+  for (long i = 0; i < n; ++i) {
+    double da[3] = {d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]}, ea[2] = {e2[2 * i], e2[2 * i + 1]}, za[3][3];
+    double db[3] = {da[0], da[1], da[2]}, eb[2] = {ea[0], ea[1]}, zb[3][3];
+    lapack3::dsteqr3(da, ea, za);
+    lapack3::dsteqr3_generic(db, eb, zb);
+    differ += memcmp(da, db, sizeof(da)) != 0 || memcmp(ea, eb, sizeof(ea)) != 0 || memcmp(za, zb, sizeof(za)) != 0;
+  }
+  return differ;
+}
+
 int hm_azimuth_octant(double x, double y) { return azimuth_octant(x, y); }
 
 // Mirrors shot_lrf_kernel: lrf9 row-major, columns [x y z].

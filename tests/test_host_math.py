@@ -73,6 +73,32 @@ def test_eigh3_matches_lapack(hm):
                 assert abs(abs(vec[c] @ v[:, c]) - 1.0) < 1e-10 / gap * 1e-4 + 1e-12
 
 
+def test_static_dsteqr_is_the_transcribed_dsteqr_bit_for_bit(hm):
+    """sf_eigh3.cuh: the kernels run dsteqr with every index resolved at compile time (blocks of 1, 2, 3; QL or QR);
+    the loop-for-loop transcription of LAPACK's routine is kept beside it as its specification."""
+    rng = np.random.default_rng(11)
+    n = 200_000
+    d = rng.normal(size=(n, 3)) * 10.0 ** rng.integers(-6, 3, size=(n, 1))
+    e = rng.normal(size=(n, 2)) * 10.0 ** rng.integers(-6, 3, size=(n, 1))
+    kind = rng.integers(0, 12, size=n)
+    d[kind == 0] = np.abs(d[kind == 0])                      # positive diagonals (covariances)
+    e[kind == 1, 0] = 0.0                                    # exact splits
+    e[kind == 2, 1] = 0.0
+    e[kind == 3] = 0.0
+    e[kind == 4, 0] *= 1e-17                                 # negligible off-diagonal entries (the eps tests)
+    e[kind == 5, 1] *= 1e-17
+    e[kind == 6] *= 1e-9                                     # nearly diagonal: deflation inside the iterations
+    d[kind == 7] = d[kind == 7][:, :1]                       # equal diagonal entries
+    d[kind == 8, 2] = d[kind == 8, 0]                        # |d3| == |d1|: the QL / QR choice at its boundary
+    d[kind == 9] = 0.0                                       # zero diagonal
+    d[kind == 10] *= 1e-150                                  # tiny values (safmin matters)
+    e[kind == 10] *= 1e-150
+    hm.hm_dsteqr3_static_vs_generic.restype = ctypes.c_long
+    hm.hm_dsteqr3_static_vs_generic.argtypes = [DP, DP, ctypes.c_long]
+    d, e = np.ascontiguousarray(d), np.ascontiguousarray(e)
+    assert hm.hm_dsteqr3_static_vs_generic(_p(d), _p(e), n) == 0
+
+
 def test_azimuth_octant_table(hm):
     g = np.load(os.path.join(ROOT, "tests", "golden", "edge_cases.npz"))
     got = [hm.hm_azimuth_octant(float(x), float(y)) for x, y in zip(g["azimuth_x"], g["azimuth_y"])]
