@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variants", default="82,73,102,63")
     ap.add_argument("--envs", default="", help="further variants, each a +-joined list of NAME=VALUE, separated by commas")
+    ap.add_argument("--no-profile", action="store_true", help="step times only: no CUDA events between the kernels")
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune_shot.json"))
@@ -48,7 +49,7 @@ def main():
             os.environ.pop(k, None)
         os.environ.update(env)
         out = torch.zeros((q, 352), dtype=torch.float32, device="cuda")
-        ops.profile_enable(True)
+        ops.profile_enable(not args.no_profile)
         stage_ms, step_ms, grid_ms = [], [], []
         pairs = deferred = None
         for it in range(3 + args.steps):
@@ -63,7 +64,7 @@ def main():
                 pairs, deferred = pr, ops.shot_last_deferred()
             torch.cuda.synchronize()
             if it >= 3:
-                stage_ms.append(ops.profile_read())
+                stage_ms.append(ops.profile_read() if not args.no_profile else (0.0, 0.0, 0.0))
                 step_ms.append(e0.elapsed_time(e2))
                 grid_ms.append(e0.elapsed_time(e1))
         ops.profile_enable(False)

@@ -107,6 +107,7 @@ struct sf_grid {
   int64_t shot_q_capacity = 0;
   int64_t* shot_cand_offsets = nullptr;
   int32_t* shot_counts = nullptr;
+  int shot_call_parity = 0;          // which of the two sets of shot_pairs counters the next call uses
   int4* shot_runs = nullptr;         // 5 x int4 per query: start[9], pref[1..9] of its culled runs (candidate_count_kernel)
   double* shot_lrf = nullptr;
   float* shot_frame32 = nullptr;

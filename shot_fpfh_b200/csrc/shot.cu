@@ -169,9 +169,17 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     candidate_count_kernel(GridView g, const double* __restrict__ queries, int64_t nq, double r2,
                            int64_t* __restrict__ cand_offsets, int4* __restrict__ runs_table,
-                           unsigned long long* __restrict__ cursor, int64_t capacity, int32_t* __restrict__ status) {
+                           unsigned long long* __restrict__ cursor, int64_t capacity, int32_t* __restrict__ status,
+                           unsigned long long* __restrict__ next_counters, int32_t* __restrict__ work_count) {
   __shared__ int warp_total[8];
   __shared__ unsigned long long block_base;
+  // first kernel of the call: the counters of the NEXT call (the other set) and this call's work list are reset here
+  // rather than by three memsets between the kernels
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    next_counters[0] = 0;
+    next_counters[1] = 0;
+    *work_count = 0;
+  }
   const int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int total = 0;
@@ -953,7 +961,8 @@ static bool env_flag(const char* name) {
 static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, double radius, const int64_t* offsets,
                              const int32_t* counts, const void* list, bool records, double* lrf, const float* frame32,
                              int write_frame, int min_nb, int normalize, void* out, int out_is_f64, int32_t* worklist,
-                             int32_t* work_count, const int32_t* status, cudaStream_t stream) {
+                             int32_t* work_count, const int32_t* status, cudaStream_t stream,
+                             bool work_count_is_reset = false) {
   const size_t smem = size_t(kShotWarpsPerBlock) * kShotSmemPerWarp;
   SF_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, SF_ERR_ARG, "SHOT output rows must be 16-byte aligned");
   SF_REQUIRE(nq < (int64_t(1) << 31), SF_ERR_ARG, "SHOT: %lld queries in one call", (long long)nq);
@@ -982,7 +991,7 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
     fp.write_frame = write_frame;
     fp.min_nb = min_nb;
     fp.normalize = normalize;
-    SF_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), stream));
+    if (!work_count_is_reset) SF_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), stream));
     // persistent: 148 SMs x resident blocks (7.6 KB of tables + staging per warp), capped by the work
     auto launch = [&](auto kernel, auto* typed_out, int warps, int per_sm) -> cudaError_t {
       const size_t fast_smem = size_t(warps) * kFastWordsPerWarp * 4;
@@ -1067,7 +1076,11 @@ static int shot_reserve_queries(sf_grid* g, int64_t nq) {
   SF_CUDA(cudaMalloc(&g->shot_lrf, size_t(cap) * 9 * 8));
   SF_CUDA(cudaMalloc(&g->shot_frame32, size_t(cap) * kFrame32Stride * 4));
   SF_CUDA(cudaMalloc(&g->shot_worklist, size_t(cap + 1) * 4));
-  if (g->shot_pairs == nullptr) SF_CUDA(cudaMalloc(&g->shot_pairs, 16));
+  if (g->shot_pairs == nullptr) {  // two sets of (pairs found, list cursor): a call resets the set of the next one
+    SF_CUDA(cudaMalloc(&g->shot_pairs, 32));
+    SF_CUDA(cudaMemset(g->shot_pairs, 0, 32));
+    g->shot_call_parity = 0;
+  }
   g->shot_q_capacity = cap;
   return SF_OK;
 }
@@ -1096,10 +1109,12 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   int32_t* counts = g->shot_counts;
   float* frame32 = g->shot_frame32;
   double* lrf = lrf_out != nullptr ? lrf_out : g->shot_lrf;
-  unsigned long long* pair_counter = g->shot_pairs;  // [0] neighbour pairs found, [1] cursor of the padded list
+  // [0] neighbour pairs found, [1] cursor of the padded list — of this call's set of counters
+  unsigned long long* pair_counter = g->shot_pairs + 2 * g->shot_call_parity;
+  unsigned long long* next_counters = g->shot_pairs + 2 * (g->shot_call_parity ^ 1);
+  g->shot_call_parity ^= 1;
   int32_t* worklist = g->shot_worklist;  // [0] = number of queries handed to the exact kernel, then their indices
   const GridView view = g->view();
-  SF_CUDA(cudaMemsetAsync(pair_counter, 0, 16, stream));
   // The padded list holds one 16-byte entry per CANDIDATE; its size is read back (the one synchronisation of the
   // call) unless the handle is in speculative mode and a previous call left an estimate: then the list is sized
   // from that estimate, the device checks it (status 2) and every kernel below returns at once when it does not fit.
@@ -1111,7 +1126,7 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   }
   candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(
       view, queries, nq, radius * radius, cand_offsets, g->shot_runs, pair_counter + 1,
-      assume_size ? g->shot_nbr_capacity : INT64_MAX, assume_size ? g->status_dev : nullptr);
+      assume_size ? g->shot_nbr_capacity : INT64_MAX, assume_size ? g->status_dev : nullptr, next_counters, worklist);
   if (!assume_size) {
     int64_t total = 0;
     SF_CUDA(cudaMemcpyAsync(&total, pair_counter + 1, 8, cudaMemcpyDeviceToHost, stream));
@@ -1128,7 +1143,7 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   lrf_eigen_kernel<<<unsigned((nq + 127) / 128), 128, 0, stream>>>(nq, cand_offsets, counts, lrf, frame32, status);
   profile_mark(2, stream);
   int rc = launch_descriptor(g, queries, nq, radius, cand_offsets, counts, nbr, true, lrf, frame32, lrf_out != nullptr, min_nb,
-                             normalize, out, out_is_f64, worklist + 1, worklist, status, stream);
+                             normalize, out, out_is_f64, worklist + 1, worklist, status, stream, true);
   profile_mark(3, stream);
   if (g->speculative && g->status_host != nullptr)  // the verdict of the device-side checks, for sf_grid_poll
     SF_CUDA(cudaMemcpyAsync(g->status_host, g->status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
