@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 8
+#define SF_ABI_VERSION 9
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -226,6 +226,12 @@ int sf_match_topk(const void* a_packed_dev, int64_t qa, const void* b_packed_dev
  * target set is sharded across GPUs). */
 int sf_topk_merge(const float* score_dev, const int32_t* idx_dev, int32_t parts, int64_t qa, int32_t k,
                   float* score_out_dev, int32_t* idx_out_dev, void* stream);
+/* Merge of the EXACT per-shard results of a target set sharded across GPUs (shot_fpfh_b200/distributed.py; replaces
+ * matching.py:164-169's argmin over the whole set): packed_dev (parts, q, 3) float64 = (d1, global index of the
+ * nearest target, d2) per shard in ascending order of target indices -> nearest (lowest index on ties), d1, and the
+ * second smallest distance over all shards. */
+int sf_nearest_merge(const double* packed_dev, int32_t parts, int64_t q, int64_t* nn_dev, double* d1_dev,
+                     double* d2_dev, void* stream);
 /* Certificate of the float16 shortlist (csrc/match.cu::certify_kernel): flags_dev[q] = 1 when the exact nearest
  * (want_second: second-nearest) distance of query q from sf_match_rerank is NOT provably below the distance to every
  * target outside its k-entry shortlist — bound from the k-th shortlist score, the float16 rounding of the operands and

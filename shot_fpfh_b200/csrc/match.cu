@@ -512,7 +512,44 @@ int launch_merge_partials(const float* score, const int32_t* idx, int parts, int
     default: return launch_merge<16>(score, idx, parts, qa, score_out, idx_out, stream);
   }
 }
+// ---- merge of the exact (nearest, d1, d2) triples of target shards (the step after the all-gather) ----------------
+// packed: (parts, q, 3) float64 = (d1, global index of the nearest, d2) per shard, shard p holding smaller target
+// indices than shard p + 1. nearest = smallest d1, first shard among equals (= lowest index, what argmin returns);
+// second = second smallest of the multiset of every shard's d1 and d2.
+__global__ void __launch_bounds__(256)
+    nearest_merge_kernel(const double* __restrict__ packed, int32_t parts, int64_t q, int64_t* __restrict__ nn,
+                         double* __restrict__ d1, double* __restrict__ d2) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= q) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double best = inf, second = inf, index = -1.0;
+  for (int p = 0; p < parts; ++p) {
+    const double* t = packed + (int64_t(p) * q + i) * 3;
+    const double a = t[0], b = t[2];
+    if (p == 0 || a < best) {  // strict: the first shard keeps a tie
+      second = fmin(second, best);
+      best = a;
+      index = t[1];
+    } else {
+      second = fmin(second, a);
+    }
+    second = fmin(second, b);
+  }
+  nn[i] = static_cast<int64_t>(index);
+  d1[i] = best;
+  d2[i] = second;
+}
 }  // namespace sf
+
+extern "C" int sf_nearest_merge(const double* packed, int32_t parts, int64_t q, int64_t* nn, double* d1, double* d2,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(packed && nn && d1 && d2 && parts >= 1 && q >= 0, SF_ERR_ARG, "sf_nearest_merge: bad arguments");
+  if (q == 0) return SF_OK;
+  nearest_merge_kernel<<<unsigned((q + 255) / 256), 256, 0, stream>>>(packed, parts, q, nn, d1, d2);
+  SF_CUDA(cudaGetLastError());
+  return SF_OK;
+}
 
 extern "C" int sf_topk_merge(const float* score, const int32_t* idx, int32_t parts, int64_t qa, int32_t k,
                              float* score_out, int32_t* idx_out, void* stream_) {

@@ -376,6 +376,16 @@ def topk_merge(score: torch.Tensor, idx: torch.Tensor):
     return so, io
 
 
+def nearest_merge(packed: torch.Tensor):
+    """(parts, q, 3) float64 (d1, global nearest index, d2) per target shard -> (nn int64, d1, d2) against the union."""
+    parts, q = int(packed.shape[0]), int(packed.shape[1])
+    nn = torch.empty(q, dtype=torch.int64, device=packed.device)
+    d1 = torch.empty(q, dtype=torch.float64, device=packed.device)
+    d2 = torch.empty(q, dtype=torch.float64, device=packed.device)
+    check(lib.sf_nearest_merge(ptr(packed.contiguous()), parts, q, ptr(nn), ptr(d1), ptr(d2), stream_ptr()))
+    return nn, d1, d2
+
+
 def match_certify(score, a_sqnorm, d1, d2, scale: float, b_norm_max: float, width: int, qb: int, want_second: bool):
     """uint8 (qa,) flags: 1 where the shortlist does not provably contain the nearest (second-nearest) neighbour."""
     qa, k = int(score.shape[0]), int(score.shape[1])

@@ -165,6 +165,27 @@ def test_topk_merge_equals_unsharded():
         assert torch.equal(i_m, i_all) and torch.equal(s_m, s_all)
 
 
+def test_nearest_merge_kernel_equals_the_rule_stated_in_torch():
+    """sf_nearest_merge (the step after the all-gather of a target set sharded over GPUs) against
+    distributed.merge_nearest: lowest shard on ties, second = second smallest of all shards' d1 and d2; empty shards."""
+    import torch
+    from shot_fpfh_b200 import distributed, ops
+
+    g = torch.Generator().manual_seed(3)
+    for parts in (1, 2, 3, 8):
+        q = 5000
+        d1 = torch.randint(0, 40, (parts, q), generator=g).double() / 8.0  # many exact ties
+        d2 = d1 + torch.randint(0, 3, (parts, q), generator=g).double() / 8.0
+        nn = torch.randint(0, 1000, (parts, q), generator=g) + 1000 * torch.arange(parts).unsqueeze(1)
+        if parts > 2:  # an empty shard
+            d1[1], d2[1], nn[1] = float("inf"), float("inf"), -1
+        d2[0, :50] = float("inf")  # a shard with a single target
+        packed = torch.stack([d1, nn.double(), d2], dim=2).cuda()
+        got = ops.nearest_merge(packed)
+        want = distributed.merge_nearest(d1, nn, d2)
+        assert torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1]) and torch.equal(got[2].cpu(), want[2])
+
+
 def test_multiscale_infinite_norm_branch():
     """(n_scales, n_points, width) descriptors: the 3-D branch of match_descriptors (matching.py:76-136)."""
     from test_oracle_golden import _multiscale_inputs
