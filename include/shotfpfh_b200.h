@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SF_ABI_VERSION 9
+#define SF_ABI_VERSION 10
 
 #define SF_OK 0
 #define SF_ERR_CUDA 1     /* a CUDA runtime call or kernel launch failed */
@@ -53,6 +53,17 @@ int sf_grid_destroy(sf_grid* grid);
 int sf_grid_build(sf_grid* grid, const double* xyz_dev, const double* normals_dev, int64_t n, double radius,
                   void* stream);
 int sf_grid_info(const sf_grid* grid, int64_t* n, int64_t* ncells, double* cell_edge, int32_t* dims3);
+/* The same build inside a bounding box the CALLER gives (lo3, hi3: host float64), without a bounding-box pass and
+ * without synchronising: the cells are exactly those of any other cloud built in that box with that radius — a cell
+ * with the same points in it yields the same candidate runs. For a rank of a spatially partitioned job (a slab of the
+ * cloud plus the cells around it, in the geometry of the whole cloud: shot_fpfh_b200/distributed.py; the reference has
+ * no counterpart, it builds one KDTree of everything, shot_parallelization.py:167). Every point is checked against the
+ * box on the device: sf_grid_poll reports 1 when one lay outside (the build is then memory-safe but wrong).
+ * sf_grid_geometry: the cell edge and table dimensions sf_grid_build / _in_box derive from a box and a radius. */
+int sf_grid_build_in_box(sf_grid* grid, const double* xyz_dev, const double* normals_dev, int64_t n, double radius,
+                         const double* lo3, const double* hi3, void* stream);
+int sf_grid_geometry(const double* lo3, const double* hi3, double radius, double* cell_edge, int32_t* dims3,
+                     int64_t* ncells);
 /* Calls without host synchronisation, for a caller that repeats the same work on one handle (a loop over time steps,
  * blocks of queries, a benchmark). `mode` bit 0: sf_grid_build on the same number of points and the same radius as the
  * handle's last synchronising build assumes that build's box (for rebuilding the SAME cloud); bit 1: sf_shot_single_scale

@@ -319,12 +319,11 @@ extern "C" int sf_grid_poll(sf_grid* g, int32_t* status) {
   return SF_OK;
 }
 
-extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normals, int64_t n, double radius,
-                             void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SF_REQUIRE(g != nullptr && xyz != nullptr, SF_ERR_ARG, "sf_grid_build: null grid or points");
-  SF_REQUIRE(n > 0 && n < (int64_t(1) << 31), SF_ERR_ARG, "sf_grid_build: n = %lld out of range", (long long)n);
-  SF_REQUIRE(radius > 0.0 && std::isfinite(radius), SF_ERR_ARG, "sf_grid_build: radius must be positive and finite");
+// Buffers of the handle for a cloud of n points.
+static int reserve_points(sf_grid* g, const double* xyz, const double* normals, int64_t n, double radius, const char* who) {
+  SF_REQUIRE(g != nullptr && xyz != nullptr, SF_ERR_ARG, "%s: null grid or points", who);
+  SF_REQUIRE(n > 0 && n < (int64_t(1) << 31), SF_ERR_ARG, "%s: n = %lld out of range", who, (long long)n);
+  SF_REQUIRE(radius > 0.0 && std::isfinite(radius), SF_ERR_ARG, "%s: radius must be positive and finite", who);
   if (n > g->capacity) {
     cudaFree(g->pts); cudaFree(g->nrm); cudaFree(g->xyzc); cudaFree(g->nrm32); cudaFree(g->perm); cudaFree(g->inv_perm);
     cudaFree(g->keys_in); cudaFree(g->keys_out); cudaFree(g->vals_in);
@@ -343,13 +342,73 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
   if (g->bbox == nullptr) SF_CUDA(cudaMalloc(&g->bbox, 6 * sizeof(double)));
   g->n = n;
   g->has_normals = normals != nullptr;
-
   if (g->status_dev == nullptr) {
     SF_CUDA(cudaMalloc(&g->status_dev, sizeof(int32_t)));
     SF_CUDA(cudaMemset(g->status_dev, 0, sizeof(int32_t)));
     SF_CUDA(cudaHostAlloc(&g->status_host, sizeof(int32_t), cudaHostAllocDefault));
     *g->status_host = 0;
   }
+  return SF_OK;
+}
+
+// Cell edge and table dimensions for a bounding box: the edge is slightly above the radius so that rounding in the
+// cell coordinate can never push a point within `radius` of a query two cells away; grown when the dense table would
+// exceed 2^25 cells.
+static int grid_geometry(const double lo[3], const double hi[3], double radius, double* cell_out, int dims[3],
+                         int64_t* ncells_out) {
+  for (int a = 0; a < 3; ++a)
+    SF_REQUIRE(std::isfinite(lo[a]) && std::isfinite(hi[a]) && hi[a] >= lo[a], SF_ERR_ARG,
+               "grid geometry: non-finite coordinates or an empty box");
+  double cell = radius * 1.001;
+  const double kMaxCells = double(1 << 25);
+  for (int iter = 0; iter < 64; ++iter) {
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) cells *= std::floor((hi[a] - lo[a]) * (1.0 / cell)) + 1.0;
+    if (cells <= kMaxCells) break;
+    cell *= std::cbrt(cells / kMaxCells) * 1.01;
+  }
+  int64_t ncells = 1;
+  for (int a = 0; a < 3; ++a) {
+    dims[a] = int(std::floor((hi[a] - lo[a]) * (1.0 / cell))) + 1;
+    ncells *= dims[a];
+  }
+  SF_REQUIRE(ncells <= (int64_t(1) << 26), SF_ERR_ARG, "grid geometry: %lld cells", (long long)ncells);
+  *cell_out = cell;
+  *ncells_out = ncells;
+  return SF_OK;
+}
+
+static int adopt_geometry(sf_grid* g, const double lo[3], const double hi[3], int64_t n, double radius) {
+  double cell;
+  int dims[3];
+  int64_t ncells;
+  if (int rc = grid_geometry(lo, hi, radius, &cell, dims, &ncells)) return rc;
+  g->cell = cell;
+  for (int a = 0; a < 3; ++a) {
+    g->origin[a] = lo[a];
+    g->dims[a] = dims[a];
+  }
+  g->ncells = ncells;
+  g->sized = true;
+  g->sized_n = n;
+  g->sized_radius = radius;
+  g->shot_entries_per_query = 0;  // another cloud: the neighbour list is sized afresh
+  return SF_OK;
+}
+
+extern "C" int sf_grid_geometry(const double* lo3, const double* hi3, double radius, double* cell, int32_t* dims3,
+                                int64_t* ncells) {
+  SF_REQUIRE(lo3 && hi3 && cell && dims3 && ncells && radius > 0.0, SF_ERR_ARG, "sf_grid_geometry: bad arguments");
+  int dims[3];
+  if (int rc = grid_geometry(lo3, hi3, radius, cell, dims, ncells)) return rc;
+  for (int a = 0; a < 3; ++a) dims3[a] = dims[a];
+  return SF_OK;
+}
+
+extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normals, int64_t n, double radius,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = reserve_points(g, xyz, normals, n, radius, "sf_grid_build")) return rc;
   // 1. bounding box (device) -> host, the only synchronisation of the build — skipped on a handle in speculative mode
   //    whose last synchronising build saw the same number of points and the same radius: the box of that build is
   //    assumed and checked on the device (sf_grid_poll tells)
@@ -368,30 +427,23 @@ extern "C" int sf_grid_build(sf_grid* g, const double* xyz, const double* normal
     hi[a] = from_ordered_bits(hbox[3 + a]);
     SF_REQUIRE(std::isfinite(lo[a]) && std::isfinite(hi[a]), SF_ERR_ARG, "sf_grid_build: non-finite coordinates");
   }
-  // 2. cell edge: slightly above the radius so that rounding in the cell coordinate can never push a point
-  //    within `radius` of a query two cells away; grown when the dense table would exceed 2^25 cells.
-  double cell = radius * 1.001;
-  const double kMaxCells = double(1 << 25);
-  for (int iter = 0; iter < 64; ++iter) {
-    double cells = 1.0;
-    for (int a = 0; a < 3; ++a) cells *= std::floor((hi[a] - lo[a]) * (1.0 / cell)) + 1.0;
-    if (cells <= kMaxCells) break;
-    cell *= std::cbrt(cells / kMaxCells) * 1.01;
-  }
-  g->cell = cell;
-  int64_t ncells = 1;
-  for (int a = 0; a < 3; ++a) {
-    g->origin[a] = lo[a];
-    g->dims[a] = int(std::floor((hi[a] - lo[a]) * (1.0 / cell))) + 1;
-    ncells *= g->dims[a];
-  }
-  SF_REQUIRE(ncells <= (int64_t(1) << 26), SF_ERR_ARG, "sf_grid_build: %lld cells", (long long)ncells);
-  g->ncells = ncells;
-  g->sized = true;
-  g->sized_n = n;
-  g->sized_radius = radius;
-  g->shot_entries_per_query = 0;  // another cloud: the neighbour list is sized afresh
+  // 2. cell edge and table dimensions
+  if (int rc = adopt_geometry(g, lo, hi, n, radius)) return rc;
   return build_cells(g, xyz, normals, n, false, stream);
+}
+
+// The same build inside a box the CALLER gives (no bounding-box pass, no synchronisation): the cells are those of any
+// other cloud built in that box with that radius. This is what a rank of a spatially partitioned job uses
+// (shot_fpfh_b200/distributed.py, "halo"): it sorts only the points of its slab and of the cells around it, in the
+// geometry of the whole cloud, and finds every neighbourhood exactly as the build of the whole cloud would lay it out.
+// Every point is checked against the box on the device (sf_grid_poll reports 1 when one lies outside).
+extern "C" int sf_grid_build_in_box(sf_grid* g, const double* xyz, const double* normals, int64_t n, double radius,
+                                    const double* lo3, const double* hi3, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SF_REQUIRE(lo3 != nullptr && hi3 != nullptr, SF_ERR_ARG, "sf_grid_build_in_box: null box");
+  if (int rc = reserve_points(g, xyz, normals, n, radius, "sf_grid_build_in_box")) return rc;
+  if (int rc = adopt_geometry(g, lo3, hi3, n, radius)) return rc;
+  return build_cells(g, xyz, normals, n, true, stream);
 }
 
 // Steps 3-5 of the build for the geometry held by the handle.

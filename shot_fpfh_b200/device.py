@@ -352,6 +352,18 @@ def device_rows_of(host_array) -> torch.Tensor | None:
     return rows
 
 
+def grid_geometry(lo, hi, radius: float) -> dict:
+    """Cell edge and table dimensions the grid derives from a bounding box and a radius (sf_grid_geometry)."""
+    import ctypes
+
+    cell, ncells = ctypes.c_double(), ctypes.c_int64()
+    dims = (ctypes.c_int32 * 3)()
+    lo_c = (ctypes.c_double * 3)(*[float(v) for v in lo])
+    hi_c = (ctypes.c_double * 3)(*[float(v) for v in hi])
+    check(lib.sf_grid_geometry(lo_c, hi_c, float(radius), ctypes.byref(cell), dims, ctypes.byref(ncells)))
+    return {"cell": cell.value, "dims": tuple(dims), "ncells": ncells.value}
+
+
 class Grid:
     """Owner of one `sf_grid` handle (uniform grid over a cloud, see csrc/grid.cu)."""
 
@@ -366,11 +378,20 @@ class Grid:
         self.has_normals = False
         self._keep = ()
 
-    def build(self, xyz: torch.Tensor, normals: torch.Tensor | None, radius: float) -> "Grid":
+    def build(self, xyz: torch.Tensor, normals: torch.Tensor | None, radius: float, box=None) -> "Grid":
+        """`box` = (lo, hi), three floats each: build in that bounding box instead of the cloud's own (the cells of a
+        cloud that CONTAINS these points, see sf_grid_build_in_box); `poll()` then tells whether a point lay outside."""
+        import ctypes
+
         assert xyz.dtype == torch.float64 and xyz.dim() == 2 and xyz.shape[1] == 3
         if normals is not None:
             assert normals.dtype == torch.float64 and normals.shape == xyz.shape
-        check(lib.sf_grid_build(self._h, ptr(xyz), ptr(normals), xyz.shape[0], float(radius), stream_ptr()))
+        if box is None:
+            check(lib.sf_grid_build(self._h, ptr(xyz), ptr(normals), xyz.shape[0], float(radius), stream_ptr()))
+        else:
+            lo = (ctypes.c_double * 3)(*[float(v) for v in box[0]])
+            hi = (ctypes.c_double * 3)(*[float(v) for v in box[1]])
+            check(lib.sf_grid_build_in_box(self._h, ptr(xyz), ptr(normals), xyz.shape[0], float(radius), lo, hi, stream_ptr()))
         self.n, self.radius, self.has_normals = int(xyz.shape[0]), float(radius), normals is not None
         return self
 

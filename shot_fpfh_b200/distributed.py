@@ -172,8 +172,15 @@ def sharded_nearest(
 # CUDA drivers (one process per GPU)
 # ---------------------------------------------------------------------------------------------------------------
 def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, min_neighborhood_size=100, gather=True,
-                      out_dtype=torch.float32, group=None) -> torch.Tensor:
-    """SHOT rows (device tensor) of the keypoint COORDINATES, queries sharded by block over the ranks."""
+                      out_dtype=torch.float32, group=None, partition: str = "blocks"):
+    """
+    SHOT rows (device tensor) of the keypoint COORDINATES over the ranks.
+    partition="blocks": queries by contiguous block, every rank grid-sorts the whole (replicated) cloud.
+    partition="slabs" : the halo scheme — see `shot_single_scale_slabs`.
+    """
+    if partition == "slabs":
+        return shot_single_scale_slabs(point_cloud, normals, keypoints, radius, normalize, min_neighborhood_size, gather,
+                                       out_dtype, group)
     from . import ops
     from .device import Grid, upload
 
@@ -185,6 +192,95 @@ def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, m
         return ops.shot_single_scale(grid, q, radius, min_neighborhood_size, normalize, out_dtype=out_dtype)[0]
 
     out = sharded_rows(int(kp.shape[0]), block, gather, group)
+    torch.cuda.synchronize()
+    grid.close()
+    return out
+
+
+# ---- halo partition ---------------------------------------------------------------------------------------------
+# A rank owns a SLAB of the cloud's bounding box along its longest axis — whole layers of grid cells, cut so that the
+# slabs hold about the same number of keypoints — and sorts only the points of its slab and of the layers of cells next
+# to it (the halo: a neighbour within the radius lies at most one cell away), in the cell geometry of the WHOLE cloud
+# (Grid.build(box=...)). Every one of the 27 cells around a keypoint of the slab then holds exactly the points it
+# holds in the grid of the whole cloud, in the same order, so each rank's rows are bit-identical to the unsharded ones.
+def cell_layer(x: torch.Tensor, origin: float, cell: float) -> torch.Tensor:
+    """Layer of grid cells a coordinate falls in: csrc/sf_common.cuh cell_coord without its clamp."""
+    return torch.floor((x - origin) * (1.0 / cell)).long()
+
+
+def slab_bounds(keypoint_layers: torch.Tensor, parts: int) -> list[int]:
+    """parts + 1 layer numbers: part r owns the layers [b[r], b[r + 1]); cut at the quantiles of the keypoints' layers
+    (a layer is never split, so a crowded layer makes its slab larger; slabs may be empty)."""
+    q = int(keypoint_layers.shape[0])
+    if q == 0:
+        return [0] * (parts + 1)
+    ordered = torch.sort(keypoint_layers).values
+    cuts = [int(ordered[min(q - 1, (q * r) // parts)].item()) for r in range(1, parts)]
+    bounds = [int(ordered[0].item())] + cuts + [int(ordered[-1].item()) + 1]
+    for r in range(1, parts + 1):
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return bounds
+
+
+def slab_members(keypoint_layers, point_layers, bounds, part: int):
+    """(indices of the part's keypoints, indices of the points it must sort: its slab plus two layers of halo — one is
+    needed, the second makes a one-off disagreement in a layer number harmless), both ascending."""
+    lo, hi = bounds[part], bounds[part + 1]
+    mine = torch.nonzero((keypoint_layers >= lo) & (keypoint_layers < hi)).squeeze(1)
+    halo = torch.nonzero((point_layers >= lo - 2) & (point_layers <= hi + 1)).squeeze(1)
+    return mine, halo
+
+
+def sharded_rows_by_slab(points, keypoints, radius: float, geometry: Callable, rows_of: Callable, width: int, gather=True,
+                         group=None, out_dtype=torch.float32):
+    """
+    `geometry(lo, hi, radius)` -> {"cell": edge}; `rows_of(point_idx, keypoint_idx, (lo, hi))` -> rows of those
+    keypoints from a grid over those points built in the box (lo, hi). Returns the (Q, width) rows on every rank
+    (each row is written by exactly one rank: a sum-reduction of otherwise zero rows moves them exactly), or
+    (keypoint indices, rows) of this rank when `gather` is false.
+    """
+    rank, size = world(group)
+    lo, hi = points.min(dim=0).values, points.max(dim=0).values  # (what sf_grid_build's bounding-box pass finds)
+    axis = int(torch.argmax(hi - lo).item())
+    box = (tuple(float(v) for v in lo.tolist()), tuple(float(v) for v in hi.tolist()))
+    cell = float(geometry(box[0], box[1], radius)["cell"])
+    k_layers = cell_layer(keypoints[:, axis], box[0][axis], cell)
+    p_layers = cell_layer(points[:, axis], box[0][axis], cell)
+    bounds = slab_bounds(k_layers, size)
+    mine, halo = slab_members(k_layers, p_layers, bounds, rank)
+    if int(mine.shape[0]) > 0 and int(halo.shape[0]) > 0:
+        local = rows_of(halo, mine, box)
+    else:  # no keypoint here, or keypoints with nothing around them: zero rows, as the whole-cloud run gives
+        local = torch.zeros((int(mine.shape[0]), width), dtype=out_dtype, device=points.device)
+    if not gather:
+        return mine, local
+    full = torch.zeros((int(keypoints.shape[0]), width), dtype=local.dtype, device=local.device)
+    full[mine] = local
+    if size > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full
+
+
+def shot_single_scale_slabs(point_cloud, normals, keypoints, radius, normalize=True, min_neighborhood_size=100,
+                            gather=True, out_dtype=torch.float32, group=None):
+    """The halo scheme on the GPUs: the raw cloud reaches every rank once (an N-th over PCIe each, the rest over
+    NVLink), each rank sorts its slab + halo only and computes the rows of its slab's keypoints."""
+    from . import ops
+    from .device import Grid, grid_geometry, upload
+
+    pts, nrm = upload_replicated(point_cloud, group=group), upload_replicated(normals, group=group)
+    kp = upload(keypoints)
+    grid = Grid()
+
+    def rows_of(point_idx, keypoint_idx, box):
+        grid.build(pts[point_idx].contiguous(), nrm[point_idx].contiguous(), radius, box=box)
+        rows = ops.shot_single_scale(grid, kp[keypoint_idx].contiguous(), radius, min_neighborhood_size, normalize,
+                                     out_dtype=out_dtype)[0]
+        torch.cuda.synchronize()
+        assert grid.poll() == 0, "a point of the slab lies outside the cloud's bounding box"
+        return rows
+
+    out = sharded_rows_by_slab(pts, kp, float(radius), grid_geometry, rows_of, 352, gather, group, out_dtype)
     torch.cuda.synchronize()
     grid.close()
     return out

@@ -175,11 +175,69 @@ def _check_matching(rank, size):
     del rng
 
 
+def _check_slabs(rank, size):
+    """Halo partition: every keypoint belongs to exactly one slab, and the points a rank sorts (slab + halo) contain
+    EVERY neighbour of its keypoints — checked with rows that are exact functions of the neighbour set (count, sum and
+    maximum of the neighbours' original indices, the SHOT oracle's rows on top), so a missing neighbour cannot hide."""
+    from sklearn.neighbors import KDTree
+
+    pts, normals, radius = _cloud()
+    pts = pts * np.array([1.0, 1.7, 0.6])  # the longest axis is not the first one
+    kp_idx = np.arange(0, pts.shape[0], 5)
+    kp = np.ascontiguousarray(pts[kp_idx])
+    kp[-3:] += 10.0 * radius  # keypoints away from the cloud: no neighbours, zero rows
+    tree = KDTree(pts)
+
+    def rows_from(points_idx, keypoints):
+        sub = pts[points_idx]
+        nbh = KDTree(sub).query_radius(keypoints, radius)
+        rows = np.zeros((keypoints.shape[0], 3 + 352))
+        for r, nb in enumerate(nbh):
+            orig = np.sort(points_idx[nb])
+            rows[r, :3] = (orig.shape[0], orig.sum(), orig.max() if orig.shape[0] else -1)
+        rows[:, 3:] = shot_oracle.shot_single_scale(sub, normals[points_idx], keypoints, radius, True, 5)
+        return rows
+
+    full = rows_from(np.arange(pts.shape[0]), kp)
+    assert len(tree.query_radius(kp[-1:], radius)[0]) == 0
+    seen = {}
+
+    def geometry(lo, hi, r):
+        return {"cell": r * 1.001}
+
+    def rows_of(point_idx, keypoint_idx, box):
+        seen["points"] = int(point_idx.shape[0])
+        return torch.from_numpy(rows_from(point_idx.numpy(), kp[keypoint_idx.numpy()]))
+
+    got = sfd.sharded_rows_by_slab(torch.from_numpy(pts), torch.from_numpy(kp), radius, geometry, rows_of, 355,
+                                   gather=True, out_dtype=torch.float64)
+    assert np.array_equal(got.numpy()[:, :3], full[:, :3])  # the same neighbour sets
+    assert np.allclose(got.numpy()[:, 3:], full[:, 3:], rtol=0, atol=1e-12)  # (KDTree order differs: summation order)
+    mine, local = sfd.sharded_rows_by_slab(torch.from_numpy(pts), torch.from_numpy(kp), radius, geometry, rows_of, 355,
+                                           gather=False, out_dtype=torch.float64)
+    counts = torch.zeros(kp.shape[0], dtype=torch.int64)
+    counts[mine] = 1
+    dist.all_reduce(counts)
+    assert bool((counts == 1).all())  # a partition of the keypoints
+    if size > 1 and "points" in seen:
+        assert seen["points"] < pts.shape[0]  # a rank does not sort the whole cloud
+
+
 @pytest.mark.parametrize("size", [2, 3])
 @pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_fpfh_by_position", "_check_upload_replicated",
-                                "_check_matching"])
+                                "_check_matching", "_check_slabs"])
 def test_sharded_equals_unsharded(fn, size):
     _spawn(fn, size)
+
+
+def test_slab_bounds_single_process():
+    layers = torch.tensor([5, 5, 5, 5, 2, 9, 9, 3, 3, 3, 7, 1])
+    for parts in (1, 2, 3, 5, 16):
+        b = sfd.slab_bounds(layers, parts)
+        assert len(b) == parts + 1 and b[0] == 1 and b[-1] == 10 and all(x <= y for x, y in zip(b[:-1], b[1:]))
+        owned = sum(int(((layers >= b[r]) & (layers < b[r + 1])).sum()) for r in range(parts))
+        assert owned == layers.shape[0]
+    assert sfd.slab_bounds(torch.empty(0, dtype=torch.long), 3) == [0, 0, 0, 0]
 
 
 def test_block_bounds_and_merge_single_process():

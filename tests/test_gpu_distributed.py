@@ -85,6 +85,57 @@ def test_virtual_ranks_shot_and_fpfh_bit_exact():
     grid.close()
 
 
+def test_virtual_ranks_halo_slabs_bit_exact():
+    """The halo partition (distributed.shot_single_scale_slabs) rank by rank on one device: a grid over a slab + halo
+    of the cloud, built in the WHOLE cloud's box (sf_grid_build_in_box), gives the rows of the slab's keypoints bit for
+    bit as the grid of the whole cloud does, and sorts a fraction of the points."""
+    from shot_fpfh_b200 import distributed as sfd
+    from shot_fpfh_b200 import ops
+    from shot_fpfh_b200.device import Grid, grid_geometry, upload
+
+    pts, normals, radius = _inputs()
+    p, nr = upload(pts), upload(normals)
+    kp = p[torch.randperm(p.shape[0], device=p.device)[:9000]].contiguous()
+    kp[-5:] += 7.0 * radius  # off the cloud: zero rows
+    whole = Grid().build(p, nr, radius)
+    want = ops.shot_single_scale(whole, kp, radius, 10, True, out_dtype=torch.float32)[0]
+    info = whole.info()
+    lo, hi = p.min(dim=0).values, p.max(dim=0).values
+    box = (tuple(lo.tolist()), tuple(hi.tolist()))
+    geo = grid_geometry(box[0], box[1], radius)
+    assert geo["cell"] == info["cell"] and tuple(geo["dims"]) == tuple(info["dims"])
+    axis = int(torch.argmax(hi - lo).item())
+    k_layers = sfd.cell_layer(kp[:, axis], box[0][axis], geo["cell"])
+    p_layers = sfd.cell_layer(p[:, axis], box[0][axis], geo["cell"])
+    for parts in (2, 5):
+        bounds = sfd.slab_bounds(k_layers, parts)
+        got = torch.zeros_like(want)
+        covered = torch.zeros(kp.shape[0], dtype=torch.int64, device=p.device)
+        sorted_points = 0
+        grid = Grid()
+        for r in range(parts):
+            mine, halo = sfd.slab_members(k_layers, p_layers, bounds, r)
+            covered[mine] += 1
+            if mine.shape[0] == 0 or halo.shape[0] == 0:
+                continue
+            sorted_points += int(halo.shape[0])
+            grid.build(p[halo].contiguous(), nr[halo].contiguous(), radius, box=box)
+            got[mine] = ops.shot_single_scale(grid, kp[mine].contiguous(), radius, 10, True, out_dtype=torch.float32)[0]
+            torch.cuda.synchronize()
+            assert grid.poll() == 0
+        assert bool((covered == 1).all())
+        assert torch.equal(got, want)
+        assert sorted_points < (1.0 + 0.35 * parts) * p.shape[0]  # slabs + halos, not `parts` whole clouds
+        grid.close()
+    # a point outside the given box is reported
+    g2 = Grid().build(p[:1000].contiguous(), nr[:1000].contiguous(), radius,
+                      box=((0.0, 0.0, 0.0), (0.01, 0.01, 0.01)))
+    torch.cuda.synchronize()
+    assert g2.poll() == 1
+    g2.close()
+    whole.close()
+
+
 def _free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -108,6 +159,8 @@ def _nccl_worker(rank, size, port, out_dir):
         with ShotMultiprocessor(min_neighborhood_size=10, verbose=False) as shot:
             want = shot.compute_descriptor_single_scale(pts, normals, pts[kp_idx], radius)
         assert np.array_equal(got.astype(np.float64), want)
+        got_h = sfd.shot_single_scale(pts, normals, pts[kp_idx], radius, True, 10, gather=True, partition="slabs")
+        assert np.array_equal(got_h.cpu().numpy().astype(np.float64), want)  # halo partition: the same rows
         got_f = sfd.fpfh(kp_idx, pts, normals, radius, 11, True, gather=True, out_dtype=torch.float64).cpu().numpy()
         want_f = compute_fpfh_descriptor(kp_idx, pts, normals, radius, 11, True, verbose=False)
         assert np.array_equal(got_f, want_f)
