@@ -6,6 +6,10 @@ this package (`dropin.install()`, one B200) and once as it is (CPU), per-stage w
 transform against the known one.
 
     python scripts/run_reference_pipeline.py --points 10000000                 # B200 leg
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/run_reference_pipeline.py --points 10000000                    # 8 B200s: rank 0 runs the reference's
+                                                                               # pipeline, ranks 1..7 lend their GPUs
+                                                                               # (shot_fpfh_b200.distributed.serve)
     python scripts/run_reference_pipeline.py --points 300000 --cpu             # the reference alone, decimated (8d)
 
 The pipeline object, its methods, their arguments and every line of pipeline.py are the reference's; only the callables
@@ -102,7 +106,28 @@ if __name__ == "__main__":
     ap.add_argument("--fpfh", action="store_true")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    result = run(a.points, on_gpu=not a.cpu, fpfh=a.fpfh)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not a.cpu:  # root + workers (the reference's script is a single process: it runs on rank 0)
+        import torch
+        import torch.distributed as dist
+
+        from shot_fpfh_b200 import distributed as sfd
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if dist.get_rank() != 0:
+            served = sfd.serve()
+            print(f"rank {dist.get_rank()}: served {served} requests", flush=True)
+            dist.destroy_process_group()
+            sys.exit(0)
+        sfd.start_root_service()
+        result = run(a.points, on_gpu=True, fpfh=a.fpfh)
+        result["leg"] = f"{world} x B200: rank 0 runs the reference's pipeline (dropin), the other ranks serve the matching"
+        sfd.stop_root_service()
+        dist.destroy_process_group()
+    else:
+        result = run(a.points, on_gpu=not a.cpu, fpfh=a.fpfh)
     if a.out:
         os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
         with open(a.out, "w") as f:

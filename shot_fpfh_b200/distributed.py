@@ -361,31 +361,17 @@ def fpfh(keypoints_indices, cloud_points, normals, radius, n_bins, decorrelated=
     return out
 
 
-def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None, timings: dict | None = None):
-    """
-    Exact nearest / second-nearest reference row of every non-empty scan row, the reference set sharded over the
-    ranks by contiguous blocks of rows: a rank uploads ITS block of the scan rows (one all-gather over NVLink gives
-    every rank all of them) and ITS block of reference rows, emits its exact (nearest, d1, d2) against that block,
-    and ONE all-gather + merge gives the result against the union
-    (lowest reference index on ties, as `cdist().argmin()`). The float16 shortlist uses the same scale on every rank
-    (a MAX all-reduce of one scalar). Returns host arrays (scan row ids, ref row ids of the nearest, d1, d2),
-    identical on every rank.
-    """
+def _nearest_of_device_rows(a, ref_block: Callable[[int, int], torch.Tensor], n_ref: int, k: int, group, mark):
+    """The sharded search once the scan rows `a` (float64, device) are on every rank; `ref_block(lo, hi)` -> this rank's
+    block of the reference rows on the device."""
     from . import ops
-    from .device import upload
     from .matching.matching import exact_nearest, largest, pack_scale
 
-    ref = ref_descriptors
-    t = timings if timings is not None else {}
-    mark = _marker(t)
-    mark("start")
-    a = upload_replicated(scan_descriptors, group=group)  # an N-th over PCIe per rank, the rest over NVLink
-    mark("scan_rows_on_every_rank")
     rows_a, a_top = ops.nonempty_rows(a, want_absmax=True)
     qa = int(rows_a.shape[0])
 
     def shard(lo, hi):
-        b = upload(ref[lo:hi])  # only this rank's block crosses PCIe
+        b = ref_block(lo, hi)
         rows_b, b_top = (ops.nonempty_rows(b, want_absmax=True) if hi > lo
                          else (torch.empty(0, dtype=torch.int64, device=a.device), 0.0))
         top = torch.tensor([largest(a_top, b_top)], dtype=torch.float64, device=a.device)
@@ -400,8 +386,103 @@ def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None,
         mark("shard_searched")
         return rows_b[nn.long()].long() + lo, d1, d2  # original reference row ids
 
-    nn, d1, d2 = sharded_nearest(int(ref.shape[0]), shard, group)
+    nn, d1, d2 = sharded_nearest(n_ref, shard, group)
     mark("gathered_and_merged")
+    return rows_a, nn, d1, d2
+
+
+def nearest_neighbors(scan_descriptors, ref_descriptors, k: int = 8, group=None, timings: dict | None = None):
+    """
+    Exact nearest / second-nearest reference row of every non-empty scan row, the reference set sharded over the
+    ranks by contiguous blocks of rows: a rank uploads ITS block of the scan rows (one all-gather over NVLink gives
+    every rank all of them) and ITS block of reference rows, emits its exact (nearest, d1, d2) against that block,
+    and ONE all-gather + merge gives the result against the union
+    (lowest reference index on ties, as `cdist().argmin()`). The float16 shortlist uses the same scale on every rank
+    (a MAX all-reduce of one scalar). Returns host arrays (scan row ids, ref row ids of the nearest, d1, d2),
+    identical on every rank.
+    """
+    from .device import upload
+
+    ref = ref_descriptors
+    t = timings if timings is not None else {}
+    mark = _marker(t)
+    mark("start")
+    a = upload_replicated(scan_descriptors, group=group)  # an N-th over PCIe per rank, the rest over NVLink
+    mark("scan_rows_on_every_rank")
+    rows_a, nn, d1, d2 = _nearest_of_device_rows(a, lambda lo, hi: upload(ref[lo:hi]), int(ref.shape[0]), k, group, mark)
     torch.cuda.synchronize()
     _elapsed(t)
     return rows_a.cpu().numpy(), nn.cpu().numpy(), d1.cpu().numpy(), d2.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Root + workers: ONE process runs the caller's code, the other ranks lend their GPUs
+# ---------------------------------------------------------------------------------------------------------------
+# The drivers above are SPMD: every rank holds the inputs on the host and calls the same function. A program that is not
+# written that way — the reference's `scripts/register_point_clouds.py` is a single process — runs on rank 0 only, and
+# the other ranks sit in `serve()`: rank 0 announces a request (a small pickled dict), sends the operands over NVLink
+# from ITS device (they are usually there already: the rows a descriptor call left behind), every rank works on its
+# share, and the merged result lands on rank 0. Matching is served this way (the one stage of a 10M-point registration
+# that is GPU-bound: two 1M x 1M x 352 searches); descriptors of one cloud are not worth sharding across processes for
+# this API — their time is the host-side construction of the float64 result, which only rank 0 wants.
+_SERVICE = {"group": None, "active": False}
+_HANDLERS: dict[str, Callable] = {}
+
+
+def root_service_active() -> bool:
+    return bool(_SERVICE["active"]) and world(_SERVICE["group"])[1] > 1
+
+
+def start_root_service(group=None) -> None:
+    """Rank 0: from now on the matchers of this package (and of a reference rebound by dropin) use every rank."""
+    assert world(group)[0] == 0, "the root service runs on rank 0"
+    _SERVICE.update(group=group, active=True)
+
+
+def stop_root_service() -> None:
+    """Rank 0: releases the workers from serve()."""
+    if root_service_active():
+        dist.broadcast_object_list([{"op": "stop"}], src=0, group=_SERVICE["group"])
+    _SERVICE.update(active=False)
+
+
+def serve(group=None) -> int:
+    """Ranks other than 0: answer rank 0's requests until it stops the service. Returns the number served."""
+    served = 0
+    while True:
+        box = [None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        request = box[0]
+        if request["op"] == "stop":
+            return served
+        _HANDLERS[request["op"]](None, None, request, group)
+        served += 1
+
+
+def _broadcast_rows(rows, shape, dtype, device, group):
+    t = rows.contiguous() if rows is not None else torch.empty(shape, dtype=dtype, device=device)
+    dist.broadcast(t, src=0, group=group)
+    return t
+
+
+def _serve_nearest(a, b, request, group):
+    """Both row sets travel from rank 0's device to every rank (two broadcasts over NVLink); the reference set is then
+    searched by blocks as in `nearest_neighbors`."""
+    device = torch.device(request["device"]) if request["device"] == "cpu" else torch.device("cuda", torch.cuda.current_device())
+    a = _broadcast_rows(a, (request["qa"], request["width"]), torch.float64, device, group)
+    b = _broadcast_rows(b, (request["qb"], request["width"]), torch.float64, device, group)
+    search = _HANDLERS.get("nearest_core", _nearest_of_device_rows)
+    return search(a, lambda lo, hi: b[lo:hi], request["qb"], request["k"], group, lambda name: None)
+
+
+_HANDLERS["nearest"] = _serve_nearest
+
+
+def nearest_neighbors_from_root(a: torch.Tensor, b: torch.Tensor, k: int = 8):
+    """Rank 0 (after start_root_service): exact nearest / second nearest row of `b` for every non-empty row of `a`
+    (float64 rows on rank 0's device), searched by all ranks. Device tensors (rows_a, nearest row of b, d1, d2)."""
+    group = _SERVICE["group"]
+    request = {"op": "nearest", "qa": int(a.shape[0]), "qb": int(b.shape[0]), "width": int(a.shape[1]), "k": int(k),
+               "device": "cpu" if a.device.type == "cpu" else "cuda"}
+    dist.broadcast_object_list([request], src=0, group=group)
+    return _serve_nearest(a, b, request, group)

@@ -204,8 +204,36 @@ def _match(scan, ref, k=DEFAULT_SHORTLIST, reverse=False, want_second=False, ten
         USE_TENSOR_CORES = previous
 
 
+def _match_with_workers(scan, ref, k, reverse):
+    """The same result with the reference rows searched by every rank of the process group: this process is rank 0 of a
+    root + workers job (distributed.start_root_service; the other ranks sit in distributed.serve)."""
+    from .. import distributed
+
+    a_dev, b_dev = _to_device(scan), _to_device(ref)
+    if a_dev.dim() != 2 or b_dev.dim() != 2:
+        raise ValueError("descriptors must be a 2-D (n, width) array")
+    if a_dev.shape[1] != b_dev.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")
+    rows_a, nn, d1, d2 = distributed.nearest_neighbors_from_root(a_dev, b_dev, k)
+    # nn are row numbers of `ref` itself: rows_b is the identity here
+    fwd = DeviceMatch(rows_a.cpu().numpy(), np.arange(int(b_dev.shape[0]), dtype=np.int64), nn.cpu().numpy().astype(np.int64),
+                      d1.cpu().numpy(), d2.cpu().numpy())
+    if not reverse:
+        return fwd, None
+    rows_b, nn_r, _, _ = distributed.nearest_neighbors_from_root(b_dev, a_dev, k)
+    position_in_rows_a = np.full(int(a_dev.shape[0]), -1, dtype=np.int64)
+    position_in_rows_a[fwd.rows_a] = np.arange(fwd.rows_a.shape[0])
+    nn_reverse = np.full(int(b_dev.shape[0]), -1, dtype=np.int64)
+    nn_reverse[rows_b.cpu().numpy()] = position_in_rows_a[nn_r.cpu().numpy()]
+    return fwd, nn_reverse
+
+
 def _match_impl(scan, ref, k, reverse, want_second):
     LAST_STATS.update(queries=0, fallback_rows=0, handoff=0)
+    from .. import distributed
+
+    if distributed.root_service_active() and np.ndim(scan) == 2 and np.ndim(ref) == 2:
+        return _match_with_workers(scan, ref, k, reverse)
     pipelined = (
         isinstance(scan, np.ndarray) and isinstance(ref, np.ndarray) and scan.ndim == 2 and ref.ndim == 2
         and scan.shape[1] == ref.shape[1] and scan.shape[0] >= _PIPELINE_MIN_ROWS

@@ -175,6 +175,51 @@ def _check_matching(rank, size):
     del rng
 
 
+def _check_root_and_workers(rank, size):
+    """One process (rank 0) runs the caller's code, the others serve: the request, the two broadcasts of the operands
+    and the merged answer — with a brute-force search standing in for the CUDA one."""
+    a = torch.from_numpy(synthetic.sparse_unit_rows(70, 32, seed=11).astype(np.float64))
+    b = torch.from_numpy(synthetic.sparse_unit_rows(101, 32, seed=12).astype(np.float64))
+    a[::8] = 0.0
+    b[50] = b[3]
+
+    def brute(a_rows, ref_block, n_ref, k, group, mark):
+        rows_a = torch.nonzero(a_rows.abs().sum(dim=1) > 0).squeeze(1)
+
+        def shard(lo, hi):
+            blk = ref_block(lo, hi)
+            live = torch.nonzero(blk.abs().sum(dim=1) > 0).squeeze(1)
+            if live.shape[0] == 0:
+                inf = torch.full((rows_a.shape[0],), float("inf"), dtype=torch.float64)
+                return torch.full((rows_a.shape[0],), -1, dtype=torch.int64), inf, inf.clone()
+            d = torch.cdist(a_rows[rows_a], blk[live], compute_mode="donot_use_mm_for_euclid_dist")
+            order = torch.sort(d, dim=1, stable=True)
+            second = order.values[:, 1] if live.shape[0] > 1 else torch.full_like(order.values[:, 0], float("inf"))
+            return live[order.indices[:, 0]] + lo, order.values[:, 0], second
+
+        return (rows_a,) + tuple(sfd.sharded_nearest(n_ref, shard, group))
+
+    sfd._HANDLERS["nearest_core"] = brute
+    try:
+        if rank == 0:
+            sfd.start_root_service()
+            assert sfd.root_service_active() == (size > 1)
+            for x, y in ((a, b), (b, a)):
+                rows, nn, d1, d2 = sfd.nearest_neighbors_from_root(x, y, 8) if size > 1 else brute(
+                    x, lambda lo, hi: y[lo:hi], y.shape[0], 8, None, None)
+                live_y = torch.nonzero(y.abs().sum(dim=1) > 0).squeeze(1)
+                d = torch.cdist(x[rows], y[live_y], compute_mode="donot_use_mm_for_euclid_dist")
+                assert torch.equal(rows, torch.nonzero(x.abs().sum(dim=1) > 0).squeeze(1))
+                assert torch.equal(nn, live_y[d.argmin(dim=1)]) and torch.equal(d1, d.min(dim=1).values)
+                assert torch.equal(d2, torch.sort(d, dim=1).values[:, 1])
+            sfd.stop_root_service()
+            assert not sfd.root_service_active()
+        else:
+            assert sfd.serve() == 2
+    finally:
+        sfd._HANDLERS.pop("nearest_core", None)
+
+
 def _check_slabs(rank, size):
     """Halo partition: every keypoint belongs to exactly one slab, and the points a rank sorts (slab + halo) contain
     EVERY neighbour of its keypoints — checked with rows that are exact functions of the neighbour set (count, sum and
@@ -225,7 +270,7 @@ def _check_slabs(rank, size):
 
 @pytest.mark.parametrize("size", [2, 3])
 @pytest.mark.parametrize("fn", ["_check_shot", "_check_fpfh", "_check_fpfh_by_position", "_check_upload_replicated",
-                                "_check_matching", "_check_slabs"])
+                                "_check_matching", "_check_slabs", "_check_root_and_workers"])
 def test_sharded_equals_unsharded(fn, size):
     _spawn(fn, size)
 

@@ -171,6 +171,23 @@ def _nccl_worker(rank, size, port, out_dir):
         o_sa, o_sb, o_nn, o_d1, dmat = matching_oracle.nearest(a, b)
         assert np.array_equal(sa, o_sa) and np.array_equal(sb_nn, o_sb[o_nn]) and np.array_equal(d1, o_d1)
         assert np.array_equal(d2, np.partition(dmat, 1, axis=1)[:, 1])
+        # root + workers: rank 0 calls the package's ordinary matchers, rank 1 lends its GPU; the same matches as alone
+        from shot_fpfh_b200 import matching as m
+
+        if rank == 0:
+            a[::11] = 0.0
+            alone = (m.basic_matching(a, b), m.match_descriptors(a, b, m.threshold_filter, True, False, 100,
+                                                                  threshold_multiplier=1.2),
+                     m.double_matching_with_rejects(a, b, 0.9, verbose=False))
+            sfd.start_root_service()
+            shared = (m.basic_matching(a, b), m.match_descriptors(a, b, m.threshold_filter, True, False, 100,
+                                                                   threshold_multiplier=1.2),
+                      m.double_matching_with_rejects(a, b, 0.9, verbose=False))
+            sfd.stop_root_service()
+            for x, y in zip(alone, shared):
+                assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[0].shape[0] > 50
+        else:
+            assert sfd.serve() == 4  # basic 1, reciprocal 2, ratio 1
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
