@@ -42,9 +42,9 @@ N_POINTS = 1_000_000
 QUERY_VOXEL_IN_SPACINGS = 3.75
 RADIUS_IN_SPACINGS = 5.0
 MIN_NB = 10
-# own kernels per steady-state step: key, place, rank_reorder (grid); candidate_count, list_capacity, search_moments,
-# lrf_eigen, shot_fast, shot_descriptor (the float64 kernel on the handed-over queries)
-OWN_KERNELS_PER_SHOT_STEP = 9
+# own kernels per steady-state step: key, place, rank_reorder (grid); candidate_count, search_moments, lrf_eigen,
+# shot_fast, shot_descriptor (the float64 kernel on the handed-over queries) — the cell-table prefix sum is CUB's
+OWN_KERNELS_PER_SHOT_STEP = 8
 
 
 _JSON_FD = None
@@ -895,6 +895,69 @@ def bench_distributed(args, dist, rank, world):
                        "ms": stages.get("gathered_and_merged")},
         "same_result_on_every_rank": bool(torch.equal(lo, hi)), "nn_checksum": float(digest[0].item()),
     }
+    del state["match"]
+
+    # ---- SHOT over the ranks, one cloud: query blocks on a replicated grid vs the halo partition -------------------
+    kp_xyz = _pinned(np.ascontiguousarray(pts[::10]))
+
+    def run_blocks(timings):
+        state["shot"] = distributed.shot_single_scale(h_pts, h_nrm, kp_xyz, radius, True, MIN_NB, gather=False)
+
+    def run_slabs(timings):
+        state["shot"] = distributed.shot_single_scale(h_pts, h_nrm, kp_xyz, radius, True, MIN_NB, gather=False, partition="slabs")
+
+    def wall(fn):
+        best = float("inf")
+        for _ in range(3):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            fn(None)
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t.item()))
+        return best * 1e3
+
+    out["shot_one_cloud_sharded"] = {
+        "workload": f"one 1M-point cloud, {kp_xyz.shape[0]} keypoints over {world} GPUs, host arrays in, rows left on the devices",
+        "query_blocks_replicated_grid_ms": wall(run_blocks), "halo_slabs_ms": wall(run_slabs), "scaling": "strong",
+        "note": "blocks: every rank uploads and grid-sorts the whole cloud; slabs: an N-th of the upload + one all-gather, "
+                "the grid over the rank's slab of cell layers + 2 layers of halo (bit-identical rows)",
+    }
+    del state["shot"]
+
+    # ---- self-test over NCCL: the sharded drivers against the single-GPU API on the same inputs (what
+    #      tests/test_gpu_distributed.py::test_two_rank_nccl checks, run here so that every scaling run carries it) ----
+    from shot_fpfh_b200.descriptors import ShotMultiprocessor, compute_fpfh_descriptor
+    from shot_fpfh_b200.matching import basic_matching
+
+    n_small = 60_000
+    s_pts, s_nrm = synthetic.bumpy_sphere(n_small, seed=9)
+    s_radius = RADIUS_IN_SPACINGS * synthetic.mean_spacing(n_small)
+    s_kp = np.arange(0, n_small, 7)
+    ok = {}
+    got_b = distributed.shot_single_scale(s_pts, s_nrm, s_pts[s_kp], s_radius, True, MIN_NB, gather=True).cpu().numpy()
+    got_h = distributed.shot_single_scale(s_pts, s_nrm, s_pts[s_kp], s_radius, True, MIN_NB, gather=True,
+                                          partition="slabs").cpu().numpy()
+    got_f = distributed.fpfh(s_kp, s_pts, s_nrm, s_radius, 11, True, gather=True, out_dtype=torch.float64).cpu().numpy()
+    sa = synthetic.sparse_unit_rows(6000, 352, seed=5).astype(np.float64)
+    sb = synthetic.sparse_unit_rows(9001, 352, seed=6).astype(np.float64)
+    sb[8000] = sb[17]
+    m_rows, m_nn, m_d1, _ = distributed.nearest_neighbors(sa, sb)
+    if rank == 0:
+        with ShotMultiprocessor(min_neighborhood_size=MIN_NB, verbose=False) as shot:
+            want = shot.compute_descriptor_single_scale(s_pts, s_nrm, s_pts[s_kp], s_radius)
+        ok["shot_query_blocks_bit_identical"] = bool(np.array_equal(got_b.astype(np.float64), want))
+        ok["shot_halo_slabs_bit_identical"] = bool(np.array_equal(got_h.astype(np.float64), want))
+        ok["fpfh_bit_identical"] = bool(np.array_equal(got_f, compute_fpfh_descriptor(s_kp, s_pts, s_nrm, s_radius, 11, True,
+                                                                                        verbose=False)))
+        w_rows, w_nn = basic_matching(sa, sb)
+        ok["matching_identical"] = bool(np.array_equal(m_rows, w_rows) and np.array_equal(m_nn, w_nn))
+    flag = torch.tensor([float(all(ok.values())) if rank == 0 else 1.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["nccl_selftest"] = {"what": f"sharded drivers over {world} ranks (NCCL) against the single-GPU API, 60k-point cloud / "
+                                    "6000 x 9001 rows", **ok, "passed": bool(flag.item() == 1.0)}
     return out
 
 

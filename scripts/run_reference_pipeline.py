@@ -116,6 +116,11 @@ if __name__ == "__main__":
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        warm = torch.ones(1 << 20, device="cuda")  # the communicator and its NVLink buffers exist before the clock starts
+        dist.all_reduce(warm)
+        dist.broadcast(warm, src=0)
+        dist.broadcast_object_list([{"op": "warm"}], src=0)
+        torch.cuda.synchronize()
         if dist.get_rank() != 0:
             served = sfd.serve()
             print(f"rank {dist.get_rank()}: served {served} requests", flush=True)
