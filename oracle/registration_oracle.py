@@ -1,10 +1,11 @@
 """
-TEST INFRASTRUCTURE — CPU restatement of the reference's RANSAC and point-to-plane ICP.
+TEST INFRASTRUCTURE — CPU restatement of the reference's RANSAC and ICP.
 Only tests/ may import this module; the product never does.
 
   ransac_on_matches    shot_fpfh/matching/ransac.py:17-82   (generator passed in: the reference keeps a module-level
                        `default_rng(72)`, so a fresh `default_rng(72)` here reproduces its FIRST call)
   icp_point_to_plane   shot_fpfh/icp.py:137-189
+  icp_point_to_point   shot_fpfh/icp.py:81-134 as intended (the reference raises: see the function)
   solvers              shot_fpfh/core/solvers.py:9-48, rigid transform algebra core/rigid_transform.py:45-70
 
 Pinned by tests/test_oracle_golden.py::test_registration_oracle_against_reference.
@@ -58,6 +59,28 @@ def point_to_plane_step(scan, ref, normals):  # solvers.py:34-48
     h = np.einsum("ij, ij->i", ref - scan, normals)
     sol = np.linalg.solve(g.T @ g, g.T @ h)
     return Rotation.from_euler("xyz", sol[:3]).as_matrix(), sol[3:6]
+
+
+def icp_point_to_point(scan, ref, init, d_max, subsampled_indices, max_iter=100, rms_threshold=1e-2):
+    """icp.py:81-134 as intended: its RMS line (:118-120) mixes shapes (n, 3) and (n, 1, 3) and the reference raises a
+    TypeError on every input with more than one pair, so this restatement cannot be pinned to reference outputs; the
+    quantity is the one of icp.py:68-72, the root of the summed squared inlier distances."""
+    tree = KDTree(ref)
+    t = init
+    rms = 0.0
+    iterations = 0
+    for _ in range(max_iter):
+        iterations += 1
+        aligned = apply(t, scan[subsampled_indices])  # :103
+        dist, nn = tree.query(aligned)  # :104
+        keep = dist.squeeze(axis=1) <= d_max
+        inliers, nbrs = aligned[keep], nn[keep, 0]
+        step = kabsch(inliers, ref[nbrs])  # :113-115
+        rms = np.sqrt((np.linalg.norm(inliers - ref[nbrs], axis=1) ** 2).sum(axis=0))
+        t = compose(step, t)  # :121
+        if rms < rms_threshold:
+            break
+    return t, rms, rms < rms_threshold, iterations
 
 
 def icp_point_to_plane(scan, ref, ref_normals, init, d_max, subsampled_indices, max_iter=50, rms_threshold=1e-2):

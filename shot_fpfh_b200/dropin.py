@@ -16,7 +16,9 @@ What is replaced (SURVEY.md §8b — exactly what pipeline.py imports at :15 and
         — the two "next" rows immediately upstream of the hot path
     shot_fpfh.matching.ransac_on_matches, shot_fpfh.icp.icp_point_to_plane   (they return this
         package's RigidTransform, which has the reference class's interface)
-Everything else (iterative / random keypoint selection, point-to-point ICP, I/O, configuration, analysis) stays the
+    shot_fpfh.icp.icp_point_to_point — the reference's raises a TypeError on every input with more than one pair (icp.py:118-120,
+        SURVEY.md D-8); the replacement is what it intends (shot_fpfh_b200/icp.py), so `run_icp("point_to_point")` works
+Everything else (iterative / random keypoint selection, the sampling ICP, I/O, configuration, analysis) stays the
 reference's code.
 (`scripts/register_point_clouds.py` does `from shot_fpfh import compute_normals` at import time: call install()
 before importing the script for the GPU normals to be picked up there.)
@@ -77,6 +79,8 @@ def install() -> list[str]:
         ("shot_fpfh.pipeline", "ransac_on_matches", m.ransac_on_matches),
         ("shot_fpfh.icp", "icp_point_to_plane", icp.icp_point_to_plane),
         ("shot_fpfh.pipeline", "icp_point_to_plane", icp.icp_point_to_plane),
+        ("shot_fpfh.icp", "icp_point_to_point", icp.icp_point_to_point),
+        ("shot_fpfh.pipeline", "icp_point_to_point", icp.icp_point_to_point),
         # pipeline.py did `from shot_fpfh.descriptors import ...` / `from shot_fpfh.matching import ...`
         ("shot_fpfh.pipeline", "ShotMultiprocessor", d.ShotMultiprocessor),
         ("shot_fpfh.pipeline", "compute_fpfh_descriptor", d.compute_fpfh_descriptor),

@@ -99,3 +99,28 @@ def test_icp_point_to_plane_against_oracle():
     true_rot = synthetic.rotation_from_rotvec(synthetic._PAIR_ROTVEC)
     assert np.abs(t.rotation - true_rot).max() < 1e-3
     assert torch.cuda.is_available()
+
+
+def test_icp_point_to_point_against_oracle():
+    """The reference's icp_point_to_point raises on every input (icp.py:118-120); the package provides
+    what it intends, checked against the NumPy / KDTree restatement of the same loop."""
+    from shot_fpfh_b200 import ops, synthetic
+    from shot_fpfh_b200.core import RigidTransform
+    from shot_fpfh_b200.device import upload
+    from shot_fpfh_b200.icp import icp_point_to_point
+
+    scan, ref, normals, scan_idx, ref_idx = registration_case()
+    s = np.sqrt(3.0 / scan.shape[0])
+    _, init = ro.ransac_on_matches(scan_idx, ref_idx, scan, ref, np.random.default_rng(seed=72), n_draws=300,
+                                   distance_threshold=0.05)
+    d_max = 4 * s
+    sub = ops.voxel_subsample(upload(scan), 3 * s).cpu().numpy()
+    for max_iter, rms_threshold in ((15, 1e-9), (60, 0.35)):  # runs out of iterations / stops early
+        t, rms, ok = icp_point_to_point(scan, ref, RigidTransform(init[0], init[1]), d_max=d_max, voxel_size=3 * s,
+                                        max_iter=max_iter, rms_threshold=rms_threshold)
+        want_t, want_rms, want_ok, iterations = ro.icp_point_to_point(scan, ref, init, d_max, sub, max_iter=max_iter,
+                                                                      rms_threshold=rms_threshold)
+        assert np.allclose(t.rotation, want_t[0], atol=1e-9) and np.allclose(t.translation, want_t[1], atol=1e-9)
+        assert np.isclose(rms, want_rms, rtol=1e-9) and bool(ok) == bool(want_ok)
+    true_rot = synthetic.rotation_from_rotvec(synthetic._PAIR_ROTVEC)
+    assert np.abs(t.rotation - true_rot).max() < 2e-3
