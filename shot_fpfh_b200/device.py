@@ -67,6 +67,9 @@ def download(t: torch.Tensor) -> np.ndarray:
     return host.numpy()
 
 
+RANKS_SHARING_HOST: int | None = None  # None: the ranks of the node (LOCAL_WORLD_SIZE); set by a root + workers job
+
+
 def host_threads(requested: int | None = None) -> int:
     """
     Host threads that rebuild the dense float64 result. Two of the cores this process may use are left to the
@@ -81,7 +84,7 @@ def host_threads(requested: int | None = None) -> int:
     except AttributeError:  # pragma: no cover
         avail = os.cpu_count() or 1
     # one process per GPU (torchrun): the ranks of a node share its cores
-    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    ranks = RANKS_SHARING_HOST if RANKS_SHARING_HOST else max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
     share = avail // ranks - 2
     return max(1, min(share, 8 if requested is None else int(requested)))
 

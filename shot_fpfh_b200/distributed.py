@@ -182,10 +182,11 @@ def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, m
         return shot_single_scale_slabs(point_cloud, normals, keypoints, radius, normalize, min_neighborhood_size, gather,
                                        out_dtype, group)
     from . import ops
-    from .device import Grid, upload
+    from .descriptors.fpfh import _cached_grid
+    from .device import upload
 
     pts, nrm, kp = upload(point_cloud), upload(normals), upload(keypoints)
-    grid = Grid().build(pts, nrm, radius)
+    grid = _cached_grid().build(pts, nrm, radius)  # (the handle keeps its buffers between calls)
 
     def block(lo, hi):
         q = kp[lo:hi].contiguous()
@@ -193,7 +194,6 @@ def shot_single_scale(point_cloud, normals, keypoints, radius, normalize=True, m
 
     out = sharded_rows(int(kp.shape[0]), block, gather, group)
     torch.cuda.synchronize()
-    grid.close()
     return out
 
 
@@ -266,11 +266,12 @@ def shot_single_scale_slabs(point_cloud, normals, keypoints, radius, normalize=T
     """The halo scheme on the GPUs: the raw cloud reaches every rank once (an N-th over PCIe each, the rest over
     NVLink), each rank sorts its slab + halo only and computes the rows of its slab's keypoints."""
     from . import ops
-    from .device import Grid, grid_geometry, upload
+    from .descriptors.fpfh import _cached_grid
+    from .device import grid_geometry, upload
 
     pts, nrm = upload_replicated(point_cloud, group=group), upload_replicated(normals, group=group)
     kp = upload(keypoints)
-    grid = Grid()
+    grid = _cached_grid()  # (the handle keeps its buffers between calls)
 
     def rows_of(point_idx, keypoint_idx, box):
         grid.build(pts[point_idx].contiguous(), nrm[point_idx].contiguous(), radius, box=box)
@@ -282,7 +283,6 @@ def shot_single_scale_slabs(point_cloud, normals, keypoints, radius, normalize=T
 
     out = sharded_rows_by_slab(pts, kp, float(radius), grid_geometry, rows_of, 352, gather, group, out_dtype)
     torch.cuda.synchronize()
-    grid.close()
     return out
 
 
@@ -437,6 +437,9 @@ def start_root_service(group=None) -> None:
     """Rank 0: from now on the matchers of this package (and of a reference rebound by dropin) use every rank."""
     assert world(group)[0] == 0, "the root service runs on rank 0"
     _SERVICE.update(group=group, active=True)
+    from . import device
+
+    device.RANKS_SHARING_HOST = 1  # the workers build no host arrays: rank 0 keeps the host's cores for its results
 
 
 def stop_root_service() -> None:
@@ -444,6 +447,9 @@ def stop_root_service() -> None:
     if root_service_active():
         dist.broadcast_object_list([{"op": "stop"}], src=0, group=_SERVICE["group"])
     _SERVICE.update(active=False)
+    from . import device
+
+    device.RANKS_SHARING_HOST = None
 
 
 def serve(group=None) -> int:
