@@ -433,13 +433,20 @@ def root_service_active() -> bool:
     return bool(_SERVICE["active"]) and world(_SERVICE["group"])[1] > 1
 
 
-def start_root_service(group=None) -> None:
-    """Rank 0: from now on the matchers of this package (and of a reference rebound by dropin) use every rank."""
+def start_root_service(group=None, warm: bool = True) -> None:
+    """Rank 0: from now on the matchers of this package (and of a reference rebound by dropin) use every rank.
+    `warm`: one small search is served at once, so that every rank has loaded the kernels, sized its allocator and
+    opened its NCCL channels before the first real request (a service is up before the work arrives)."""
     assert world(group)[0] == 0, "the root service runs on rank 0"
     _SERVICE.update(group=group, active=True)
     from . import device
 
     device.RANKS_SHARING_HOST = 1  # the workers build no host arrays: rank 0 keeps the host's cores for its results
+    if warm and root_service_active() and torch.cuda.is_available():
+        g = torch.Generator(device="cuda").manual_seed(1)
+        rows = torch.rand((8192, 352), generator=g, device="cuda", dtype=torch.float64)
+        nearest_neighbors_from_root(rows[:4096].contiguous(), rows, 8)
+        torch.cuda.synchronize()
 
 
 def stop_root_service() -> None:
@@ -473,12 +480,30 @@ def _broadcast_rows(rows, shape, dtype, device, group):
 
 def _serve_nearest(a, b, request, group):
     """Both row sets travel from rank 0's device to every rank (two broadcasts over NVLink); the reference set is then
-    searched by blocks as in `nearest_neighbors`."""
-    device = torch.device(request["device"]) if request["device"] == "cpu" else torch.device("cuda", torch.cuda.current_device())
+    searched by blocks as in `nearest_neighbors`. SF_TRACE_SERVICE=1: rank 0 prints where the time of a request goes."""
+    import os
+    import time
+
+    on_cpu = request["device"] == "cpu"
+    device = torch.device("cpu") if on_cpu else torch.device("cuda", torch.cuda.current_device())
+    trace = os.environ.get("SF_TRACE_SERVICE") == "1" and world(group)[0] == 0 and not on_cpu
+    stamps = []
+
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize()
+            stamps.append((name, time.perf_counter()))
+
+    mark("start")
     a = _broadcast_rows(a, (request["qa"], request["width"]), torch.float64, device, group)
     b = _broadcast_rows(b, (request["qb"], request["width"]), torch.float64, device, group)
+    mark("operands_on_every_rank")
     search = _HANDLERS.get("nearest_core", _nearest_of_device_rows)
-    return search(a, lambda lo, hi: b[lo:hi], request["qb"], request["k"], group, lambda name: None)
+    out = search(a, lambda lo, hi: b[lo:hi], request["qb"], request["k"], group, mark)
+    if trace:
+        print("  service: " + ", ".join(f"{n} {1e3 * (t1 - t0):.1f} ms" for (_, t0), (n, t1) in zip(stamps[:-1], stamps[1:])),
+              flush=True)
+    return out
 
 
 _HANDLERS["nearest"] = _serve_nearest

@@ -202,7 +202,7 @@ def _check_root_and_workers(rank, size):
     sfd._HANDLERS["nearest_core"] = brute
     try:
         if rank == 0:
-            sfd.start_root_service()
+            sfd.start_root_service(warm=False)
             assert sfd.root_service_active() == (size > 1)
             for x, y in ((a, b), (b, a)):
                 rows, nn, d1, d2 = sfd.nearest_neighbors_from_root(x, y, 8) if size > 1 else brute(

@@ -187,7 +187,7 @@ def _nccl_worker(rank, size, port, out_dir):
             for x, y in zip(alone, shared):
                 assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[0].shape[0] > 50
         else:
-            assert sfd.serve() == 4  # basic 1, reciprocal 2, ratio 1
+            assert sfd.serve() == 5  # the warm-up, basic 1, reciprocal 2, ratio 1
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
