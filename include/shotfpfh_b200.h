@@ -223,8 +223,7 @@ int sf_fpfh_block_rows(sf_grid* grid, int64_t first, int64_t count, const int64_
 int sf_nonempty_rows(const double* desc_dev, int64_t n, int32_t width, int64_t* rows_dev, int64_t* count_host,
                      double* absmax_host, void* stream);
 /* Gathers rows `rows_dev` of a float64 matrix into the GEMM operand format: float16 (count, width_padded)
- * scaled by `scale`, plus the float32 squared norms of the ROUNDED rows. width_padded is a multiple of 32 (>= width; the
- * columns past `width` are zero). */
+ * scaled by `scale`, plus the float32 squared norms of the ROUNDED rows. width_padded is a multiple of 64. */
 int sf_match_pack(const double* desc_dev, int32_t width, const int64_t* rows_dev, int64_t count, double scale,
                   void* packed_dev, int32_t width_padded, float* sqnorm_dev, void* stream);
 /* Shortlist: for each of the qa packed query rows, the k packed target rows with the smallest

@@ -454,8 +454,8 @@ extern "C" int sf_match_pack(const double* desc, int32_t width, const int64_t* r
                              void* packed, int32_t width_padded, float* sqnorm, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(desc && rows && packed && sqnorm, SF_ERR_ARG, "sf_match_pack: null argument");
-  SF_REQUIRE(width > 0 && width_padded >= width && width_padded % 32 == 0, SF_ERR_ARG,
-             "sf_match_pack: width_padded must be a multiple of 32 that is >= width");
+  SF_REQUIRE(width > 0 && width_padded >= width && width_padded % 64 == 0, SF_ERR_ARG,
+             "sf_match_pack: width_padded must be a multiple of 64 that is >= width");
   if (count == 0) return SF_OK;
   pack_kernel<<<unsigned((count * 32 + 255) / 256), 256, 0, stream>>>(desc, width, rows, count, scale,
                                                                      static_cast<__half*>(packed), width_padded, sqnorm);
@@ -476,7 +476,7 @@ extern "C" int sf_match_topk(const void* a, int64_t qa, const void* b, const flo
                              int32_t use_tensor_cores, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(a && b && bnorm && score && idx, SF_ERR_ARG, "sf_match_topk: null argument");
-  SF_REQUIRE(width_padded > 0 && width_padded % 32 == 0, SF_ERR_ARG, "sf_match_topk: width_padded %% 32 != 0");
+  SF_REQUIRE(width_padded > 0 && width_padded % 64 == 0, SF_ERR_ARG, "sf_match_topk: width_padded %% 64 != 0");
   SF_REQUIRE(k == 1 || k == 2 || k == 4 || k == 8 || k == 16, SF_ERR_CAPACITY, "sf_match_topk: k must be 1,2,4,8,16");
   SF_REQUIRE(qb + int64_t(index_offset) < (int64_t(1) << 31), SF_ERR_ARG, "sf_match_topk: target index overflow");
   if (qa == 0) return SF_OK;

@@ -174,12 +174,8 @@ struct TopK {
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
     topk_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   const float* __restrict__ bnorm, int64_t qa, int64_t qb, int num_kb, int last_ksteps,
-                   int tiles_per_split, int index_offset, float* __restrict__ score, int32_t* __restrict__ idx,
-                   int debug) {
-  // last_ksteps: 16-column MMA steps of the LAST 64-column block that hold columns of the operands (rows are padded to
-  // 32 columns, not 64: at 352 columns the sixth block is half out of bounds — TMA fills it with zeros — and only its
-  // first two steps are issued: 22 steps per tile, not 24).
+                   const float* __restrict__ bnorm, int64_t qa, int64_t qb, int num_kb, int tiles_per_split,
+                   int index_offset, float* __restrict__ score, int32_t* __restrict__ idx, int debug) {
   // `debug` (env SF_TC_DEBUG, profiling only; results are garbage when set): 1 = skip the MMAs, 2 = skip the
   // epilogue's TMEM reads / top-k, 4 = skip the B loads. Used to attribute time to TMA / MMA / epilogue.
   extern __shared__ uint8_t smem_raw[];
@@ -246,11 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (debug & 1) { mbar_arrive(bar_b_empty(s)); continue; }
         const uint64_t da = make_desc(smem_base + kSmemA + kb * kABlockBytes);
         const uint64_t db = make_desc(smem_base + kSmemB + s * kBStageBytes);
-        const int ksteps = kb == num_kb - 1 ? last_ksteps : kBK / 16;
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k)  // UMMA_K = 16 halves = 32 bytes: +2 in the (>> 4) start-address field
-          if (k < ksteps)
-            tcgen05_mma_f16(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), kIdesc, uint32_t((kb | k) != 0));
+          tcgen05_mma_f16(tmem_d, da + uint64_t(2 * k), db + uint64_t(2 * k), kIdesc, uint32_t((kb | k) != 0));
         tcgen05_commit(bar_b_empty(s));  // frees the B stage once the MMAs that read it have retired
       }
       if (debug & 1) mbar_arrive(bar_t_full(acc));
@@ -388,8 +382,7 @@ static int make_map(CUtensorMap* map, const __half* base, int64_t rows, int wp, 
 
 template <int K>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bnorm, int64_t qa, int64_t qb, int num_kb,
-                  int last_ksteps, int splits, int tiles_per_split, int off, float* score, int32_t* idx,
-                  cudaStream_t stream) {
+                  int splits, int tiles_per_split, int off, float* score, int32_t* idx, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     SF_CUDA(cudaFuncSetAttribute(topk_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
@@ -397,8 +390,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bno
   }
   const dim3 grid(unsigned((qa + kBM - 1) / kBM), unsigned(splits));
   static const int debug = getenv("SF_TC_DEBUG") ? atoi(getenv("SF_TC_DEBUG")) : 0;
-  topk_tc_kernel<K><<<grid, kThreads, kSmemBytes, stream>>>(ma, mb, bnorm, qa, qb, num_kb, last_ksteps, tiles_per_split, off,
-                                                            score, idx, debug);
+  topk_tc_kernel<K><<<grid, kThreads, kSmemBytes, stream>>>(ma, mb, bnorm, qa, qb, num_kb, tiles_per_split, off, score, idx,
+                                                            debug);
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }
@@ -408,7 +401,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bno
 int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bnorm, int64_t qb, int wp, int k,
                    int index_offset, float* score, int32_t* idx, cudaStream_t stream) {
   using namespace tc;
-  SF_REQUIRE(wp % 32 == 0 && wp >= kBK && (wp + kBK - 1) / kBK <= kMaxKBlocks, SF_ERR_CAPACITY,
+  SF_REQUIRE(wp % kBK == 0 && wp / kBK <= kMaxKBlocks, SF_ERR_CAPACITY,
              "tensor-core shortlist: padded width %d exceeds %d (use the CUDA-core kernel)", wp, kMaxKBlocks * kBK);
   SF_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0, SF_ERR_ARG,
              "tensor-core shortlist: operands must be 16-byte aligned");
@@ -433,15 +426,14 @@ int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bn
   int32_t* part_idx = nullptr;
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&part_score), size_t(parts) * qa * k * sizeof(float), stream));
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&part_idx), size_t(parts) * qa * k * sizeof(int32_t), stream));
-  const int num_kb = (wp + kBK - 1) / kBK;
-  const int last_ksteps = (wp - (num_kb - 1) * kBK) / 16;
+  const int num_kb = wp / kBK;
   int rc = SF_OK;
   switch (k) {
-    case 1: rc = launch<1>(map_a, map_b, bnorm, qa, qb, num_kb, last_ksteps, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
-    case 2: rc = launch<2>(map_a, map_b, bnorm, qa, qb, num_kb, last_ksteps, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
-    case 4: rc = launch<4>(map_a, map_b, bnorm, qa, qb, num_kb, last_ksteps, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
-    case 8: rc = launch<8>(map_a, map_b, bnorm, qa, qb, num_kb, last_ksteps, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
-    default: rc = launch<16>(map_a, map_b, bnorm, qa, qb, num_kb, last_ksteps, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
+    case 1: rc = launch<1>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
+    case 2: rc = launch<2>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
+    case 4: rc = launch<4>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
+    case 8: rc = launch<8>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
+    default: rc = launch<16>(map_a, map_b, bnorm, qa, qb, num_kb, splits, tiles_per_split, index_offset, part_score, part_idx, stream); break;
   }
   if (rc == SF_OK) rc = launch_merge_partials(part_score, part_idx, parts, qa, k, score, idx, stream);
   cudaFreeAsync(part_score, stream);

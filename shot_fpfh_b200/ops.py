@@ -341,9 +341,7 @@ def nonempty_rows(desc: torch.Tensor, want_absmax: bool = False):
 
 
 def padded_width(width: int) -> int:
-    """Columns of the packed float16 operand: the next multiple of 32 (352 stays 352: the tensor-core kernel then runs
-    22 K-steps of 16 per tile instead of the 24 a padding to 64 costs)."""
-    return max(64, (width + 31) // 32 * 32)
+    return (width + 63) // 64 * 64
 
 
 def match_pack(desc: torch.Tensor, rows: torch.Tensor, scale: float):
