@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(256)
 // in registers. The votes then run inside the descriptor kernel.
 // One THREAD per query works out the query's cell, the gaps to its faces and its nine culled runs — the part of the
 // search every lane of a warp would otherwise repeat (a third of search_moments_kernel's instructions in its first
-// form) — and leaves them as a table of five int4: start[0..8], pref[1..9] (running totals), two unused words.
+// form) — and leaves them as a table of five int4: delta[0..8] = start - pref (candidate v of run j sits at
+// v + delta[j]), pref[1..9] (running totals), two unused words.
 // The query's slots in the padded list are handed out here as well: a block adds up its queries' candidate counts and
 // takes its share of the list with ONE atomicAdd on a cursor (round 2; a device-wide prefix sum did this before: two
 // more kernels and their launch gaps, 25 us of a 0.57 ms step). Where a query's slots lie is internal — the order of
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 9; ++j) {
       int len;
       culled_run(g, cg, j, r2, start[j], len);
+      start[j] -= total;  // (delta)
       total += len;
       pref[j] = total;
     }
@@ -233,18 +235,26 @@ __global__ void __launch_bounds__(256)
   const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (q >= nq) return;
   const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
-  Runs runs;  // (candidate_count_kernel's table: five broadcast loads, cells out of reach already dropped)
+  // candidate_count_kernel's table (five broadcast loads; cells out of reach already dropped): candidate v of the
+  // concatenated runs sits at v + delta[j] for the last run j with pref[j] <= v. The offset is SELECTED and added once
+  // (written as start[j] + v - pref[j] per run, the compiler keeps nine running sums per lane and bumps them each round)
+  int delta[9], pref[9];
+  int total;
   {
     const int4* t = runs_table + 5 * q;
     const int4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4);
-    runs.start[0] = t0.x; runs.start[1] = t0.y; runs.start[2] = t0.z; runs.start[3] = t0.w;
-    runs.start[4] = t1.x; runs.start[5] = t1.y; runs.start[6] = t1.z; runs.start[7] = t1.w;
-    runs.start[8] = t2.x;
-    runs.pref[0] = 0; runs.pref[1] = t2.y; runs.pref[2] = t2.z; runs.pref[3] = t2.w;
-    runs.pref[4] = t3.x; runs.pref[5] = t3.y; runs.pref[6] = t3.z; runs.pref[7] = t3.w;
-    runs.pref[8] = t4.x; runs.pref[9] = t4.y;
+    delta[0] = t0.x; delta[1] = t0.y; delta[2] = t0.z; delta[3] = t0.w;
+    delta[4] = t1.x; delta[5] = t1.y; delta[6] = t1.z; delta[7] = t1.w; delta[8] = t2.x;
+    pref[0] = 0; pref[1] = t2.y; pref[2] = t2.z; pref[3] = t2.w;
+    pref[4] = t3.x; pref[5] = t3.y; pref[6] = t3.z; pref[7] = t3.w; pref[8] = t4.x;
+    total = t4.y;
   }
-  const int total = runs.pref[9];
+  auto position = [&](int v) {
+    int d = delta[0];
+#pragma unroll
+    for (int j = 1; j < 9; ++j) d = v >= pref[j] ? delta[j] : d;
+    return v + d;
+  };
   int64_t out = cand_offsets[q];
   int count = 0;
   double sw = 0, m[6] = {0, 0, 0, 0, 0, 0};
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(256)
   int pos_next = 0;
   double4 p_next = make_double4(0, 0, 0, 0);
   if (lane < total) {
-    pos_next = run_position(runs, lane);
+    pos_next = position(lane);
     p_next = load_pt(g.pts + pos_next);
   }
   for (int base = 0; base < total; base += 32) {
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(256)
     const int pos = pos_next;
     const double4 p = p_next;
     if (v + 32 < total) {
-      pos_next = run_position(runs, v + 32);
+      pos_next = position(v + 32);
       p_next = load_pt(g.pts + pos_next);
     }
     if (v < total) {
