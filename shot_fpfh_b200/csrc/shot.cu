@@ -517,6 +517,162 @@ __global__ void __launch_bounds__(kShotWarpsPerBlock * 32, 5)
 }
 
 
+// ---- S2, the same float64 kernel with a BLOCK per query -----------------------------------------------------------
+// For the work list of the fast kernel: a few hundred queries (603 of 102 336 at C2), i.e. one warp on each SM walking
+// its query's neighbours 32 at a time — 15-17 us of pure latency at the end of the step. Here the four warps of a block
+// share one set of winner tables and take the batches of 32 neighbours in turn (the sign votes as well), with block
+// barriers where the warp kernel has warp barriers; the assembly of the 352 bins is warp 0's, in the warp kernel's
+// order of additions, so the rows are the warp kernel's bit for bit (the tests compare the two kernels).
+constexpr int kBlockQueryWarps = 4;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kBlockQueryWarps * 32)
+    shot_descriptor_block_kernel(GridView g, const double* __restrict__ queries, double radius,
+                                 const int64_t* __restrict__ offsets, const int32_t* __restrict__ counts,
+                                 const int32_t* __restrict__ nbr, double* __restrict__ lrf, int fuse_votes, int min_nb,
+                                 int normalize, OutT* __restrict__ out, const int32_t* __restrict__ worklist,
+                                 const int32_t* __restrict__ work_count, int nbr_stride,
+                                 const int32_t* __restrict__ status) {
+  if (status != nullptr && *status != 0) return;
+  __shared__ __align__(16) uint32_t keys[kKeyCount];
+  __shared__ __align__(16) float vals[kValCount];
+  __shared__ int part[3][kBlockQueryWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double inv_radius = 1.0 / radius;
+  const int nbr_word = nbr_stride - 1;
+  const int n_items = *work_count;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t q = worklist[item];
+    for (int j = tid; j < kKeyCount / 4; j += kBlockQueryWarps * 32) reinterpret_cast<uint4*>(keys)[j] = make_uint4(0u, 0u, 0u, 0u);
+    const double qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
+    const int64_t begin = offsets[q], end = counts ? begin + counts[q] : offsets[q + 1];
+    double f[9];
+    if (!fuse_votes) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = lrf[9 * q + k];
+    } else if (end == begin) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = (k % 4 == 0) ? 1.0 : 0.0;  // shot.py:24-25
+      if (tid < 9) lrf[9 * q + tid] = (tid % 4 == 0) ? 1.0 : 0.0;
+    } else {
+      double x[3] = {lrf[9 * q], lrf[9 * q + 1], lrf[9 * q + 2]}, z[3] = {lrf[9 * q + 3], lrf[9 * q + 4], lrf[9 * q + 5]};
+      int neg_x = 0, neg_z = 0;
+      for (int64_t i = begin + tid; i < end; i += kBlockQueryWarps * 32) {
+        const double4 p = load_pt(g.pts + (__ldg(nbr + i * nbr_stride + nbr_word) & 0x7fffffff));
+        const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+        neg_x += (cx * x[0] + cy * x[1] + cz * x[2]) < 0.0;
+        neg_z += (cx * z[0] + cy * z[1] + cz * z[2]) < 0.0;
+      }
+      neg_x = warp_sum(neg_x);
+      neg_z = warp_sum(neg_z);
+      if (lane == 0) { part[0][warp] = neg_x; part[1][warp] = neg_z; }
+      __syncthreads();  // (also: every thread has read the raw axes before the frame overwrites them)
+      neg_x = neg_z = 0;
+#pragma unroll
+      for (int w = 0; w < kBlockQueryWarps; ++w) { neg_x += part[0][w]; neg_z += part[1][w]; }
+      const int k_all = int(end - begin);
+      if (neg_x > k_all - neg_x) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
+      if (neg_z > k_all - neg_z) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
+      const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { f[3 * a] = x[a]; f[3 * a + 1] = y[a]; f[3 * a + 2] = z[a]; }
+      if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) lrf[9 * q + k] = f[k];
+      }
+    }
+    __syncthreads();  // the keys are cleared
+    int positive = 0;
+    for (int64_t base = begin; base < end; base += kBlockQueryWarps * 32) {  // block-uniform trip count (barriers inside)
+      const int64_t i = base + tid;
+      ShotDecision d;
+      bool active = false;
+      if (i < end) {
+        const int s = __ldg(nbr + i * nbr_stride + nbr_word) & 0x7fffffff;
+        const double4 p = load_pt(g.pts + s), n = load_pt(g.nrm + s);
+        const double cx = p.x - qx, cy = p.y - qy, cz = p.z - qz;
+        const double d2 = rdist3(cx, cy, cz);
+        if (d2 > 0.0) {  // shot.py:213
+          active = true;
+          ++positive;
+          const double rho = sqrt(d2);
+          const double X = cx * f[0] + cy * f[3] + cz * f[6];
+          const double Y = cx * f[1] + cy * f[4] + cz * f[7];
+          const double Z = cx * f[2] + cy * f[5] + cz * f[8];
+          double cosine = n.x * f[2] + n.y * f[5] + n.z * f[8];
+          cosine = fmin(1.0, fmax(-1.0, cosine));
+          d = shot_decide(X, Y, Z, cosine, rho, radius, inv_radius);
+          atomicMax(keys + kKeyOwn + d.own, d.key);
+          atomicMax(keys + kKeyCos + d.cos_nb, d.key);
+          atomicMax(keys + kKeyAz + d.az_nb, d.key);
+        }
+      }
+      __syncthreads();
+      if (active) {
+        const bool win_own = keys[kKeyOwn + d.own] == d.key;
+        const bool win_cos = keys[kKeyCos + d.cos_nb] == d.key;
+        const bool win_az = keys[kKeyAz + d.az_nb] == d.key;
+        float a_az = 0.0f;
+        if (win_own || win_az) a_az = shot_azimuth(d);
+        if (win_own) {
+          float own_vol, other_vol;
+          shot_elevation(d, own_vol, other_vol);
+          vals[kValOwn + d.own] = (1.0f - d.a_cos) + d.own_shell + own_vol + (1.0f - a_az);
+          vals[kValRad + d.own] = d.other_shell;
+          vals[kValEl + d.own] = other_vol;
+        }
+        if (win_cos) vals[kValCos + d.cos_nb] = d.a_cos;
+        if (win_az) vals[kValAz + d.az_nb] = a_az;
+      }
+      __syncthreads();  // the stores above are ordered before the next round's key updates
+    }
+    positive = warp_sum(positive);
+    if (lane == 0) part[2][warp] = positive;
+    __syncthreads();
+    if (warp == 0) {  // the warp kernel's assembly, lane for lane
+      positive = 0;
+#pragma unroll
+      for (int w = 0; w < kBlockQueryWarps; ++w) positive += part[2][w];
+      constexpr int kGroups = kShotLen / 4, kGroupRounds = (kGroups + 31) / 32;
+      float v[kGroupRounds][4];
+      double sq = 0.0;
+#pragma unroll
+      for (int j = 0; j < kGroupRounds; ++j) {
+        const int grp = lane + 32 * j;
+        if (grp < kGroups) {
+          const uint4 ko = *reinterpret_cast<const uint4*>(keys + kKeyOwn + 4 * grp);
+          const uint4 kc = *reinterpret_cast<const uint4*>(keys + kKeyCos + 4 * grp);
+          const uint4 ka = *reinterpret_cast<const uint4*>(keys + kKeyAz + 4 * grp);
+          const float4 vo = *reinterpret_cast<const float4*>(vals + kValOwn + 4 * grp);
+          const float4 vr = *reinterpret_cast<const float4*>(vals + kValRad + 4 * grp);
+          const float4 ve = *reinterpret_cast<const float4*>(vals + kValEl + 4 * grp);
+          const float4 vc = *reinterpret_cast<const float4*>(vals + kValCos + 4 * grp);
+          const float4 va = *reinterpret_cast<const float4*>(vals + kValAz + 4 * grp);
+          const uint32_t ko_[4] = {ko.x, ko.y, ko.z, ko.w}, kc_[4] = {kc.x, kc.y, kc.z, kc.w},
+                         ka_[4] = {ka.x, ka.y, ka.z, ka.w};
+          const float vo_[4] = {vo.x, vo.y, vo.z, vo.w}, vr_[4] = {vr.x, vr.y, vr.z, vr.w},
+                      ve_[4] = {ve.x, ve.y, ve.z, ve.w}, vc_[4] = {vc.x, vc.y, vc.z, vc.w},
+                      va_[4] = {va.x, va.y, va.z, va.w};
+          shot_bin_group_compact(ko_, kc_, ka_, vo_, vr_, ve_, vc_, va_, v[j]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) sq += double(v[j][t]) * double(v[j][t]);
+        }
+      }
+      sq = warp_sum(sq);
+      const double norm = sqrt(sq);
+      const bool keep = positive > min_nb && norm > 0.0;  // shot.py:212, :301-306
+      const float inv = keep ? (normalize ? float(1.0 / norm) : 1.0f) : 0.0f;
+      OutT* row = out + q * kShotLen;
+#pragma unroll
+      for (int j = 0; j < kGroupRounds; ++j) {
+        const int grp = lane + 32 * j;
+        if (grp < kGroups) store_group(row + 4 * grp, v[j][0] * inv, v[j][1] * inv, v[j][2] * inv, v[j][3] * inv);
+      }
+    }
+    __syncthreads();  // the tables are read before the next query clears the keys
+  }
+}
+
 // ---- S2, fast path: float32-filtered decisions -----------------------------------------------------------------------
 // One warp per query with at most 128 neighbours (four per lane, kept in registers; a slot's code is skipped when the
 // query has no neighbour for it). Round 1's kernel (above) issues ~1650 warp instructions per query, half of them
@@ -1045,14 +1201,27 @@ static int launch_descriptor(sf_grid* g, const double* queries, int64_t nq, doub
   const int32_t* wl = exact_only ? nullptr : worklist;
   const int32_t* nbr = static_cast<const int32_t*>(list);
   const int stride = records ? 4 : 1;
-  if (out_is_f64)
+  if (wl != nullptr && !env_flag("SF_SHOT_WARP_WORKLIST")) {
+    // the work list of the fast kernel: a block per query (as many blocks as the device holds at once; each strides over
+    // the list, whose length only the device knows)
+    const unsigned list_blocks = unsigned(std::min<int64_t>(nq, 148 * 8));
+    if (out_is_f64)
+      shot_descriptor_block_kernel<double><<<list_blocks, kBlockQueryWarps * 32, 0, stream>>>(
+          view, queries, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<double*>(out), wl,
+          work_count, stride, status);
+    else
+      shot_descriptor_block_kernel<float><<<list_blocks, kBlockQueryWarps * 32, 0, stream>>>(
+          view, queries, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<float*>(out), wl,
+          work_count, stride, status);
+  } else if (out_is_f64) {
     shot_descriptor_kernel<double><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
         view, queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<double*>(out), wl,
         work_count, stride, status);
-  else
+  } else {
     shot_descriptor_kernel<float><<<blocks, kShotWarpsPerBlock * 32, smem, stream>>>(
         view, queries, nq, radius, offsets, counts, nbr, lrf, fuse_votes, min_nb, normalize, static_cast<float*>(out), wl,
         work_count, stride, status);
+  }
   SF_CUDA(cudaGetLastError());
   return SF_OK;
 }

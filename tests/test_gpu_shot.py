@@ -277,6 +277,35 @@ def test_calls_without_host_synchronisation_check_their_assumptions():
     assert np.array_equal(rows(spec, sparse_q + np.array([0.0, 0.0, 0.5])), want_moved) and spec.poll() == 0
 
 
+def test_block_per_query_kernel_equals_the_warp_kernel_on_the_work_list(monkeypatch):
+    """The queries the float32 kernel hands over are finished by shot_descriptor_block_kernel (a block per query, four
+    warps sharing the winner tables); SF_SHOT_WARP_WORKLIST=1 sends them to the warp-per-query float64 kernel instead:
+    the same rows bit for bit, frames included — also with more than 128 neighbours per query (everything handed over)."""
+    import torch
+
+    from shot_fpfh_b200 import ops
+    from shot_fpfh_b200.device import Grid, upload
+
+    n = 120_000
+    pts, normals = synthetic.bumpy_sphere(n, seed=23)
+    p_dev, n_dev = upload(pts), upload(normals)
+    for spacings, stride in ((5.0, 2), (8.0, 40)):  # K ~ 71: a few hundred handed over; K ~ 190: nearly all of them
+        radius = spacings * synthetic.mean_spacing(n)
+        q_dev = upload(np.ascontiguousarray(pts[::stride]))
+        grid = Grid().build(p_dev, n_dev, radius)
+        got = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("SF_SHOT_WARP_WORKLIST", flag)
+            d, lrf, pairs = ops.shot_single_scale(grid, q_dev, radius, 10, True, out_dtype=torch.float32, want_lrf=True,
+                                                  want_pairs=True)
+            torch.cuda.synchronize()
+            got[flag] = (d.clone(), lrf.clone(), ops.shot_last_deferred())
+        assert got["0"][2] == got["1"][2] and got["0"][2] > (50 if spacings == 5.0 else 0.9 * q_dev.shape[0])
+        assert torch.equal(got["0"][0], got["1"][0]) and torch.equal(got["0"][1], got["1"][1])
+        assert bool((got["0"][0].abs().sum(dim=1) > 0).float().mean() > 0.99)
+        grid.close()
+
+
 def test_result_transport_equals_a_dense_copy():
     """device.SparseRowsDownload (csrc/transport.cu + csrc/host_io.cpp): compact -> copy -> expand == rows.double()."""
     import torch
