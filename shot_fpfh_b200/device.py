@@ -40,7 +40,7 @@ def upload(a, dtype=torch.float64) -> torch.Tensor:
     np_dtype = {torch.float64: np.float64, torch.float32: np.float32, torch.int64: np.int64, torch.int32: np.int32}[dtype]
     host = np.ascontiguousarray(a, dtype=np_dtype)
     source = torch.from_numpy(host)
-    if host.nbytes >= _STAGED_UPLOAD_BYTES and not source.is_pinned() and not os.environ.get("SF_NO_STAGED_UPLOAD"):
+    if host.nbytes >= _STAGED_UPLOAD_BYTES and not source.is_pinned():
         # Pageable memory: the driver would stage the copy itself, synchronously and on one thread (50 MB of cloud:
         # 9 ms). The library's host threads copy it into a page-locked block of PyTorch's caching host allocator (the
         # allocator keeps the block until the copy queued below has run), and the DMA engine takes it from there.
