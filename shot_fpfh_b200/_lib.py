@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_voi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libshotfpfh_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 SF_OK, SF_ERR_CUDA, SF_ERR_ARG, SF_ERR_CAPACITY = 0, 1, 2, 3
 
@@ -73,7 +73,7 @@ def _load() -> ctypes.CDLL:
         "sf_match_certify": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_int64,
                              c_int32, c_void_p, c_void_p],
         "sf_match_exhaustive": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
-                                c_void_p, c_void_p],
+                                c_double, c_void_p, c_void_p],
         "sf_match_exhaustive_topk": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_void_p, c_void_p],
         "sf_match_pack": [c_void_p, c_int32, c_void_p, c_int64, c_double, c_void_p, c_int32, c_void_p, c_void_p],

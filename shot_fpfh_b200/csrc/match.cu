@@ -331,57 +331,84 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// The exhaustive redo as ONE pass over the targets for all the flagged queries together: a block stages 32 target rows
-// in shared memory (column-major: lane = target, conflict-free) and every warp runs its share of the flagged queries
-// against them in float64. Only targets at most `limit[q]` away matter — the exact nearest (second-nearest) distance
-// the re-rank already found bounds the true one from above — so they are appended to a short per-query list
-// (kExhaustiveCap entries; a query with more such near-ties is marked for the block-per-query kernel above).
-constexpr int kExhaustiveTile = 32;
+// The exhaustive redo as ONE pass over the targets for all the flagged queries together. Only targets at most `limit[q]`
+// away matter — the exact nearest (second-nearest) distance the re-rank already found bounds the true one from above —
+// and the float64 re-rank decides among them afterwards, so this pass only has to FIND them: it runs in float32 on the
+// CUDA cores with a proven slack (first form: float64, a warp per query against 32 staged target rows, one broadcast
+// load per element: 21 ms for 514 flagged queries x 200k targets, as long as the tensor-core shortlist of all 200k).
+//   * distances are accumulated as sum (a_i - b_i)^2 on the float32 images of the rows — not as |a|^2 + |b|^2 - 2 a.b,
+//     whose error scales with the norms and not with the distance (the flagged queries ARE the near-duplicates);
+//   * |fl32(a) - a| <= u |a| element-wise (u = 2^-24), so the distance of the images differs from the true one by at
+//     most u (|a| + |b|) <= u * norm_bound; a sum of n squares accumulated in float32 is within (n + 2) u of itself,
+//     relatively. A target is listed when   s <= (limit + 2 u norm_bound)^2 * (1 + (n + 8) 2^-23):   never misses one
+//     that is within `limit`, lists a few more than the float64 test would;
+//   * a block computes 64 flagged queries x 64 targets, 4 x 4 per thread, from shared-memory tiles of 32 columns.
+// The list is capped at kExhaustiveCap; the selection below keeps at most 16 and marks longer lists for the
+// block-per-query float64 kernel above.
 constexpr int kExhaustiveCap = 64;
+constexpr int kEx32Rows = 64, kEx32Cols = 32;
 
 __global__ void __launch_bounds__(256)
-    exhaustive_tile_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a,
-                           const int64_t* __restrict__ which, int64_t n_which, const double* __restrict__ limit,
-                           const double* __restrict__ b, const int64_t* __restrict__ rows_b, int64_t qb, int width,
-                           int32_t* __restrict__ counts, double* __restrict__ list_d, int32_t* __restrict__ list_i) {
-  extern __shared__ double tile[];  // [width][kExhaustiveTile]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t first = blockIdx.x * int64_t(kExhaustiveTile);
-  for (int e = threadIdx.x; e < width * kExhaustiveTile; e += blockDim.x) {
-    const int t = e / width, c = e - t * width;  // consecutive threads read consecutive columns of a row
-    const int64_t j = first + t;
-    tile[c * kExhaustiveTile + t] = j < qb ? b[(rows_b ? rows_b[j] : j) * width + c] : 0.0;
+    exhaustive_tile32_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a,
+                             const int64_t* __restrict__ which, int64_t n_which, const double* __restrict__ limit,
+                             const double* __restrict__ b, const int64_t* __restrict__ rows_b, int64_t qb, int width,
+                             double norm_bound, int32_t* __restrict__ counts, double* __restrict__ list_d,
+                             int32_t* __restrict__ list_i) {
+  __shared__ __align__(16) float as[kEx32Cols][kEx32Rows + 4];  // [column][query of the tile]
+  __shared__ __align__(16) float bs[kEx32Cols][kEx32Rows + 4];  // [column][target of the tile]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 4 targets 4 tx.., 4 queries 4 ty..
+  const int64_t j0 = blockIdx.x * int64_t(kEx32Rows), i0 = blockIdx.y * int64_t(kEx32Rows);
+  // the rows this thread stages: row (tid >> 2) of both tiles, 8 of the 32 columns of a chunk (coalesced 64-byte pieces)
+  const int load_row = tid >> 2, load_col = (tid & 3) * 8;
+  const int64_t item_l = i0 + load_row, j_l = j0 + load_row;
+  const double* src_a = item_l < n_which ? a + (rows_a ? rows_a[which[item_l]] : which[item_l]) * width : nullptr;
+  const double* src_b = j_l < qb ? b + (rows_b ? rows_b[j_l] : j_l) * width : nullptr;
+  float acc[4][4] = {};
+  for (int c0 = 0; c0 < width; c0 += kEx32Cols) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + load_col + e;
+      as[load_col + e][load_row] = (src_a != nullptr && c < width) ? float(__ldg(src_a + c)) : 0.0f;
+      bs[load_col + e][load_row] = (src_b != nullptr && c < width) ? float(__ldg(src_b + c)) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < kEx32Cols; ++c) {
+      const float4 av = *reinterpret_cast<const float4*>(&as[c][4 * ty]);
+      const float4 bv = *reinterpret_cast<const float4*>(&bs[c][4 * tx]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float d = a4[u] - b4[v];
+          acc[u][v] = fmaf(d, d, acc[u][v]);
+        }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  const int64_t j = first + lane;
-  for (int64_t item = warp; item < n_which; item += 8) {
-    const int64_t q = which[item];
-    const double* ra = a + (rows_a ? rows_a[q] : q) * width;
-    double s0 = 0.0, s1 = 0.0;
-    int c = 0;
-    for (; c + 1 < width; c += 2) {
-      const double d0 = __ldg(ra + c) - tile[c * kExhaustiveTile + lane];
-      const double d1 = __ldg(ra + c + 1) - tile[(c + 1) * kExhaustiveTile + lane];
-      s0 = fma(d0, d0, s0);
-      s1 = fma(d1, d1, s1);
-    }
-    if (c < width) {
-      const double d0 = __ldg(ra + c) - tile[c * kExhaustiveTile + lane];
-      s0 = fma(d0, d0, s0);
-    }
-    const double d2 = s0 + s1, lim = limit[item];
-    if (j < qb && d2 <= lim * lim * (1.0 + 1e-12)) {
-      const int slot = atomicAdd(counts + item, 1);
-      if (slot < kExhaustiveCap) {
-        list_d[item * kExhaustiveCap + slot] = d2;
-        list_i[item * kExhaustiveCap + slot] = int32_t(j);
+  const double slack = 2.0 * 5.9604644775390625e-8 * norm_bound, grow = 1.0 + double(width + 8) * 1.1920928955078125e-7;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t item = i0 + 4 * ty + u;
+    if (item >= n_which) continue;
+    const double lim = limit[item] + slack, bound = lim * lim * grow;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int64_t j = j0 + 4 * tx + v;
+      if (j < qb && double(acc[u][v]) <= bound) {
+        const int slot = atomicAdd(counts + item, 1);
+        if (slot < kExhaustiveCap) {
+          list_d[item * kExhaustiveCap + slot] = double(acc[u][v]);
+          list_i[item * kExhaustiveCap + slot] = int32_t(j);
+        }
       }
     }
   }
 }
 
-// The 16 nearest of each flagged query's list (by distance, then index), -1 padded; cand[item][0] = -2 marks a list
-// that overflowed.
+// The listed targets of each flagged query in (float32 distance, index) order, -1 padded — all of them go to the float64
+// re-rank, so the order only matters to nobody; cand[item][0] = -2 marks a list longer than the 16 the re-rank takes.
 __global__ void exhaustive_select_kernel(int64_t n_which, const int32_t* __restrict__ counts,
                                          const double* __restrict__ list_d, const int32_t* __restrict__ list_i,
                                          int32_t* __restrict__ cand) {
@@ -389,7 +416,7 @@ __global__ void exhaustive_select_kernel(int64_t n_which, const int32_t* __restr
   if (item >= n_which) return;
   const int n = counts[item];
   int32_t* out = cand + item * 16;
-  if (n > kExhaustiveCap) {
+  if (n > 16) {
     for (int t = 0; t < 16; ++t) out[t] = t == 0 ? -2 : -1;
     return;
   }
@@ -596,18 +623,12 @@ extern "C" int sf_match_exhaustive_topk(const double* a, const int64_t* rows_a, 
 
 extern "C" int sf_match_exhaustive(const double* a, const int64_t* rows_a, const int64_t* which, int64_t n_which,
                                    const double* limit, const double* b, const int64_t* rows_b, int64_t qb, int32_t width,
-                                   int32_t* cand16, void* stream_) {
+                                   double norm_bound, int32_t* cand16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(a && which && limit && b && cand16 && width > 0, SF_ERR_ARG, "sf_match_exhaustive: bad arguments");
+  SF_REQUIRE(norm_bound >= 0.0 && std::isfinite(norm_bound), SF_ERR_ARG, "sf_match_exhaustive: norm_bound must be finite");
   SF_REQUIRE(qb < (int64_t(1) << 31), SF_ERR_ARG, "sf_match_exhaustive: too many targets");
   if (n_which == 0) return SF_OK;
-  const size_t smem = size_t(width) * kExhaustiveTile * sizeof(double);
-  SF_REQUIRE(smem <= 200 * 1024, SF_ERR_CAPACITY, "sf_match_exhaustive: rows of %d columns do not fit the tile", width);
-  static bool configured = false;
-  if (!configured) {
-    SF_CUDA(cudaFuncSetAttribute(exhaustive_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
   int32_t* counts = nullptr;
   double* list_d = nullptr;
   int32_t* list_i = nullptr;
@@ -615,9 +636,11 @@ extern "C" int sf_match_exhaustive(const double* a, const int64_t* rows_a, const
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&list_d), size_t(n_which) * kExhaustiveCap * 8, stream));
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&list_i), size_t(n_which) * kExhaustiveCap * 4, stream));
   SF_CUDA(cudaMemsetAsync(counts, 0, size_t(n_which) * 4, stream));
-  const unsigned tiles = unsigned((qb + kExhaustiveTile - 1) / kExhaustiveTile);
-  exhaustive_tile_kernel<<<tiles, 256, smem, stream>>>(a, rows_a, which, n_which, limit, b, rows_b, qb, width, counts, list_d,
-                                                       list_i);
+  const int64_t query_tiles = (n_which + kEx32Rows - 1) / kEx32Rows;
+  SF_REQUIRE(query_tiles <= 65535, SF_ERR_CAPACITY, "sf_match_exhaustive: %lld flagged queries", (long long)n_which);
+  const dim3 grid(unsigned((qb + kEx32Rows - 1) / kEx32Rows), unsigned(query_tiles));
+  exhaustive_tile32_kernel<<<grid, 256, 0, stream>>>(a, rows_a, which, n_which, limit, b, rows_b, qb, width, norm_bound, counts,
+                                                     list_d, list_i);
   exhaustive_select_kernel<<<unsigned((n_which + 127) / 128), 128, 0, stream>>>(n_which, counts, list_d, list_i, cand16);
   SF_CUDA(cudaGetLastError());
   cudaFreeAsync(counts, stream);
