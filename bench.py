@@ -748,8 +748,8 @@ def bench_match(args, pk, q: int = 200_000):
                 which = torch.nonzero(flags).squeeze(1)
                 state["fallback_rows"] = int(which.shape[0])
                 if state["fallback_rows"]:
-                    norm_bound = (1.01 * (float(an.max().sqrt().item()) + bmax) + 352 ** 0.5 * 2.0 ** -23) / scale
-                    mm.exhaustive_redo(a, ra, which, b, rb, d2[which], norm_bound)
+                    norm_bound = 1.01 * (float(an.max().sqrt().item()) + bmax) + 352 ** 0.5 * 2.0 ** -23
+                    mm.exhaustive_redo(a, ra, which, b, rb, d2[which], scale, norm_bound)
 
         ms, stages = timed_steps(step, steps, min(args.warmup, 3), lambda: flush_buf.fill_(1))
         tf = 2.0 * qa * int(b.shape[0]) * 352 / (stages["shortlist_gemm"] * 1e-3) / 1e12

@@ -254,13 +254,14 @@ int sf_match_certify(const float* score_dev, int32_t k, const float* a_sqnorm_de
                      int32_t want_second, uint8_t* flags_dev, void* stream);
 /* The exhaustive redo of all flagged queries in ONE pass over the targets: limit_dev[i] = an upper bound on the wanted
  * distance of flagged query which_dev[i] (its exact nearest / second-nearest distance from the re-rank); every target at
- * most that far is listed — the pass runs in float32 with a proven slack, norm_bound = an upper bound on |a| + |b| over
- * the rows, so it may list a few more — and the list goes to cand16_dev (n_which, 16), -1 padded, for sf_match_rerank,
+ * most that far is listed — the pass runs in float32 on the rows multiplied by `scale` (a power of two that brings every
+ * |entry| below 1: sf_match_pack's) with a proven slack, norm_bound = an upper bound on |a| + |b| over the SCALED rows,
+ * so it may list a few more — and the list goes to cand16_dev (n_which, 16), -1 padded, for sf_match_rerank,
  * which decides in float64. cand16_dev[i][0] = -2 marks a query with more than 16 listed targets: those take
  * sf_match_exhaustive_topk. */
 int sf_match_exhaustive(const double* a_dev, const int64_t* rows_a_dev, const int64_t* which_dev, int64_t n_which,
                         const double* limit_dev, const double* b_dev, const int64_t* rows_b_dev, int64_t qb, int32_t width,
-                        double norm_bound, int32_t* cand16_dev, void* stream);
+                        double scale, double norm_bound, int32_t* cand16_dev, void* stream);
 /* Exhaustive float64 shortlist of the flagged queries which_dev[0..n_which) (positions in rows_a): the k (8 or 16)
  * nearest targets by float64 distance, lowest index on ties, written into their rows of cand_dev (qa, k); the caller
  * re-ranks those rows with sf_match_rerank. */

@@ -73,7 +73,7 @@ def _load() -> ctypes.CDLL:
         "sf_match_certify": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_int64,
                              c_int32, c_void_p, c_void_p],
         "sf_match_exhaustive": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
-                                c_double, c_void_p, c_void_p],
+                                c_double, c_double, c_void_p, c_void_p],
         "sf_match_exhaustive_topk": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_void_p, c_void_p],
         "sf_match_pack": [c_void_p, c_int32, c_void_p, c_int64, c_double, c_void_p, c_int32, c_void_p, c_void_p],

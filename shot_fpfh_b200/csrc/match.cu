@@ -352,8 +352,11 @@ __global__ void __launch_bounds__(256)
     exhaustive_tile32_kernel(const double* __restrict__ a, const int64_t* __restrict__ rows_a,
                              const int64_t* __restrict__ which, int64_t n_which, const double* __restrict__ limit,
                              const double* __restrict__ b, const int64_t* __restrict__ rows_b, int64_t qb, int width,
-                             double norm_bound, int32_t* __restrict__ counts, double* __restrict__ list_d,
-                             int32_t* __restrict__ list_i) {
+                             double scale, double norm_bound, int32_t* __restrict__ counts,
+                             double* __restrict__ list_d, int32_t* __restrict__ list_i) {
+  // scale: the power of two that brings the largest |entry| of both sets just below 1 (the float16 operands' scale):
+  // the rows are multiplied by it (exactly) before they are narrowed, so no square can overflow float32 whatever the
+  // caller's units; limit and norm_bound (given in scaled units) follow.
   __shared__ __align__(16) float as[kEx32Cols][kEx32Rows + 4];  // [column][query of the tile]
   __shared__ __align__(16) float bs[kEx32Cols][kEx32Rows + 4];  // [column][target of the tile]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 4 targets 4 tx.., 4 queries 4 ty..
@@ -368,8 +371,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + load_col + e;
-      as[load_col + e][load_row] = (src_a != nullptr && c < width) ? float(__ldg(src_a + c)) : 0.0f;
-      bs[load_col + e][load_row] = (src_b != nullptr && c < width) ? float(__ldg(src_b + c)) : 0.0f;
+      as[load_col + e][load_row] = (src_a != nullptr && c < width) ? float(__ldg(src_a + c) * scale) : 0.0f;
+      bs[load_col + e][load_row] = (src_b != nullptr && c < width) ? float(__ldg(src_b + c) * scale) : 0.0f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -387,12 +390,13 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  const double slack = 2.0 * 5.9604644775390625e-8 * norm_bound, grow = 1.0 + double(width + 8) * 1.1920928955078125e-7;
+  // (+ 1e-30: entries that underflow float32 after the scaling are off by at most 2^-150 each)
+  const double slack = 2.0 * 5.9604644775390625e-8 * norm_bound + 1e-30, grow = 1.0 + double(width + 8) * 1.1920928955078125e-7;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int64_t item = i0 + 4 * ty + u;
     if (item >= n_which) continue;
-    const double lim = limit[item] + slack, bound = lim * lim * grow;
+    const double lim = limit[item] * scale + slack, bound = lim * lim * grow;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       const int64_t j = j0 + 4 * tx + v;
@@ -623,10 +627,11 @@ extern "C" int sf_match_exhaustive_topk(const double* a, const int64_t* rows_a, 
 
 extern "C" int sf_match_exhaustive(const double* a, const int64_t* rows_a, const int64_t* which, int64_t n_which,
                                    const double* limit, const double* b, const int64_t* rows_b, int64_t qb, int32_t width,
-                                   double norm_bound, int32_t* cand16, void* stream_) {
+                                   double scale, double norm_bound, int32_t* cand16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SF_REQUIRE(a && which && limit && b && cand16 && width > 0, SF_ERR_ARG, "sf_match_exhaustive: bad arguments");
-  SF_REQUIRE(norm_bound >= 0.0 && std::isfinite(norm_bound), SF_ERR_ARG, "sf_match_exhaustive: norm_bound must be finite");
+  SF_REQUIRE(norm_bound >= 0.0 && std::isfinite(norm_bound) && scale > 0.0 && std::isfinite(scale), SF_ERR_ARG,
+             "sf_match_exhaustive: scale and norm_bound must be finite");
   SF_REQUIRE(qb < (int64_t(1) << 31), SF_ERR_ARG, "sf_match_exhaustive: too many targets");
   if (n_which == 0) return SF_OK;
   int32_t* counts = nullptr;
@@ -639,8 +644,8 @@ extern "C" int sf_match_exhaustive(const double* a, const int64_t* rows_a, const
   const int64_t query_tiles = (n_which + kEx32Rows - 1) / kEx32Rows;
   SF_REQUIRE(query_tiles <= 65535, SF_ERR_CAPACITY, "sf_match_exhaustive: %lld flagged queries", (long long)n_which);
   const dim3 grid(unsigned((qb + kEx32Rows - 1) / kEx32Rows), unsigned(query_tiles));
-  exhaustive_tile32_kernel<<<grid, 256, 0, stream>>>(a, rows_a, which, n_which, limit, b, rows_b, qb, width, norm_bound, counts,
-                                                     list_d, list_i);
+  exhaustive_tile32_kernel<<<grid, 256, 0, stream>>>(a, rows_a, which, n_which, limit, b, rows_b, qb, width, scale, norm_bound,
+                                                     counts, list_d, list_i);
   exhaustive_select_kernel<<<unsigned((n_which + 127) / 128), 128, 0, stream>>>(n_which, counts, list_d, list_i, cand16);
   SF_CUDA(cudaGetLastError());
   cudaFreeAsync(counts, stream);

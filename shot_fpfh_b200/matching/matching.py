@@ -95,20 +95,20 @@ def exact_nearest(a_dev, rows_a, b_dev, rows_b, scale: float, k: int = DEFAULT_S
     if int(which.shape[0]):
         LAST_STATS["fallback_rows"] += int(which.shape[0])
         # (within the current SECOND distance: the redo then returns both neighbours exactly)
-        # |a| + |b| over the rows, from the float16 operands' norms (a margin for their rounding and underflow)
-        norm_bound = (1.01 * (float(a_sqnorm.max().sqrt().item()) + b_norm_max) + float(np.sqrt(width)) * 2.0**-23) / scale
-        nn[which], d1[which], d2[which] = exhaustive_redo(a_dev, rows_a, which, b_dev, rows_b, d2[which], norm_bound)
+        # |a| + |b| over the SCALED rows, from the float16 operands' norms (a margin for their rounding and underflow)
+        norm_bound = 1.01 * (float(a_sqnorm.max().sqrt().item()) + b_norm_max) + float(np.sqrt(width)) * 2.0**-23
+        nn[which], d1[which], d2[which] = exhaustive_redo(a_dev, rows_a, which, b_dev, rows_b, d2[which], scale, norm_bound)
     return nn, d1, d2, packed_b
 
 
-def exhaustive_redo(a_dev, rows_a, which, b_dev, rows_b, limit, norm_bound: float):
+def exhaustive_redo(a_dev, rows_a, which, b_dev, rows_b, limit, scale: float, norm_bound: float):
     """Exact (nn, d1, d2) of the flagged queries `which`: one pass over all the targets lists every target within `limit`
-    (the exact distance the re-rank found: an upper bound on the true one) — in float32 with a proven slack, `norm_bound`
-    bounding |a| + |b| —, the float64 re-rank decides among the listed; the rare query with more than 16 of them gets a
+    (the exact distance the re-rank found: an upper bound on the true one) — in float32 on the rows times `scale`, with a
+    proven slack, `norm_bound` bounding |a| + |b| of the scaled rows —, the float64 re-rank decides among the listed; the rare query with more than 16 of them gets a
     full float64 scan of its own."""
     finite = torch.isfinite(limit)
     limit = torch.where(finite, limit, torch.full_like(limit, 1e300))  # (fewer than two candidates so far: everything)
-    cand16 = ops.match_exhaustive(a_dev, rows_a, which, limit, b_dev, rows_b, norm_bound)
+    cand16 = ops.match_exhaustive(a_dev, rows_a, which, limit, b_dev, rows_b, scale, norm_bound)
     crowded = torch.nonzero(cand16[:, 0] == -2).squeeze(1)
     if int(crowded.shape[0]):
         full = torch.full((int(rows_a.shape[0]), 16), -1, dtype=torch.int32, device=a_dev.device)

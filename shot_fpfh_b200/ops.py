@@ -395,14 +395,15 @@ def match_certify(score, a_sqnorm, d1, d2, scale: float, b_norm_max: float, widt
     return flags
 
 
-def match_exhaustive(a_desc, rows_a, which, limit, b_desc, rows_b, norm_bound: float) -> torch.Tensor:
+def match_exhaustive(a_desc, rows_a, which, limit, b_desc, rows_b, scale: float, norm_bound: float) -> torch.Tensor:
     """(n_which, 16) int32 lists of the flagged queries `which`: every target within `limit` (float64 per flagged query;
-    found in float32 with a proven slack: `norm_bound` >= |a| + |b| over the rows); row[0] == -2 where more than 16
+    found in float32 on the rows times `scale` with a proven slack: `norm_bound` >= |a| + |b| over the scaled rows);
+    row[0] == -2 where more than 16
     targets qualified (see sf_match_exhaustive)."""
     n = int(which.shape[0])
     cand = torch.empty((n, 16), dtype=torch.int32, device=a_desc.device)
     check(lib.sf_match_exhaustive(ptr(a_desc), ptr(rows_a), ptr(which.contiguous()), n, ptr(limit.contiguous()), ptr(b_desc),
-                                  ptr(rows_b), int(rows_b.shape[0]), int(a_desc.shape[1]), float(norm_bound), ptr(cand),
+                                  ptr(rows_b), int(rows_b.shape[0]), int(a_desc.shape[1]), float(scale), float(norm_bound), ptr(cand),
                                   stream_ptr()))
     return cand
 

@@ -313,6 +313,13 @@ def test_certificate_catches_adversarial_near_ties_and_quantised_rows():
     assert np.array_equal(m[1], cdist(a, b_big).argmin(axis=1))
     assert mm.LAST_STATS["fallback_rows"] > 0
     print("quantised:", mm.LAST_STATS)
+    # the redo finds its candidates in float32 on rows brought below 1 by the operands' scale: the caller's units do not
+    # matter (1e25 squared would overflow float32, 1e-25 squared underflow it)
+    for units in (1e25, 1e-25):
+        fwd, _ = mm._match(a_adv * units, b_adv * units, want_second=True)
+        du = np.sort(cdist(a_adv * units, b_adv * units), axis=1)
+        assert np.array_equal(fwd.rows_b[fwd.nn], want) and mm.LAST_STATS["fallback_rows"] >= 1
+        assert np.array_equal(fwd.d1, du[:, 0]) and np.array_equal(fwd.d2, du[:, 1])
     # plain data: nothing falls back
     mm.basic_matching(a, b)
     assert mm.LAST_STATS["fallback_rows"] == 0
