@@ -122,9 +122,10 @@ def result_buffer(shape) -> tuple[np.ndarray, np.ndarray]:
     if entry is None:
         entry = [np.empty(count, dtype=np.float64), False]
         if entry[0].nbytes >= _HUGE_PAGE_HINT_BYTES:
-            # first touch of a LARGE fresh buffer (1M keypoints: 2.8 GB = 700 000 page faults): ask for 2 MB pages.
-            # Measured through the reference's pipeline on the 10M-point pair, alternating runs on one box: descriptor
-            # stage 0.75-0.88 s with the hint, 1.2-3.3 s without; at 288 MB (C2) it makes no difference.
+            # first touch of a LARGE fresh buffer (1M keypoints: 2.8 GB = 700 000 page faults, taken by eight writer
+            # threads at once): ask for 2 MB pages. Measured through the reference's pipeline on the 10M-point pair,
+            # alternating runs on three boxes (THP "madvise"): descriptor stage 0.71-0.88 s with the hint, every time;
+            # without it 0.61 s on a good run but 1.2-3.3 s on every second one. At 288 MB (C2) it makes no difference.
             lib.sf_host_advise_huge(entry[0].ctypes.data, entry[0].nbytes)
     _RESULT_POOL.append(entry)
     held = sum(e[0].nbytes for e in _RESULT_POOL)
