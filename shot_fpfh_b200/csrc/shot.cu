@@ -1291,7 +1291,6 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   // [0] neighbour pairs found, [1] cursor of the padded list — of this call's set of counters
   unsigned long long* pair_counter = g->shot_pairs + 2 * g->shot_call_parity;
   unsigned long long* next_counters = g->shot_pairs + 2 * (g->shot_call_parity ^ 1);
-  g->shot_call_parity ^= 1;
   int32_t* worklist = g->shot_worklist;  // [0] = number of queries handed to the exact kernel, then their indices
   const GridView view = g->view();
   // The padded list holds one 16-byte entry per CANDIDATE; its size is read back (the one synchronisation of the
@@ -1306,6 +1305,8 @@ extern "C" int sf_shot_single_scale(sf_grid* g, const double* queries, int64_t n
   candidate_count_kernel<<<unsigned((nq + 255) / 256), 256, 0, stream>>>(
       view, queries, nq, radius * radius, cand_offsets, g->shot_runs, pair_counter + 1,
       assume_size ? g->shot_nbr_capacity : INT64_MAX, assume_size ? g->status_dev : nullptr, next_counters, worklist);
+  SF_CUDA(cudaGetLastError());
+  g->shot_call_parity ^= 1;  // (only once the kernel that resets the other set is in the stream)
   if (!assume_size) {
     int64_t total = 0;
     SF_CUDA(cudaMemcpyAsync(&total, pair_counter + 1, 8, cudaMemcpyDeviceToHost, stream));
