@@ -42,13 +42,21 @@ constexpr int kBN = 256;        // target rows per accumulator tile (= TMEM colu
 constexpr int kBK = 64;         // halves per K block: 128 bytes = one swizzle-128B row
 constexpr int kStages = 3;      // B pipeline depth
 constexpr int kMaxKBlocks = 6;  // K <= 384 (SHOT: 352 padded to 384)
-constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
+// (4 parts = 16 epilogue warps were measured: 22.5 ms against 21.6 ms with 8 at 200k x 200k — 96 registers per thread
+// and twice the partial lists cost more than the extra warps hide)
+#ifndef SF_TC_EPI_PARTS
+#define SF_TC_EPI_PARTS 2
+#endif
+constexpr int kEpiParts = SF_TC_EPI_PARTS;       // column parts of an accumulator tile, one epilogue warp per (lane quarter, part)
+constexpr int kEpiCols = kBN / kEpiParts;        // columns per epilogue warp: 128 or 64
+constexpr int kEpiChunks = kEpiCols / 32;        // TMEM loads of 32 columns per warp and tile
+constexpr int kThreads = (4 + 4 * kEpiParts) * 32;  // 4 control warps + 8 or 16 epilogue warps
 constexpr uint32_t kABlockBytes = kBM * kBK * 2;  // 16 KB
 constexpr uint32_t kBStageBytes = kBN * kBK * 2;  // 32 KB
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemB = kMaxKBlocks * kABlockBytes;            // 96 KB
 constexpr uint32_t kSmemBar = kSmemB + kStages * kBStageBytes;     // 192 KB
-constexpr uint32_t kSmemBnorm = 8 * 2 * 32 * 16;                   // per epilogue warp: 2 buffers of 128 floats
+constexpr uint32_t kSmemBnorm = 4 * kEpiParts * 2 * (kEpiCols / 4) * 16;  // per epilogue warp: 2 buffers of kEpiCols floats
 constexpr uint32_t kSmemBytes = kSmemBar + 256 + kSmemBnorm + 1024;  // barriers + |b|^2 staging + alignment slack
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1 && lane == 0) {
     mbar_init(bar_a_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_t_full(a), 1); mbar_init(bar_t_empty(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_t_full(a), 1); mbar_init(bar_t_empty(a), 4 * kEpiParts * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns (two 128 x 256 float32 accumulators)
@@ -258,12 +266,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     //     so the inner loop reads it with broadcast LDS instead of waiting on L2;
     //   - the TMEM load of chunk c+1 is in flight while chunk c is processed.
     const int quarter = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;  // (the column part of this warp: 0 .. kEpiParts - 1)
     const int row = m0 + quarter * 32 + lane;
-    float4* bn_buf = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256) + (warp - 4) * 64;
+    constexpr int kBnVec = kEpiCols / 4;  // float4 per buffer
+    float4* bn_buf = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256) + (warp - 4) * 2 * kBnVec;
     const bool bn_aligned = (reinterpret_cast<uintptr_t>(bnorm) & 15) == 0;
-    auto load_bn = [&](int tile) -> float4 {  // |b|^2 of columns 4*lane .. +3 of this warp's half; +inf past the end
-      const int64_t col = int64_t(tile) * kBN + half * 128 + 4 * lane;
+    auto load_bn = [&](int tile) -> float4 {  // |b|^2 of columns 4*lane .. +3 of this warp's part; +inf past the end
+      if (lane >= kBnVec) return make_float4(0, 0, 0, 0);
+      const int64_t col = int64_t(tile) * kBN + half * kEpiCols + 4 * lane;
       if (bn_aligned && col + 4 <= qb) return __ldg(reinterpret_cast<const float4*>(bnorm + col));
       float4 r;
       r.x = col + 0 < qb ? __ldg(bnorm + col + 0) : INFINITY;
@@ -278,15 +288,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     float4 bn_next = my_tiles > 0 ? load_bn(tile_begin) : make_float4(0, 0, 0, 0);
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      const int n0 = (tile_begin + t) * kBN + half * 128;
-      float4* bn = bn_buf + acc * 32;
-      bn[lane] = bn_next;
+      const int n0 = (tile_begin + t) * kBN + half * kEpiCols;
+      float4* bn = bn_buf + acc * kBnVec;
+      if (lane < kBnVec) bn[lane] = bn_next;
       __syncwarp();
       if (t + 1 < my_tiles) bn_next = load_bn(tile_begin + t + 1);
       mbar_wait(bar_t_full(acc), (t >> 1) & 1);
       tcgen05_fence_after();
       if (debug & 2) { mbar_arrive(bar_t_empty(acc)); continue; }
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kBN + half * 128);
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kBN + half * kEpiCols);
       uint32_t va[32], vb[32];
       tmem_ld32_issue(taddr, va);
       // Pass 1, branch-free and fully unrolled: the minimum score of each group of 8 columns against the row's
@@ -295,10 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       // every insertion missed the instruction cache, ~4 k cycles each: 74 ms instead of 20 ms at 200k x 200k.)
       uint32_t flags = 0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kEpiChunks; ++c) {
         tmem_ld_wait();
         uint32_t(&v)[32] = (c & 1) ? vb : va;
-        if (c + 1 < 4) tmem_ld32_issue(taddr + 32 * (c + 1), (c & 1) ? va : vb);
+        if (c + 1 < kEpiChunks) tmem_ld32_issue(taddr + 32 * (c + 1), (c & 1) ? va : vb);
         if (debug & 8) continue;
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
     if (row < qa) {
-      const int64_t o = ((int64_t(blockIdx.y) * 2 + half) * qa + row) * K;
+      const int64_t o = ((int64_t(blockIdx.y) * kEpiParts + half) * qa + row) * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) { score[o + k] = top.s[k]; idx[o + k] = top.i[k]; }
     }
@@ -420,8 +430,8 @@ int launch_topk_tc(const __half* a, int64_t qa, const __half* b, const float* bn
   if (m_tiles < 2 * 148) splits = std::min(n_tiles, std::max(1, (2 * 148 + m_tiles - 1) / m_tiles));
   const int tiles_per_split = (n_tiles + splits - 1) / splits;
   splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-  // every CTA emits two partial shortlists per row (one per column half of its tiles): parts = 2 * splits
-  const int parts = 2 * splits;
+  // every CTA emits kEpiParts partial shortlists per row (one per column part of its tiles)
+  const int parts = kEpiParts * splits;
   float* part_score = nullptr;
   int32_t* part_idx = nullptr;
   SF_CUDA(scratch_alloc(reinterpret_cast<void**>(&part_score), size_t(parts) * qa * k * sizeof(float), stream));
